@@ -1,0 +1,148 @@
+/*
+ * la_cabi.h -- C ABI of the B200-native dense hot path behind rust-la's public API.
+ *
+ * The reference (xasmx/rust-la, crate `la`) has NO FFI/plugin interface: its boundary is the Rust API
+ * (`Matrix<T>`, operator `*`, `LUDecomposition<T>`).  This header is the seam a maintainer binds from a new
+ * `src/ffi.rs`: every entry point below names the reference item it replaces
+ * (file:line relative to the reference repository root).
+ *
+ * Conventions
+ *   - all matrices are dense ROW-MAJOR with tight leading dimension unless an explicit `ld*` is given
+ *     (reference layout: data[r * cols + c], src/matrix/mod.rs:26-30, :557-560);
+ *   - every function returns an `int` status, LA_OK == 0.  Shape/contract violations are the CALLER's job
+ *     (the Rust side keeps the reference's `assert!`s so the panic happens before any FFI call); the library
+ *     still validates and returns LA_ERR_INVALID instead of computing garbage;
+ *   - numerical singularity is NOT an error: `la_lu_is_nonsingular_*` reports it and the Rust side maps it to
+ *     `Option::None` exactly like src/decomp/lu.rs:241-243;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with LA_ERR_NO_DEVICE;
+ *   - thread safety: all entry points may be called concurrently from many host threads (Matrix<T> is
+ *     Send + Sync in the reference).  `la_last_error` is thread-local.  `*_host` entry points run on a
+ *     per-host-thread CUDA stream; `*_dev` entry points run on the stream the caller passes.
+ *   - `piv` has the reference's semantics (src/decomp/lu.rs:108-111,147-149): piv[i] = index of the ORIGINAL
+ *     row that ends up in row i, i.e. A(piv,:) = L*U.  Rust `usize` == uint64_t on the supported target.
+ */
+#ifndef LA_CABI_H
+#define LA_CABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LA_API __attribute__((visibility("default")))
+#else
+#define LA_API
+#endif
+
+enum {
+  LA_OK = 0,
+  LA_ERR_INVALID = 1,   /* bad argument: null pointer, zero dimension, size overflow, misaligned pointer        */
+  LA_ERR_CUDA = 2,      /* a CUDA runtime/driver call failed; la_last_error() has the text                      */
+  LA_ERR_NOMEM = 3,     /* device or pinned-host allocation failed                                              */
+  LA_ERR_NO_DEVICE = 4, /* no usable sm_100 device (the library never falls back to the CPU)                    */
+  LA_ERR_UNSUPPORTED = 5
+};
+
+/* Epilogue of the device GEMM: what is done with the product P = A*B. */
+enum {
+  LA_GEMM_ASSIGN = 0, /* C  = P   (operator Mul / mmul)                                   */
+  LA_GEMM_SUB = 1,    /* C -= P   (LU trailing update, src/decomp/lu.rs:122-129, i > j)   */
+  LA_GEMM_ADD = 2     /* C += P   (K-panel pipelined multi-GPU Mul)                       */
+};
+
+typedef struct la_buf la_buf; /* opaque device buffer handle */
+
+/* ---- library / device ---------------------------------------------------------------------------- */
+LA_API int la_version(void);                      /* 100 * major + minor */
+LA_API const char* la_last_error(void);           /* thread-local, never NULL */
+LA_API int la_device_count(int* out);             /* number of visible CUDA devices */
+LA_API int la_device_sm_count(int device, int* out);
+LA_API int la_sync(int device);                   /* waits for all work this library queued on `device` */
+
+/* ---- buffers: replace `alloc_dirty_vec` (src/internalutil.rs:7-13) and the `Vec<T>` backing of
+ *      `Matrix<T>` (src/matrix/mod.rs:26-30).  Contents of a fresh buffer are unspecified ("dirty"). ---- */
+LA_API int la_buf_alloc(size_t bytes, int device, la_buf** out);
+LA_API int la_buf_free(la_buf* buf);
+LA_API int la_buf_upload(la_buf* dst, size_t dst_offset_bytes, const void* host, size_t bytes);
+LA_API int la_buf_download(const la_buf* src, size_t src_offset_bytes, void* host, size_t bytes);
+LA_API int la_buf_copy(la_buf* dst, const la_buf* src, size_t bytes); /* `ludata = a.get_data().clone()`, lu.rs:105 */
+LA_API void* la_buf_device_ptr(const la_buf* buf);
+LA_API size_t la_buf_bytes(const la_buf* buf);
+LA_API int la_buf_device(const la_buf* buf);
+/* pinned host memory for the host mirror of a device-backed Matrix (fast H2D/D2H) */
+LA_API int la_host_alloc(size_t bytes, void** out);
+LA_API int la_host_free(void* ptr);
+
+/* ---- GEMM: replaces `impl Mul<&Matrix<T>> for &Matrix<T>` (src/matrix/mod.rs:957-980, loop nest :965-973)
+ *      and `Matrix::mmul` (src/matrix/mmatrix.rs:82-98).  C[m x n] = A[m x k] * B[k x n]. ---- */
+LA_API int la_gemm_f64(const la_buf* A, const la_buf* B, la_buf* C, size_t m, size_t k, size_t n);
+LA_API int la_gemm_f32(const la_buf* A, const la_buf* B, la_buf* C, size_t m, size_t k, size_t n);
+/* host-pointer form (what `&a * &b` on host-resident matrices binds): H2D, kernel, D2H, synchronous */
+LA_API int la_gemm_f64_host(const double* A, const double* B, double* C, size_t m, size_t k, size_t n);
+LA_API int la_gemm_f32_host(const float* A, const float* B, float* C, size_t m, size_t k, size_t n);
+/* integer instance: the reference's Mul is generic over T and is unit-tested on integer matrices
+ * (src/matrix/mod.rs:1479-1484, src/matrix/mmatrix.rs:234-241).  Exact, two's-complement wrapping. */
+LA_API int la_gemm_i64_host(const int64_t* A, const int64_t* B, int64_t* C, size_t m, size_t k, size_t n);
+/* raw device pointers, explicit leading dimensions (in elements), epilogue mode, caller's stream
+ * (`cuda_stream` is a cudaStream_t; NULL = the per-thread default stream).  Asynchronous. */
+LA_API int la_gemm_f64_dev(const double* A, size_t lda, const double* B, size_t ldb, double* C, size_t ldc,
+                           size_t m, size_t k, size_t n, int mode, void* cuda_stream);
+LA_API int la_gemm_f32_dev(const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc,
+                           size_t m, size_t k, size_t n, int mode, void* cuda_stream);
+
+/* ---- LU: replaces `LUDecomposition::new` (src/decomp/lu.rs:104-168).  Factorises IN PLACE the m x n
+ *      row-major matrix in `LU` (the caller clones A first, lu.rs:105).  Outputs: packed L\U, the permutation
+ *      vector `piv_out[m]` and `*pospivsign_out` (1 = even number of swaps, lu.rs:113,151).
+ *      Pivot rule: largest |x| at or below the diagonal, lowest row index wins ties, NaN never displaces the
+ *      incumbent (lu.rs:132-137); a zero pivot skips the division and the factorisation continues (:156-160). */
+LA_API int la_lu_factor_f64(la_buf* LU, size_t m, size_t n, uint64_t* piv_out, int* pospivsign_out);
+LA_API int la_lu_factor_f32(la_buf* LU, size_t m, size_t n, uint64_t* piv_out, int* pospivsign_out);
+LA_API int la_lu_factor_f64_host(const double* A, double* LU_out, size_t m, size_t n, uint64_t* piv_out,
+                                 int* pospivsign_out);
+LA_API int la_lu_factor_f32_host(const float* A, float* LU_out, size_t m, size_t n, uint64_t* piv_out,
+                                 int* pospivsign_out);
+/* device-pointer form: `piv_dev` is uint64_t[m] and `sign_dev` is int[1] in DEVICE memory.  Asynchronous. */
+LA_API int la_lu_factor_f64_dev(double* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, void* cuda_stream);
+LA_API int la_lu_factor_f32_dev(float* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, void* cuda_stream);
+
+/* `is_non_singular` (src/decomp/lu.rs:174-182): *out = 0 iff some LU[j*n+j] == 0 exactly, j < n. */
+LA_API int la_lu_is_nonsingular_f64(const la_buf* LU, size_t n, int* out);
+LA_API int la_lu_is_nonsingular_f32(const la_buf* LU, size_t n, int* out);
+/* `det` (src/decomp/lu.rs:224-232): (+1|-1) * LU[0][0] * LU[1][1] * ... multiplied in index order. */
+LA_API int la_lu_det_f64(const la_buf* LU, size_t n, int pospivsign, double* out);
+LA_API int la_lu_det_f32(const la_buf* LU, size_t n, int pospivsign, float* out);
+/* `solve` (src/decomp/lu.rs:237-278) for an n x n factorisation: X[n x nx] = A^-1 * B[n x nx].  `piv` is a HOST
+ * array of n entries.  The caller has already checked non-singularity (lu.rs:241-243 -> None). */
+LA_API int la_lu_solve_f64(const la_buf* LU, size_t m, size_t n, const uint64_t* piv, const la_buf* B, size_t nx,
+                           la_buf* X);
+LA_API int la_lu_solve_f32(const la_buf* LU, size_t m, size_t n, const uint64_t* piv, const la_buf* B, size_t nx,
+                           la_buf* X);
+LA_API int la_lu_solve_f64_host(const double* LU, size_t m, size_t n, const uint64_t* piv, const double* B, size_t nx,
+                                double* X);
+LA_API int la_lu_solve_f32_host(const float* LU, size_t m, size_t n, const uint64_t* piv, const float* B, size_t nx,
+                                float* X);
+LA_API int la_lu_solve_f64_dev(const double* LU, size_t n, const uint64_t* piv_dev, const double* B, size_t nx,
+                               double* X, void* cuda_stream);
+LA_API int la_lu_solve_f32_dev(const float* LU, size_t n, const uint64_t* piv_dev, const float* B, size_t nx,
+                               float* X, void* cuda_stream);
+
+/* ---- aux ------------------------------------------------------------------------------------------ */
+/* `Matrix::id` (src/matrix/mod.rs:416-426), the RHS of `inverse` (mod.rs:1034-1037) */
+LA_API int la_identity_f64(la_buf* dst, size_t n);
+LA_API int la_identity_f32(la_buf* dst, size_t n);
+/* Counter-based synthetic inputs, uniform [0,1) like `Matrix::random` (src/matrix/mod.rs:842-851):
+ * element i of dst gets hash(seed, first_idx + i).  Device pointers; asynchronous on `cuda_stream`. */
+LA_API int la_fill_hash_f64_dev(double* dst, size_t count, uint64_t seed, uint64_t first_idx, void* cuda_stream);
+LA_API int la_fill_hash_f32_dev(float* dst, size_t count, uint64_t seed, uint64_t first_idx, void* cuda_stream);
+
+/* Test hook (not part of the drop-in surface): 0 = automatic kernel choice, 1 = force the generic CUDA-core GEMM,
+ * 2 = force the TMA/DMMA GEMM (fails with LA_ERR_INVALID when the operands are not TMA-addressable). */
+LA_API int la_debug_set_gemm_path(int path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LA_CABI_H */

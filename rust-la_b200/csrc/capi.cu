@@ -1,0 +1,437 @@
+// capi.cu -- the extern "C" surface declared in include/la_cabi.h.  Thin glue: argument validation, device selection,
+// host<->device staging for the *_host forms.  All arithmetic lives in the kernels (gemm_*.cu, lu*.cu).
+#include <string.h>
+
+#include "la_common.cuh"
+
+using namespace la;
+
+struct la_buf {
+  void* ptr;
+  size_t bytes;
+  int device;
+};
+
+namespace la {
+void debug_set_gemm_path(int p);
+}
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool active = false;
+  int enter(int device) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(LA_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                  cudaGetErrorString(e));
+    }
+    if (prev != device) {
+      LA_CUDA_TRY(cudaSetDevice(device));
+      active = true;
+    }
+    return LA_OK;
+  }
+  ~DeviceGuard() {
+    if (active) cudaSetDevice(prev);
+  }
+};
+
+bool mul_overflows(size_t a, size_t b, size_t elem, size_t* out) {
+  if (a != 0 && b > SIZE_MAX / a) return true;
+  size_t ab = a * b;
+  if (elem != 0 && ab > SIZE_MAX / elem) return true;
+  *out = ab * elem;
+  return false;
+}
+
+template <typename T>
+int gemm_bufs(const la_buf* A, const la_buf* B, la_buf* C, size_t m, size_t k, size_t n) {
+  LA_REQUIRE(A && B && C, "la_gemm: null buffer handle");
+  LA_REQUIRE(m > 0 && k > 0 && n > 0, "la_gemm: zero dimension (m=%zu k=%zu n=%zu)", m, k, n);
+  size_t ba, bb, bc;
+  LA_REQUIRE(!mul_overflows(m, k, sizeof(T), &ba) && !mul_overflows(k, n, sizeof(T), &bb) &&
+                 !mul_overflows(m, n, sizeof(T), &bc),
+             "la_gemm: size overflow");
+  LA_REQUIRE(A->bytes >= ba && B->bytes >= bb && C->bytes >= bc, "la_gemm: buffer smaller than the matrix it must hold");
+  LA_REQUIRE(A->device == B->device && A->device == C->device, "la_gemm: buffers live on different devices");
+  LA_REQUIRE(C->ptr != A->ptr && C->ptr != B->ptr, "la_gemm: output aliases an input");
+  DeviceGuard g;
+  LA_TRY(g.enter(A->device));
+  return gemm_dev<T>((const T*)A->ptr, k, (const T*)B->ptr, n, (T*)C->ptr, n, m, k, n, LA_GEMM_ASSIGN,
+                     cudaStreamPerThread);
+}
+
+// Host-pointer Mul: H2D, kernel, D2H on the calling thread's stream.  A is uploaded and multiplied in row blocks so
+// that the copy of block i+1 and the download of block i-1 overlap the kernel of block i (B is needed by every block
+// and goes first).
+template <typename T>
+int gemm_host(const T* A, const T* B, T* C, size_t m, size_t k, size_t n) {
+  LA_REQUIRE(A && B && C, "la_gemm_host: null pointer");
+  LA_REQUIRE(m > 0 && k > 0 && n > 0, "la_gemm_host: zero dimension (m=%zu k=%zu n=%zu)", m, k, n);
+  size_t ba, bb, bc;
+  LA_REQUIRE(!mul_overflows(m, k, sizeof(T), &ba) && !mul_overflows(k, n, sizeof(T), &bb) &&
+                 !mul_overflows(m, n, sizeof(T), &bc),
+             "la_gemm_host: size overflow");
+  const DeviceCtx* ctx;
+  LA_TRY(current_device_ctx(&ctx));
+  void *dA, *dB, *dC;
+  LA_TRY(scratch_get(ctx->device, 0, ba, &dA));
+  LA_TRY(scratch_get(ctx->device, 1, bb, &dB));
+  LA_TRY(scratch_get(ctx->device, 2, bc, &dC));
+  cudaStream_t st = cudaStreamPerThread;
+
+  // small problems: one shot
+  const size_t flops2 = m * n;  // proxy; block pipelining only pays for big outputs
+  size_t blocks = 1;
+  if (flops2 >= (size_t)4096 * 4096 && m >= 1024) blocks = 8;
+  if (blocks == 1) {
+    LA_CUDA_TRY(cudaMemcpyAsync(dB, B, bb, cudaMemcpyHostToDevice, st));
+    LA_CUDA_TRY(cudaMemcpyAsync(dA, A, ba, cudaMemcpyHostToDevice, st));
+    LA_TRY(gemm_dev<T>((const T*)dA, k, (const T*)dB, n, (T*)dC, n, m, k, n, LA_GEMM_ASSIGN, st));
+    LA_CUDA_TRY(cudaMemcpyAsync(C, dC, bc, cudaMemcpyDeviceToHost, st));
+    LA_CUDA_TRY(cudaStreamSynchronize(st));
+    return LA_OK;
+  }
+  // pipelined: copy stream(s) + compute stream, events between them
+  static thread_local cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  static thread_local cudaEvent_t ev_up[16], ev_done[16];
+  static thread_local bool ev_init = false;
+  if (!s_h2d) {
+    LA_CUDA_TRY(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
+    LA_CUDA_TRY(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
+  }
+  if (!ev_init) {
+    for (int i = 0; i < 16; ++i) {
+      LA_CUDA_TRY(cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming));
+      LA_CUDA_TRY(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+    }
+    ev_init = true;
+  }
+  // rows per block: multiple of 128 (the GEMM tile)
+  size_t rows_blk = ((m + blocks - 1) / blocks + 127) / 128 * 128;
+  blocks = (m + rows_blk - 1) / rows_blk;
+  LA_CUDA_TRY(cudaMemcpyAsync(dB, B, bb, cudaMemcpyHostToDevice, s_h2d));
+  for (size_t b = 0; b < blocks; ++b) {
+    const size_t r0 = b * rows_blk;
+    const size_t nr = (m - r0 < rows_blk) ? (m - r0) : rows_blk;
+    LA_CUDA_TRY(cudaMemcpyAsync((T*)dA + r0 * k, A + r0 * k, nr * k * sizeof(T), cudaMemcpyHostToDevice, s_h2d));
+    LA_CUDA_TRY(cudaEventRecord(ev_up[b], s_h2d));
+    LA_CUDA_TRY(cudaStreamWaitEvent(st, ev_up[b], 0));
+    LA_TRY(gemm_dev<T>((const T*)dA + r0 * k, k, (const T*)dB, n, (T*)dC + r0 * n, n, nr, k, n, LA_GEMM_ASSIGN, st));
+    LA_CUDA_TRY(cudaEventRecord(ev_done[b], st));
+    LA_CUDA_TRY(cudaStreamWaitEvent(s_d2h, ev_done[b], 0));
+    LA_CUDA_TRY(cudaMemcpyAsync(C + r0 * n, (T*)dC + r0 * n, nr * n * sizeof(T), cudaMemcpyDeviceToHost, s_d2h));
+  }
+  LA_CUDA_TRY(cudaStreamSynchronize(s_d2h));
+  LA_CUDA_TRY(cudaStreamSynchronize(st));
+  return LA_OK;
+}
+
+template <typename T>
+int lu_factor_buf(la_buf* LU, size_t m, size_t n, uint64_t* piv_out, int* pospivsign_out) {
+  LA_REQUIRE(LU && piv_out && pospivsign_out, "la_lu_factor: null pointer");
+  LA_REQUIRE(m > 0 && n > 0, "la_lu_factor: zero dimension");
+  size_t bytes;
+  LA_REQUIRE(!mul_overflows(m, n, sizeof(T), &bytes) && LU->bytes >= bytes, "la_lu_factor: buffer too small");
+  DeviceGuard g;
+  LA_TRY(g.enter(LU->device));
+  void* meta;
+  LA_TRY(scratch_get(LU->device, 3, sizeof(uint64_t) * m + 64, &meta));
+  uint64_t* piv_dev = (uint64_t*)meta;
+  int* sign_dev = (int*)(piv_dev + m);
+  cudaStream_t st = cudaStreamPerThread;
+  LA_TRY(lu_factor_dev<T>((T*)LU->ptr, m, n, piv_dev, sign_dev, st));
+  LA_CUDA_TRY(cudaMemcpyAsync(piv_out, piv_dev, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, st));
+  LA_CUDA_TRY(cudaMemcpyAsync(pospivsign_out, sign_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LA_CUDA_TRY(cudaStreamSynchronize(st));
+  return LA_OK;
+}
+
+template <typename T>
+int lu_factor_host(const T* A, T* LU_out, size_t m, size_t n, uint64_t* piv_out, int* pospivsign_out) {
+  LA_REQUIRE(A && LU_out && piv_out && pospivsign_out, "la_lu_factor_host: null pointer");
+  LA_REQUIRE(m > 0 && n > 0, "la_lu_factor_host: zero dimension");
+  size_t bytes;
+  LA_REQUIRE(!mul_overflows(m, n, sizeof(T), &bytes), "la_lu_factor_host: size overflow");
+  const DeviceCtx* ctx;
+  LA_TRY(current_device_ctx(&ctx));
+  void *dLU, *meta;
+  LA_TRY(scratch_get(ctx->device, 0, bytes, &dLU));
+  LA_TRY(scratch_get(ctx->device, 3, sizeof(uint64_t) * m + 64, &meta));
+  uint64_t* piv_dev = (uint64_t*)meta;
+  int* sign_dev = (int*)(piv_dev + m);
+  cudaStream_t st = cudaStreamPerThread;
+  LA_CUDA_TRY(cudaMemcpyAsync(dLU, A, bytes, cudaMemcpyHostToDevice, st));  // == ludata = a.get_data().clone()
+  LA_TRY(lu_factor_dev<T>((T*)dLU, m, n, piv_dev, sign_dev, st));
+  LA_CUDA_TRY(cudaMemcpyAsync(LU_out, dLU, bytes, cudaMemcpyDeviceToHost, st));
+  LA_CUDA_TRY(cudaMemcpyAsync(piv_out, piv_dev, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, st));
+  LA_CUDA_TRY(cudaMemcpyAsync(pospivsign_out, sign_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LA_CUDA_TRY(cudaStreamSynchronize(st));
+  return LA_OK;
+}
+
+template <typename T>
+int lu_solve_buf(const la_buf* LU, size_t m, size_t n, const uint64_t* piv, const la_buf* B, size_t nx, la_buf* X) {
+  LA_REQUIRE(LU && piv && B && X, "la_lu_solve: null pointer");
+  LA_REQUIRE(m == n, "la_lu_solve: the factorisation must be square (m=%zu n=%zu); see src/decomp/lu.rs:237-278", m, n);
+  LA_REQUIRE(n > 0 && nx > 0, "la_lu_solve: zero dimension");
+  size_t bl, bx;
+  LA_REQUIRE(!mul_overflows(n, n, sizeof(T), &bl) && !mul_overflows(n, nx, sizeof(T), &bx), "la_lu_solve: size overflow");
+  LA_REQUIRE(LU->bytes >= bl && B->bytes >= bx && X->bytes >= bx, "la_lu_solve: buffer too small");
+  LA_REQUIRE(LU->device == B->device && LU->device == X->device, "la_lu_solve: buffers live on different devices");
+  DeviceGuard g;
+  LA_TRY(g.enter(LU->device));
+  void* meta;
+  LA_TRY(scratch_get(LU->device, 3, sizeof(uint64_t) * n + 64, &meta));
+  cudaStream_t st = cudaStreamPerThread;
+  LA_CUDA_TRY(cudaMemcpyAsync(meta, piv, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, st));
+  LA_TRY(lu_solve_dev<T>((const T*)LU->ptr, n, (const uint64_t*)meta, (const T*)B->ptr, nx, (T*)X->ptr, st));
+  LA_CUDA_TRY(cudaStreamSynchronize(st));
+  return LA_OK;
+}
+
+template <typename T>
+int lu_solve_host(const T* LU, size_t m, size_t n, const uint64_t* piv, const T* B, size_t nx, T* X) {
+  LA_REQUIRE(LU && piv && B && X, "la_lu_solve_host: null pointer");
+  LA_REQUIRE(m == n, "la_lu_solve_host: the factorisation must be square (m=%zu n=%zu)", m, n);
+  LA_REQUIRE(n > 0 && nx > 0, "la_lu_solve_host: zero dimension");
+  size_t bl, bx;
+  LA_REQUIRE(!mul_overflows(n, n, sizeof(T), &bl) && !mul_overflows(n, nx, sizeof(T), &bx),
+             "la_lu_solve_host: size overflow");
+  const DeviceCtx* ctx;
+  LA_TRY(current_device_ctx(&ctx));
+  void *dLU, *dB, *dX, *meta;
+  LA_TRY(scratch_get(ctx->device, 0, bl, &dLU));
+  LA_TRY(scratch_get(ctx->device, 1, bx, &dB));
+  LA_TRY(scratch_get(ctx->device, 2, bx, &dX));
+  LA_TRY(scratch_get(ctx->device, 3, sizeof(uint64_t) * n + 64, &meta));
+  cudaStream_t st = cudaStreamPerThread;
+  LA_CUDA_TRY(cudaMemcpyAsync(dLU, LU, bl, cudaMemcpyHostToDevice, st));
+  LA_CUDA_TRY(cudaMemcpyAsync(dB, B, bx, cudaMemcpyHostToDevice, st));
+  LA_CUDA_TRY(cudaMemcpyAsync(meta, piv, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, st));
+  LA_TRY(lu_solve_dev<T>((const T*)dLU, n, (const uint64_t*)meta, (const T*)dB, nx, (T*)dX, st));
+  LA_CUDA_TRY(cudaMemcpyAsync(X, dX, bx, cudaMemcpyDeviceToHost, st));
+  LA_CUDA_TRY(cudaStreamSynchronize(st));
+  return LA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int la_version(void) { return 1; }
+const char* la_last_error(void) { return la::error_text(); }
+
+int la_device_count(int* out) {
+  LA_REQUIRE(out, "la_device_count: null output");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *out = 0;
+    return fail(LA_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  }
+  *out = n;
+  return LA_OK;
+}
+int la_device_sm_count(int device, int* out) {
+  LA_REQUIRE(out, "la_device_sm_count: null output");
+  const DeviceCtx* ctx;
+  LA_TRY(device_ctx(device, &ctx));
+  *out = ctx->sm_count;
+  return LA_OK;
+}
+int la_sync(int device) {
+  DeviceGuard g;
+  LA_TRY(g.enter(device));
+  LA_CUDA_TRY(cudaDeviceSynchronize());
+  return LA_OK;
+}
+
+int la_buf_alloc(size_t bytes, int device, la_buf** out) {
+  LA_REQUIRE(out, "la_buf_alloc: null output");
+  *out = nullptr;
+  LA_REQUIRE(bytes > 0, "la_buf_alloc: zero bytes");
+  const DeviceCtx* ctx;
+  LA_TRY(device_ctx(device, &ctx));
+  DeviceGuard g;
+  LA_TRY(g.enter(device));
+  void* p = nullptr;
+  LA_CUDA_TRY(cudaMalloc(&p, bytes));
+  la_buf* b = new la_buf{p, bytes, device};
+  *out = b;
+  return LA_OK;
+}
+int la_buf_free(la_buf* buf) {
+  if (!buf) return LA_OK;
+  DeviceGuard g;
+  LA_TRY(g.enter(buf->device));
+  cudaError_t e = cudaFree(buf->ptr);
+  delete buf;
+  if (e != cudaSuccess) return fail(LA_ERR_CUDA, "cudaFree failed: %s", cudaGetErrorString(e));
+  return LA_OK;
+}
+int la_buf_upload(la_buf* dst, size_t off, const void* host, size_t bytes) {
+  LA_REQUIRE(dst && host, "la_buf_upload: null pointer");
+  LA_REQUIRE(off <= dst->bytes && bytes <= dst->bytes - off, "la_buf_upload: range exceeds the buffer");
+  DeviceGuard g;
+  LA_TRY(g.enter(dst->device));
+  LA_CUDA_TRY(cudaMemcpyAsync((char*)dst->ptr + off, host, bytes, cudaMemcpyHostToDevice, cudaStreamPerThread));
+  LA_CUDA_TRY(cudaStreamSynchronize(cudaStreamPerThread));
+  return LA_OK;
+}
+int la_buf_download(const la_buf* src, size_t off, void* host, size_t bytes) {
+  LA_REQUIRE(src && host, "la_buf_download: null pointer");
+  LA_REQUIRE(off <= src->bytes && bytes <= src->bytes - off, "la_buf_download: range exceeds the buffer");
+  DeviceGuard g;
+  LA_TRY(g.enter(src->device));
+  LA_CUDA_TRY(cudaMemcpyAsync(host, (const char*)src->ptr + off, bytes, cudaMemcpyDeviceToHost, cudaStreamPerThread));
+  LA_CUDA_TRY(cudaStreamSynchronize(cudaStreamPerThread));
+  return LA_OK;
+}
+int la_buf_copy(la_buf* dst, const la_buf* src, size_t bytes) {
+  LA_REQUIRE(dst && src, "la_buf_copy: null pointer");
+  LA_REQUIRE(bytes <= dst->bytes && bytes <= src->bytes, "la_buf_copy: range exceeds a buffer");
+  DeviceGuard g;
+  LA_TRY(g.enter(dst->device));
+  LA_CUDA_TRY(cudaMemcpyAsync(dst->ptr, src->ptr, bytes, cudaMemcpyDefault, cudaStreamPerThread));
+  return LA_OK;
+}
+void* la_buf_device_ptr(const la_buf* buf) { return buf ? buf->ptr : nullptr; }
+size_t la_buf_bytes(const la_buf* buf) { return buf ? buf->bytes : 0; }
+int la_buf_device(const la_buf* buf) { return buf ? buf->device : -1; }
+
+int la_host_alloc(size_t bytes, void** out) {
+  LA_REQUIRE(out && bytes > 0, "la_host_alloc: null output or zero bytes");
+  *out = nullptr;
+  const DeviceCtx* ctx;
+  LA_TRY(current_device_ctx(&ctx));
+  LA_CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+  return LA_OK;
+}
+int la_host_free(void* ptr) {
+  if (!ptr) return LA_OK;
+  LA_CUDA_TRY(cudaFreeHost(ptr));
+  return LA_OK;
+}
+
+int la_gemm_f64(const la_buf* A, const la_buf* B, la_buf* C, size_t m, size_t k, size_t n) {
+  return gemm_bufs<double>(A, B, C, m, k, n);
+}
+int la_gemm_f32(const la_buf* A, const la_buf* B, la_buf* C, size_t m, size_t k, size_t n) {
+  return gemm_bufs<float>(A, B, C, m, k, n);
+}
+int la_gemm_f64_host(const double* A, const double* B, double* C, size_t m, size_t k, size_t n) {
+  return gemm_host<double>(A, B, C, m, k, n);
+}
+int la_gemm_f32_host(const float* A, const float* B, float* C, size_t m, size_t k, size_t n) {
+  return gemm_host<float>(A, B, C, m, k, n);
+}
+int la_gemm_i64_host(const int64_t* A, const int64_t* B, int64_t* C, size_t m, size_t k, size_t n) {
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64_t must be long long sized");
+  return gemm_host<long long>((const long long*)A, (const long long*)B, (long long*)C, m, k, n);
+}
+int la_gemm_f64_dev(const double* A, size_t lda, const double* B, size_t ldb, double* C, size_t ldc, size_t m, size_t k,
+                    size_t n, int mode, void* stream) {
+  return gemm_f64_dev(A, lda, B, ldb, C, ldc, m, k, n, mode, resolve_stream(stream));
+}
+int la_gemm_f32_dev(const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, size_t m, size_t k,
+                    size_t n, int mode, void* stream) {
+  return gemm_f32_dev(A, lda, B, ldb, C, ldc, m, k, n, mode, resolve_stream(stream));
+}
+
+int la_lu_factor_f64(la_buf* LU, size_t m, size_t n, uint64_t* piv_out, int* sign_out) {
+  return lu_factor_buf<double>(LU, m, n, piv_out, sign_out);
+}
+int la_lu_factor_f32(la_buf* LU, size_t m, size_t n, uint64_t* piv_out, int* sign_out) {
+  return lu_factor_buf<float>(LU, m, n, piv_out, sign_out);
+}
+int la_lu_factor_f64_host(const double* A, double* LU_out, size_t m, size_t n, uint64_t* piv_out, int* sign_out) {
+  return lu_factor_host<double>(A, LU_out, m, n, piv_out, sign_out);
+}
+int la_lu_factor_f32_host(const float* A, float* LU_out, size_t m, size_t n, uint64_t* piv_out, int* sign_out) {
+  return lu_factor_host<float>(A, LU_out, m, n, piv_out, sign_out);
+}
+int la_lu_factor_f64_dev(double* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, void* stream) {
+  return lu_factor_dev<double>(LU, m, n, piv_dev, sign_dev, resolve_stream(stream));
+}
+int la_lu_factor_f32_dev(float* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, void* stream) {
+  return lu_factor_dev<float>(LU, m, n, piv_dev, sign_dev, resolve_stream(stream));
+}
+
+int la_lu_is_nonsingular_f64(const la_buf* LU, size_t n, int* out) {
+  LA_REQUIRE(LU && out && n > 0 && LU->bytes / sizeof(double) / n >= n, "la_lu_is_nonsingular: bad arguments");
+  DeviceGuard g;
+  LA_TRY(g.enter(LU->device));
+  return lu_is_nonsingular_dev<double>((const double*)LU->ptr, n, out, cudaStreamPerThread);
+}
+int la_lu_is_nonsingular_f32(const la_buf* LU, size_t n, int* out) {
+  LA_REQUIRE(LU && out && n > 0 && LU->bytes / sizeof(float) / n >= n, "la_lu_is_nonsingular: bad arguments");
+  DeviceGuard g;
+  LA_TRY(g.enter(LU->device));
+  return lu_is_nonsingular_dev<float>((const float*)LU->ptr, n, out, cudaStreamPerThread);
+}
+int la_lu_det_f64(const la_buf* LU, size_t n, int pospivsign, double* out) {
+  LA_REQUIRE(LU && out && n > 0 && LU->bytes / sizeof(double) / n >= n, "la_lu_det: bad arguments");
+  DeviceGuard g;
+  LA_TRY(g.enter(LU->device));
+  return lu_det_dev<double>((const double*)LU->ptr, n, pospivsign, out, cudaStreamPerThread);
+}
+int la_lu_det_f32(const la_buf* LU, size_t n, int pospivsign, float* out) {
+  LA_REQUIRE(LU && out && n > 0 && LU->bytes / sizeof(float) / n >= n, "la_lu_det: bad arguments");
+  DeviceGuard g;
+  LA_TRY(g.enter(LU->device));
+  return lu_det_dev<float>((const float*)LU->ptr, n, pospivsign, out, cudaStreamPerThread);
+}
+int la_lu_solve_f64(const la_buf* LU, size_t m, size_t n, const uint64_t* piv, const la_buf* B, size_t nx, la_buf* X) {
+  return lu_solve_buf<double>(LU, m, n, piv, B, nx, X);
+}
+int la_lu_solve_f32(const la_buf* LU, size_t m, size_t n, const uint64_t* piv, const la_buf* B, size_t nx, la_buf* X) {
+  return lu_solve_buf<float>(LU, m, n, piv, B, nx, X);
+}
+int la_lu_solve_f64_host(const double* LU, size_t m, size_t n, const uint64_t* piv, const double* B, size_t nx,
+                         double* X) {
+  return lu_solve_host<double>(LU, m, n, piv, B, nx, X);
+}
+int la_lu_solve_f32_host(const float* LU, size_t m, size_t n, const uint64_t* piv, const float* B, size_t nx, float* X) {
+  return lu_solve_host<float>(LU, m, n, piv, B, nx, X);
+}
+int la_lu_solve_f64_dev(const double* LU, size_t n, const uint64_t* piv_dev, const double* B, size_t nx, double* X,
+                        void* stream) {
+  return lu_solve_dev<double>(LU, n, piv_dev, B, nx, X, resolve_stream(stream));
+}
+int la_lu_solve_f32_dev(const float* LU, size_t n, const uint64_t* piv_dev, const float* B, size_t nx, float* X,
+                        void* stream) {
+  return lu_solve_dev<float>(LU, n, piv_dev, B, nx, X, resolve_stream(stream));
+}
+
+int la_identity_f64(la_buf* dst, size_t n) {
+  LA_REQUIRE(dst && n > 0 && dst->bytes / sizeof(double) / n >= n, "la_identity: bad arguments");
+  DeviceGuard g;
+  LA_TRY(g.enter(dst->device));
+  return identity_dev<double>((double*)dst->ptr, n, cudaStreamPerThread);
+}
+int la_identity_f32(la_buf* dst, size_t n) {
+  LA_REQUIRE(dst && n > 0 && dst->bytes / sizeof(float) / n >= n, "la_identity: bad arguments");
+  DeviceGuard g;
+  LA_TRY(g.enter(dst->device));
+  return identity_dev<float>((float*)dst->ptr, n, cudaStreamPerThread);
+}
+int la_fill_hash_f64_dev(double* dst, size_t count, uint64_t seed, uint64_t first_idx, void* stream) {
+  return fill_hash_dev<double>(dst, count, seed, first_idx, resolve_stream(stream));
+}
+int la_fill_hash_f32_dev(float* dst, size_t count, uint64_t seed, uint64_t first_idx, void* stream) {
+  return fill_hash_dev<float>(dst, count, seed, first_idx, resolve_stream(stream));
+}
+
+/* test hook: 0 = automatic kernel choice, 1 = force the CUDA-core kernel, 2 = force the TMA/DMMA kernel */
+int la_debug_set_gemm_path(int path) {
+  LA_REQUIRE(path >= 0 && path <= 2, "la_debug_set_gemm_path: bad value %d", path);
+  la::debug_set_gemm_path(path);
+  return LA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// la_common.cuh -- shared host/device helpers for the sm_100a hot-path library.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/la_cabi.h"
+
+namespace la {
+
+// ---- error plumbing (thread-local message, int status across the C ABI) ---------------------------
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+const char* error_text();
+
+#define LA_CUDA_TRY(expr)                                                                              \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess) {                                                                           \
+      int _code = (_e == cudaErrorMemoryAllocation) ? LA_ERR_NOMEM                                     \
+                  : (_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver) ? LA_ERR_NO_DEVICE  \
+                                                                                   : LA_ERR_CUDA;      \
+      return ::la::fail(_code, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    }                                                                                                  \
+  } while (0)
+
+#define LA_TRY(expr)                 \
+  do {                               \
+    int _s = (expr);                 \
+    if (_s != LA_OK) return _s;      \
+  } while (0)
+
+#define LA_REQUIRE(cond, ...)                                   \
+  do {                                                          \
+    if (!(cond)) return ::la::fail(LA_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// ---- runtime services (la_runtime.cu) --------------------------------------------------------------
+struct DeviceCtx {
+  int device = -1;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  size_t smem_optin = 0;
+  bool coop = false;
+};
+int device_ctx(int device, const DeviceCtx** out);  // validates sm_100, caches properties
+int current_device_ctx(const DeviceCtx** out);
+cudaStream_t resolve_stream(void* s);               // NULL -> cudaStreamPerThread
+// Grow-only per-(thread,device) scratch used by the *_host entry points and the LU driver.
+int scratch_get(int device, int slot, size_t bytes, void** out);
+
+// cuTensorMapEncodeTiled fetched through the runtime (no link-time libcuda dependency).
+int encode_tensor_map_2d(CUtensorMap* map, CUtensorMapDataType dtype, size_t elem_bytes, const void* base,
+                         uint64_t inner, uint64_t outer, uint64_t row_stride_bytes, uint32_t box_inner,
+                         uint32_t box_outer, CUtensorMapSwizzle swizzle);
+
+// ---- typed internal entry points shared between translation units ------------------------------------
+int gemm_f64_dev(const double* A, size_t lda, const double* B, size_t ldb, double* C, size_t ldc, size_t m, size_t k,
+                 size_t n, int mode, cudaStream_t st);
+int gemm_f32_dev(const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, size_t m, size_t k,
+                 size_t n, int mode, cudaStream_t st);
+template <typename T>
+int gemm_dev(const T* A, size_t lda, const T* B, size_t ldb, T* C, size_t ldc, size_t m, size_t k, size_t n, int mode,
+             cudaStream_t st);
+template <typename T>
+int gemm_simt(const T* A, size_t lda, const T* B, size_t ldb, T* C, size_t ldc, size_t m, size_t k, size_t n, int mode,
+              cudaStream_t st);
+
+template <typename T>
+int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, cudaStream_t st);
+template <typename T>
+int lu_solve_dev(const T* LU, size_t n, const uint64_t* piv_dev, const T* B, size_t nx, T* X, cudaStream_t st);
+template <typename T>
+int lu_is_nonsingular_dev(const T* LU, size_t n, int* out_host, cudaStream_t st);
+template <typename T>
+int lu_det_dev(const T* LU, size_t n, int pospivsign, T* out_host, cudaStream_t st);
+template <typename T>
+int identity_dev(T* dst, size_t n, cudaStream_t st);
+template <typename T>
+int fill_hash_dev(T* dst, size_t count, uint64_t seed, uint64_t first_idx, cudaStream_t st);
+
+#ifdef __CUDACC__
+// ---- device-side PTX wrappers (mbarrier / TMA / DMMA) ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// 2-D tiled TMA load: coordinates are (inner, outer) in elements.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner,
+                                            int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+// D(8x8) += A(8x4, row) * B(4x8, col), fp64.  SASS: DMMA.8x8x4 (the only fp64 MMA shape sm_100a issues).
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// counter-based hash shared by la_fill_hash_* and the oracle
+__host__ __device__ __forceinline__ uint64_t hash64(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed * 0x9E3779B97F4A7C15ull + idx;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+#endif  // __CUDACC__
+
+}  // namespace la

@@ -1,0 +1,297 @@
+"""`la` -- host-side mirror of the rust-la crate API for the dense hot path, backed by libla_b200.so (sm_100a CUDA).
+
+Mirrors (reference, relative to /root/reference):
+  Matrix<T>            src/matrix/mod.rs:26-30     Matrix.new :207-211, rows :256, cols :260, get_data :264, get :557-560,
+                                                   id :416-426, operator * :957-998, det/solve/inverse/is_singular :1025-1047
+  Matrix::mmul         src/matrix/mmatrix.rs:82-98
+  LUDecomposition<T>   src/decomp/lu.rs:95-278     new, is_singular, is_non_singular, get_l, get_u, get_p, get_piv, det, solve
+  m!                   src/macros.rs:39-42         -> m("1, 2; 3, 4") / m([[1, 2], [3, 4]])
+  ApproxEq             src/approxeq.rs:34-47       absolute 1e-6
+
+Error conventions are the reference's: contract violations "panic" (raise `Panic`, an AssertionError), numerical
+singularity is `None`.  There is no CPU fallback: every multiplication / factorisation / solve runs in CUDA through the
+C ABI in include/la_cabi.h, and raises `LaError` when the library or a B200 is not available.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import LaError, lib, check  # noqa: F401
+
+__all__ = ["Matrix", "LUDecomposition", "m", "Panic", "LaError", "APPROX_EPS"]
+
+APPROX_EPS = 1e-6  # src/approxeq.rs:20,36
+
+
+class Panic(AssertionError):
+    """The reference `assert!`s on shape/contract violations; the mirror raises this instead of unwinding."""
+
+
+def _assert(cond, what):
+    if not cond:
+        raise Panic(f"assertion failed: {what}")
+
+
+_SUF = {np.dtype(np.float64): "f64", np.dtype(np.float32): "f32"}
+
+
+def _suffix(dtype):
+    try:
+        return _SUF[np.dtype(dtype)]
+    except KeyError:
+        raise TypeError(f"the CUDA path supports f32/f64 (and i64 for Mul); got {np.dtype(dtype)}") from None
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Matrix:
+    """Row-major dense matrix: `{ no_rows, data }` with element (r, c) at data[r * cols + c]."""
+
+    __slots__ = ("no_rows", "data")
+
+    def __init__(self, no_rows, data):
+        self.no_rows = int(no_rows)
+        self.data = data  # 1-D contiguous numpy array (the `Vec<T>`)
+
+    # ---- constructors ---------------------------------------------------------------------------
+    @staticmethod
+    def new(no_rows, no_cols, data, dtype=None):
+        """Matrix::new, src/matrix/mod.rs:207-211."""
+        arr = np.ascontiguousarray(np.asarray(data, dtype=dtype)).reshape(-1)
+        if arr.dtype not in (np.float64, np.float32, np.int64):
+            arr = arr.astype(np.int64 if np.issubdtype(arr.dtype, np.integer) else np.float64)
+        _assert(no_rows * no_cols == arr.size, "no_rows * no_cols == data.len()")
+        _assert(no_rows > 0 and no_cols > 0, "no_rows > 0 && no_cols > 0")
+        return Matrix(no_rows, arr)
+
+    @staticmethod
+    def id(m, n, dtype=np.float64):
+        """Matrix::id, src/matrix/mod.rs:416-426."""
+        d = np.zeros(m * n, dtype=dtype)
+        d[: min(m, n) * n : n + 1] = 1
+        return Matrix(m, d)
+
+    @staticmethod
+    def from_numpy(a):
+        a = np.asarray(a)
+        _assert(a.ndim == 2, "2-D array")
+        return Matrix.new(a.shape[0], a.shape[1], a)
+
+    # ---- accessors ------------------------------------------------------------------------------
+    def rows(self):
+        return self.no_rows
+
+    def cols(self):
+        return self.data.size // self.no_rows
+
+    def get_data(self):
+        return self.data
+
+    def get(self, row, col):
+        _assert(row < self.no_rows and col < self.cols(), "row < rows && col < cols")
+        return self.data[row * self.cols() + col]
+
+    def to_numpy(self):
+        return self.data.reshape(self.no_rows, self.cols())
+
+    def t(self):
+        return Matrix(self.cols(), np.ascontiguousarray(self.to_numpy().T).reshape(-1))
+
+    def __eq__(self, other):  # #[derive(PartialEq)]
+        return isinstance(other, Matrix) and self.no_rows == other.no_rows and self.data.size == other.data.size and \
+            bool(np.array_equal(self.data, other.data))
+
+    def approx_eq(self, other):
+        """src/matrix/mod.rs:1141-1147 with ApproxEq = absolute 1e-6."""
+        if self.no_rows != other.no_rows or self.data.size != other.data.size:
+            return False
+        return bool(np.all(np.abs(self.data - other.data) < APPROX_EPS))
+
+    def __repr__(self):
+        return f"Matrix({self.no_rows}x{self.cols()}, {self.data.dtype})"
+
+    # ---- Mul: src/matrix/mod.rs:957-998 -----------------------------------------------------------
+    def __mul__(self, other):
+        _assert(isinstance(other, Matrix), "rhs is a Matrix")
+        _assert(self.cols() == other.no_rows, "self.cols() == m.no_rows")
+        _assert(self.data.dtype == other.data.dtype, "same element type")
+        out = np.empty(self.no_rows * other.cols(), dtype=self.data.dtype)  # alloc_dirty_vec
+        self._gemm_into(other, out)
+        return Matrix(self.no_rows, out)
+
+    def mmul(self, other, dst):
+        """Matrix::mmul, src/matrix/mmatrix.rs:82-98: product into the caller's `dst`."""
+        _assert(self.cols() == other.no_rows, "self.cols() == m.no_rows")
+        _assert(dst.rows() == self.no_rows, "dst.rows() == self.no_rows")
+        _assert(dst.cols() == other.cols(), "dst.cols() == m.cols()")
+        _assert(self.data.dtype == other.data.dtype == dst.data.dtype, "same element type")
+        self._gemm_into(other, dst.data)
+        return dst
+
+    def _gemm_into(self, other, out):
+        L = lib()
+        if self.data.dtype == np.int64:
+            fn = L.la_gemm_i64_host
+        else:
+            fn = getattr(L, f"la_gemm_{_suffix(self.data.dtype)}_host")
+        check(fn(_ptr(self.data), _ptr(other.data), _ptr(out), self.no_rows, self.cols(), other.cols()))
+
+    # ---- LU callers: src/matrix/mod.rs:1025-1047 (each call re-factorises, like the reference) -------------------
+    def det(self):
+        _assert(self.cols() == self.no_rows, "self.cols() == self.no_rows")
+        return LUDecomposition.new(self).det()
+
+    def solve(self, b):
+        return LUDecomposition.new(self).solve(b)
+
+    def inverse(self):
+        _assert(self.no_rows == self.cols(), "self.no_rows == self.cols()")
+        return LUDecomposition.new(self).solve(Matrix.id(self.no_rows, self.no_rows, self.data.dtype))
+
+    def is_singular(self):
+        return not self.is_non_singular()
+
+    def is_non_singular(self):
+        _assert(self.no_rows == self.cols(), "self.no_rows == self.cols()")
+        return LUDecomposition.new(self).is_non_singular()
+
+
+class _DeviceBuf:
+    """RAII wrapper over la_buf (the device backing of a Matrix / LUDecomposition)."""
+
+    def __init__(self, nbytes, device=0):
+        self.handle = ctypes.c_void_p()
+        check(lib().la_buf_alloc(nbytes, device, ctypes.byref(self.handle)))
+        self.nbytes = nbytes
+
+    def upload(self, arr):
+        check(lib().la_buf_upload(self.handle, 0, _ptr(arr), arr.nbytes))
+
+    def download(self, arr):
+        check(lib().la_buf_download(self.handle, 0, _ptr(arr), arr.nbytes))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().la_buf_free(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class LUDecomposition:
+    """LUDecomposition<T>, src/decomp/lu.rs:95-101: `{ lu: Matrix<T>, pospivsign: bool, piv: Vec<usize> }`.
+
+    The packed factors stay resident in HBM (la_buf); the host copy is materialised lazily for get_l/get_u/get_lu."""
+
+    def __init__(self, m, n, dtype, buf, piv, pospivsign):
+        self._m, self._n, self._dtype = m, n, np.dtype(dtype)
+        self._buf = buf
+        self.piv = piv
+        self.pospivsign = bool(pospivsign)
+        self._lu_host = None
+
+    @staticmethod
+    def new(a, device=0):
+        """LUDecomposition::new, src/decomp/lu.rs:104-168 (factorises a copy; `a` is untouched)."""
+        m, n = a.rows(), a.cols()
+        suf = _suffix(a.data.dtype)
+        buf = _DeviceBuf(a.data.nbytes, device)
+        buf.upload(a.data)  # ludata = a.get_data().clone()
+        piv = np.empty(m, dtype=np.uint64)
+        sign = ctypes.c_int(1)
+        check(getattr(lib(), f"la_lu_factor_{suf}")(buf.handle, m, n, _ptr(piv), ctypes.byref(sign)))
+        return LUDecomposition(m, n, a.data.dtype, buf, piv, sign.value)
+
+    def get_lu(self):
+        if self._lu_host is None:
+            h = np.empty(self._m * self._n, dtype=self._dtype)
+            self._buf.download(h)
+            self._lu_host = Matrix(self._m, h)
+        return self._lu_host
+
+    def is_singular(self):
+        return not self.is_non_singular()
+
+    def is_non_singular(self):
+        """src/decomp/lu.rs:174-182 (indexes lu[j*n+j] for j < n: the reference panics out of bounds when m < n)."""
+        _assert(self._m >= self._n, "index out of bounds: lu[j*n+j] for m < n")
+        out = ctypes.c_int(0)
+        check(getattr(lib(), f"la_lu_is_nonsingular_{_suffix(self._dtype)}")(self._buf.handle, self._n, ctypes.byref(out)))
+        return bool(out.value)
+
+    def get_l(self):
+        """src/decomp/lu.rs:184-202 (host-side unpack)."""
+        lu = self.get_lu().to_numpy()
+        nn = min(self._m, self._n)
+        l = np.tril(lu[:, :nn], -1)
+        l[np.arange(nn), np.arange(nn)] = 1
+        return Matrix(self._m, np.ascontiguousarray(l).reshape(-1))
+
+    def get_u(self):
+        """src/decomp/lu.rs:204-215."""
+        lu = self.get_lu().to_numpy()
+        mm = min(self._m, self._n)
+        return Matrix(mm, np.ascontiguousarray(np.triu(lu[:mm, :])).reshape(-1))
+
+    def get_p(self):
+        """src/decomp/lu.rs:217-220: id(len, len).permute_rows(piv)."""
+        ln = self.piv.size
+        p = np.zeros((ln, ln), dtype=self._dtype)
+        p[np.arange(ln), self.piv.astype(np.int64)] = 1
+        return Matrix(ln, p.reshape(-1))
+
+    def get_piv(self):
+        return self.piv
+
+    def det(self):
+        """src/decomp/lu.rs:224-232."""
+        _assert(self._m == self._n, "self.lu.rows() == self.lu.cols()")
+        suf = _suffix(self._dtype)
+        out = ctypes.c_double(0) if suf == "f64" else ctypes.c_float(0)
+        check(getattr(lib(), f"la_lu_det_{suf}")(self._buf.handle, self._n, int(self.pospivsign), ctypes.byref(out)))
+        return self._dtype.type(out.value)
+
+    def solve(self, b):
+        """src/decomp/lu.rs:237-278: Some(X) or None when singular."""
+        _assert(b.rows() == self._m, "b.rows() == m")
+        _assert(b.data.dtype == self._dtype, "same element type")
+        if not self.is_non_singular():
+            return None
+        _assert(self._m == self._n, "solve needs a square factorisation (lu.rs:257-275 index with n)")
+        nx = b.cols()
+        suf = _suffix(self._dtype)
+        bbuf = _DeviceBuf(b.data.nbytes, 0)
+        xbuf = _DeviceBuf(b.data.nbytes, 0)
+        bbuf.upload(b.data)
+        check(getattr(lib(), f"la_lu_solve_{suf}")(self._buf.handle, self._m, self._n, _ptr(self.piv), bbuf.handle, nx,
+                                                   xbuf.handle))
+        x = np.empty(self._m * nx, dtype=self._dtype)
+        xbuf.download(x)
+        return Matrix(self._m, x)
+
+
+def m(spec, dtype=None):
+    """The `m!` macro (src/macros.rs:39-42): m("1.0, 2.0; 3.0, 4.0") or m([[1.0, 2.0], [3.0, 4.0]]).
+
+    Like the Rust literal, integer literals give an integer matrix and float literals a float matrix."""
+    if isinstance(spec, str):
+        rows = [r.strip() for r in spec.strip().split(";") if r.strip()]
+        parsed = []
+        is_float = False
+        for r in rows:
+            items = [t.strip() for t in r.split(",") if t.strip()]
+            is_float |= any(("." in t) or ("e" in t.lower()) or ("nan" in t.lower()) or ("inf" in t.lower()) for t in items)
+            parsed.append(items)
+        conv = float if is_float else int
+        spec = [[conv(t) for t in items] for items in parsed]
+    rows = len(spec)
+    cols = len(spec[0])
+    _assert(all(len(r) == cols for r in spec), "all rows have the same number of columns")
+    flat = [v for r in spec for v in r]
+    if dtype is None:
+        dtype = np.int64 if all(isinstance(v, (int, np.integer)) and not isinstance(v, bool) for v in flat) else np.float64
+    return Matrix.new(rows, cols, np.array(flat, dtype=dtype))

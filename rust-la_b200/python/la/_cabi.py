@@ -1,0 +1,100 @@
+"""ctypes binding of include/la_cabi.h (libla_b200.so).  There is NO CPU fallback: if the CUDA library is missing or
+no device is usable, every compute call raises."""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_PKG, "..", "..", "libla_b200.so"))
+
+LA_OK, LA_ERR_INVALID, LA_ERR_CUDA, LA_ERR_NOMEM, LA_ERR_NO_DEVICE, LA_ERR_UNSUPPORTED = range(6)
+LA_GEMM_ASSIGN, LA_GEMM_SUB, LA_GEMM_ADD = 0, 1, 2
+
+
+class LaError(RuntimeError):
+    def __init__(self, status, text):
+        super().__init__(f"la_b200 status {status}: {text}")
+        self.status = status
+
+
+_sz = ctypes.c_size_t
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_u64 = ctypes.c_uint64
+_pp = ctypes.POINTER(ctypes.c_void_p)
+_pi = ctypes.POINTER(ctypes.c_int)
+
+# name -> (argtypes, restype); the C header is the single source of truth, tests/test_cabi_symbols.py cross-checks it
+SIGNATURES = {
+    "la_version": ([], _i),
+    "la_last_error": ([], ctypes.c_char_p),
+    "la_device_count": ([_pi], _i),
+    "la_device_sm_count": ([_i, _pi], _i),
+    "la_sync": ([_i], _i),
+    "la_buf_alloc": ([_sz, _i, _pp], _i),
+    "la_buf_free": ([_p], _i),
+    "la_buf_upload": ([_p, _sz, _p, _sz], _i),
+    "la_buf_download": ([_p, _sz, _p, _sz], _i),
+    "la_buf_copy": ([_p, _p, _sz], _i),
+    "la_buf_device_ptr": ([_p], _p),
+    "la_buf_bytes": ([_p], _sz),
+    "la_buf_device": ([_p], _i),
+    "la_host_alloc": ([_sz, _pp], _i),
+    "la_host_free": ([_p], _i),
+    "la_gemm_f64": ([_p, _p, _p, _sz, _sz, _sz], _i),
+    "la_gemm_f32": ([_p, _p, _p, _sz, _sz, _sz], _i),
+    "la_gemm_f64_host": ([_p, _p, _p, _sz, _sz, _sz], _i),
+    "la_gemm_f32_host": ([_p, _p, _p, _sz, _sz, _sz], _i),
+    "la_gemm_i64_host": ([_p, _p, _p, _sz, _sz, _sz], _i),
+    "la_gemm_f64_dev": ([_p, _sz, _p, _sz, _p, _sz, _sz, _sz, _sz, _i, _p], _i),
+    "la_gemm_f32_dev": ([_p, _sz, _p, _sz, _p, _sz, _sz, _sz, _sz, _i, _p], _i),
+    "la_lu_factor_f64": ([_p, _sz, _sz, _p, _pi], _i),
+    "la_lu_factor_f32": ([_p, _sz, _sz, _p, _pi], _i),
+    "la_lu_factor_f64_host": ([_p, _p, _sz, _sz, _p, _pi], _i),
+    "la_lu_factor_f32_host": ([_p, _p, _sz, _sz, _p, _pi], _i),
+    "la_lu_factor_f64_dev": ([_p, _sz, _sz, _p, _p, _p], _i),
+    "la_lu_factor_f32_dev": ([_p, _sz, _sz, _p, _p, _p], _i),
+    "la_lu_is_nonsingular_f64": ([_p, _sz, _pi], _i),
+    "la_lu_is_nonsingular_f32": ([_p, _sz, _pi], _i),
+    "la_lu_det_f64": ([_p, _sz, _i, ctypes.POINTER(ctypes.c_double)], _i),
+    "la_lu_det_f32": ([_p, _sz, _i, ctypes.POINTER(ctypes.c_float)], _i),
+    "la_lu_solve_f64": ([_p, _sz, _sz, _p, _p, _sz, _p], _i),
+    "la_lu_solve_f32": ([_p, _sz, _sz, _p, _p, _sz, _p], _i),
+    "la_lu_solve_f64_host": ([_p, _sz, _sz, _p, _p, _sz, _p], _i),
+    "la_lu_solve_f32_host": ([_p, _sz, _sz, _p, _p, _sz, _p], _i),
+    "la_lu_solve_f64_dev": ([_p, _sz, _p, _p, _sz, _p, _p], _i),
+    "la_lu_solve_f32_dev": ([_p, _sz, _p, _p, _sz, _p, _p], _i),
+    "la_identity_f64": ([_p, _sz], _i),
+    "la_identity_f32": ([_p, _sz], _i),
+    "la_fill_hash_f64_dev": ([_p, _sz, _u64, _u64, _p], _i),
+    "la_fill_hash_f32_dev": ([_p, _sz, _u64, _u64, _p], _i),
+    "la_debug_set_gemm_path": ([_i], _i),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads libla_b200.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LaError(LA_ERR_NO_DEVICE,
+                          f"{LIB_PATH} is missing: build it with `make -C rust-la_b200` (there is no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (args, res) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = res
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != LA_OK:
+        raise LaError(status, lib().la_last_error().decode("utf-8", "replace"))
+
+
+def device_count():
+    n = _i(0)
+    st = lib().la_device_count(ctypes.byref(n))
+    return n.value if st == LA_OK else 0

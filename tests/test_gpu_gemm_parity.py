@@ -1,0 +1,154 @@
+"""GEMM parity: CUDA path (through the C ABI) vs the oracle on the same seeded inputs.
+Bar (BASELINE.json): max relative element error <= 1e-12 * k for f64, <= 1e-4 * k for f32 (k = inner dimension)."""
+import numpy as np
+import pytest
+
+from gpu_util import DevBuf, fill_hash, gemm_dev, max_rel_err, sync
+from la import _cabi
+from la._cabi import check, lib
+
+pytestmark = pytest.mark.gpu
+
+F64_TOL = 1e-12
+F32_TOL = 1e-4
+
+SHAPES = [(1, 1, 1), (2, 2, 2), (3, 5, 7), (64, 64, 64), (128, 128, 128), (129, 130, 131), (127, 17, 255),
+          (256, 512, 384), (200, 1000, 136), (512, 512, 512), (130, 4, 260), (1000, 2, 1000), (640, 1024, 768)]
+
+
+@pytest.mark.parametrize("path", ["auto", "simt", "tma"])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_gemm_f64_host_api(oracle, shape, path):
+    m, k, n = shape
+    if path == "tma" and (k % 2 or n % 2):
+        pytest.skip("TMA needs 16-byte aligned rows")
+    a = oracle.fill((m, k), 1)
+    b = oracle.fill((k, n), 2)
+    ref = oracle.gemm(a, b)
+    c = np.full((m, n), np.nan)
+    check(lib().la_debug_set_gemm_path({"auto": 0, "simt": 1, "tma": 2}[path]))
+    try:
+        check(lib().la_gemm_f64_host(a.ctypes.data, b.ctypes.data, c.ctypes.data, m, k, n))
+    finally:
+        lib().la_debug_set_gemm_path(0)
+    assert np.all(np.isfinite(c))
+    assert max_rel_err(c, ref) <= F64_TOL * k
+
+
+@pytest.mark.parametrize("shape", [(3, 5, 7), (128, 128, 128), (257, 300, 129), (512, 1024, 256)])
+def test_gemm_f32_host_api(oracle, shape):
+    m, k, n = shape
+    a = oracle.fill((m, k), 1, np.float32)
+    b = oracle.fill((k, n), 2, np.float32)
+    ref = oracle.gemm(a, b)
+    c = np.full((m, n), np.nan, dtype=np.float32)
+    check(lib().la_gemm_f32_host(a.ctypes.data, b.ctypes.data, c.ctypes.data, m, k, n))
+    assert max_rel_err(c, ref) <= F32_TOL * k
+
+
+def test_gemm_signed_inputs_absolute_error(oracle):
+    """Inputs in [-0.5, 0.5): sums cancel, so compare against the norm-wise bound k * eps * |a|.|b| instead."""
+    m, k, n = 192, 777 * 2, 320
+    a = oracle.fill((m, k), 11) - 0.5
+    b = oracle.fill((k, n), 12) - 0.5
+    ref = oracle.gemm(a, b)
+    c = np.empty((m, n))
+    check(lib().la_gemm_f64_host(a.ctypes.data, b.ctypes.data, c.ctypes.data, m, k, n))
+    bound = (np.abs(a) @ np.abs(b)) * (k * 2.3e-16)
+    assert np.all(np.abs(c - ref) <= bound)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("path", ["simt", "tma"])
+def test_gemm_dev_modes_and_leading_dims(oracle, mode, path):
+    """Device-pointer entry with sub-matrix views (ld > width), as the LU trailing update uses it."""
+    ld = 400
+    m, k, n = 150, 96, 170
+    big_a = oracle.fill((300, ld), 21)
+    big_b = oracle.fill((300, ld), 22)
+    big_c = oracle.fill((300, ld), 23)
+    a_off, b_off, c_off = 10 * ld + 4, 20 * ld + 8, 30 * ld + 2
+    a = big_a.ravel()[a_off:].reshape(-1)  # views via offsets
+    A = np.lib.stride_tricks.as_strided(big_a.ravel()[a_off:], (m, k), (ld * 8, 8))
+    B = np.lib.stride_tricks.as_strided(big_b.ravel()[b_off:], (k, n), (ld * 8, 8))
+    C0 = np.lib.stride_tricks.as_strided(big_c.ravel()[c_off:], (m, n), (ld * 8, 8)).copy()
+    prod = oracle.gemm(np.ascontiguousarray(A), np.ascontiguousarray(B))
+    want = {0: prod, 1: C0 - prod, 2: C0 + prod}[mode]
+    da, db, dc = DevBuf.from_array(big_a), DevBuf.from_array(big_b), DevBuf.from_array(big_c)
+    check(lib().la_debug_set_gemm_path({"simt": 1, "tma": 2}[path]))
+    try:
+        gemm_dev(da, ld, db, ld, dc, ld, m, k, n, mode, np.float64, a_off, b_off, c_off)
+        sync()
+    finally:
+        lib().la_debug_set_gemm_path(0)
+    out = dc.to_array((300, ld), np.float64)
+    got = np.lib.stride_tricks.as_strided(out.ravel()[c_off:], (m, n), (ld * 8, 8))
+    scale = np.maximum(np.abs(want), np.abs(prod))
+    assert np.max(np.abs(got - want) / scale) <= F64_TOL * k
+    # nothing outside the C view was touched
+    mask = np.ones((300, ld), dtype=bool)
+    r0, c0 = divmod(c_off, ld)
+    mask[r0:r0 + m, c0:c0 + n] = False
+    assert np.array_equal(out[mask], big_c[mask])
+
+
+def test_gemm_buf_api(oracle):
+    m, k, n = 300, 200, 100
+    a, b = oracle.fill((m, k), 1), oracle.fill((k, n), 2)
+    da, db, dc = DevBuf.from_array(a), DevBuf.from_array(b), DevBuf(m * n * 8)
+    check(lib().la_gemm_f64(da.h, db.h, dc.h, m, k, n))
+    sync()
+    assert max_rel_err(dc.to_array((m, n), np.float64), oracle.gemm(a, b)) <= F64_TOL * k
+    # contract violations come back as LA_ERR_INVALID, not as garbage
+    assert lib().la_gemm_f64(da.h, db.h, dc.h, m, k, n * 2) == _cabi.LA_ERR_INVALID
+    assert lib().la_gemm_f64(da.h, db.h, da.h, m, k, n) == _cabi.LA_ERR_INVALID
+    assert lib().la_gemm_f64(da.h, db.h, dc.h, 0, k, n) == _cabi.LA_ERR_INVALID
+
+
+def test_gemm_linearity_property(oracle):
+    """(A1 + A2) * B == A1*B + A2*B up to rounding: a size-independent check that needs no oracle."""
+    m, k, n = 512, 640, 384
+    a1, a2, b = oracle.fill((m, k), 31), oracle.fill((m, k), 32), oracle.fill((k, n), 33)
+    out = []
+    for a in (a1, a2, a1 + a2):
+        c = np.empty((m, n))
+        check(lib().la_gemm_f64_host(np.ascontiguousarray(a).ctypes.data, b.ctypes.data, c.ctypes.data, m, k, n))
+        out.append(c)
+    assert max_rel_err(out[0] + out[1], out[2]) <= F64_TOL * k
+
+
+def test_device_fill_matches_oracle(oracle):
+    for dt in (np.float64, np.float32):
+        n = 100003
+        buf = DevBuf(n * np.dtype(dt).itemsize)
+        fill_hash(buf, n, 7, dt, first_idx=12345)
+        sync()
+        assert np.array_equal(buf.to_array((n,), dt), oracle.fill((n,), 7, dt, first_idx=12345))
+
+
+@pytest.mark.parametrize("n", [8192])
+def test_gemm_f64_full_size_sampled_rows(oracle, n):
+    """BASELINE config 1 (8192^3): inputs generated on the device, 64 full rows compared with the oracle (rows are
+    independent, so the sample is exact), plus a checksum identity: (1^T A) B == 1^T C."""
+    da, db, dc = DevBuf(n * n * 8), DevBuf(n * n * 8), DevBuf(n * n * 8)
+    fill_hash(da, n * n, 1, np.float64)
+    fill_hash(db, n * n, 2, np.float64)
+    gemm_dev(da, n, db, n, dc, n, n, n, n, 0, np.float64)
+    sync()
+    b = oracle.fill((n, n), 2)
+    rows = np.unique(np.concatenate([[0, 1, 127, 128, n - 1], np.random.default_rng(0).integers(0, n, 59)]))
+    worst = 0.0
+    for r in rows:
+        a_row = oracle.fill((1, n), 1, first_idx=int(r) * n)
+        ref = oracle.gemm_rows(a_row, b, 0, 1)
+        got = dc.to_array((1, n), np.float64, byte_offset=int(r) * n * 8)
+        worst = max(worst, max_rel_err(got, ref))
+    assert worst <= F64_TOL * n
+    # column-sum checksum over the whole product
+    c = dc.to_array((n, n), np.float64)
+    a_colsum = np.zeros(n)
+    for r0 in range(0, n, 1024):
+        a_colsum += oracle.fill((1024, n), 1, first_idx=r0 * n).sum(axis=0)
+    lhs = a_colsum @ b
+    rhs = c.sum(axis=0)
+    assert np.max(np.abs(lhs - rhs) / np.abs(lhs)) <= 1e-11
