@@ -37,6 +37,7 @@ constexpr int GEMM_THREADS = (CONSUMER_WARPS + 4) * 32;
 constexpr int CONSUMER_REGS = 232;
 constexpr int PRODUCER_REGS = 40;
 constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;  // + barriers + alignment slack
+constexpr double SMALL_GEMM_MNK = 128.0 * 128.0 * 128.0;  // <= this many multiply-adds: bit-exact CUDA-core kernel
 constexpr int GROUP_M = 16;  // tile rasterisation: GROUP_M tile-rows share each B tile-column while it is hot in L2
 
 template <int MODE>
@@ -224,7 +225,11 @@ int gemm_f64_dev(const double* A, size_t lda, const double* B, size_t ldb, doubl
   const bool aligned = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0) &&
                        lda % 2 == 0 && ldb % 2 == 0 && ldc % 2 == 0;
   const bool tiles_ok = (m + BM - 1) / BM * ((n + BN - 1) / BN) < (size_t)1 << 31;
-  bool use_tma = aligned && tiles_ok;
+  // Small products go to the CUDA-core kernel, which keeps the reference's exact per-element operation order (so the
+  // reference's own `==` unit tests hold bit-for-bit); the tensor path takes over where throughput matters.
+  const bool small = (double)m * (double)n * (double)k <= (double)SMALL_GEMM_MNK;
+  bool use_tma = aligned && tiles_ok && !small;
+  if (g_gemm_path == 2) use_tma = aligned && tiles_ok;
   if (g_gemm_path == 1) use_tma = false;
   if (g_gemm_path == 2 && !use_tma) return fail(LA_ERR_INVALID, "la_gemm_f64: TMA path forced but operands are unaligned");
   if (!use_tma) return gemm_simt<double>(A, lda, B, ldb, C, ldc, m, k, n, mode, st);

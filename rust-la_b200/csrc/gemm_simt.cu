@@ -1,5 +1,6 @@
-// gemm_simt.cu -- generic CUDA-core GEMM (fp64 / fp32) for operands the TMA kernels cannot take: odd leading
-// dimensions, unaligned base pointers, or tiny shapes.  Same contract as the tensor kernels (row-major, explicit
+// gemm_simt.cu -- generic CUDA-core GEMM (fp64 / fp32 / i64) for operands the TMA kernels cannot take (odd leading
+// dimensions, unaligned base pointers) and for small shapes, where it reproduces the reference bit-for-bit: every
+// element is accumulated for k ascending from zero with separately rounded multiply and add.  Same contract as the tensor kernels (row-major, explicit
 // leading dimensions, ASSIGN / SUB / ADD epilogue).  Replaces the same reference loops: src/matrix/mod.rs:965-973.
 // This is still a GPU path -- the library has no CPU fallback.
 #include "la_common.cuh"
@@ -11,8 +12,10 @@ constexpr int TS = 64;   // CTA tile 64 x 64
 constexpr int TK = 16;   // k-step
 constexpr int TPB = 256; // 16 x 16 threads, 4 x 4 outputs each
 
-__device__ __forceinline__ double mul_add(double a, double b, double c) { return fma(a, b, c); }
-__device__ __forceinline__ float mul_add(float a, float b, float c) { return fmaf(a, b, c); }
+// res = res + a * b with the product and the sum rounded separately, k ascending from a zero accumulator: exactly the
+// reference's expression (src/matrix/mod.rs:969), so this kernel is BIT-IDENTICAL to the reference's Mul.
+__device__ __forceinline__ double mul_add(double a, double b, double c) { return add_rn(c, mul_rn(a, b)); }
+__device__ __forceinline__ float mul_add(float a, float b, float c) { return add_rn(c, mul_rn(a, b)); }
 // integer instance (the reference's Mul is generic and is unit-tested on integer matrices, src/matrix/mod.rs:1479-1484);
 // two's-complement wrapping like a Rust release build
 __device__ __forceinline__ long long mul_add(long long a, long long b, long long c) {

@@ -133,6 +133,16 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+// Separately rounded multiply / add / subtract: never contracted into FMA by the compiler.  The reference (Rust) rounds
+// the product and the sum separately (src/matrix/mod.rs:969, src/decomp/lu.rs:125-128, :260, :272); the small-problem
+// and panel paths use these so that results are bit-identical to the reference where the operation ORDER is also kept.
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+
 // counter-based hash shared by la_fill_hash_* and the oracle
 __host__ __device__ __forceinline__ uint64_t hash64(uint64_t seed, uint64_t idx) {
   uint64_t z = seed * 0x9E3779B97F4A7C15ull + idx;

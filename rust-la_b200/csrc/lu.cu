@@ -36,6 +36,8 @@ constexpr int MAX_MOVES = 2 * MAX_NB;
 constexpr size_t PANEL_SMEM_BUDGET = 200 * 1024;
 
 // Global workspace of one factorisation (per stream use; lives in the scratch pool).
+// Exchange rows carry 2*MAX_NB values: the row itself and (EXACT mode) its deferred-subtraction sums.
+constexpr int XROW = 2 * MAX_NB;
 template <typename T>
 struct PanelWs {
   unsigned int barrier;  // grid barrier counter, zeroed before every panel launch
@@ -45,7 +47,7 @@ struct PanelWs {
   int move_dst[MAX_MOVES];      // net permutation of the panel: row move_dst[i] receives old row move_src[i]
   int move_src[MAX_MOVES];
   // double-buffered per-step exchange area, laid out after the struct:
-  //   double cand_key[2][G]; int cand_idx[2][G]; T cand_row[2][G][MAX_NB]; T top_row[2][MAX_NB];
+  //   double cand_key[2][G]; int cand_idx[2][G]; T cand_row[2][G][XROW]; T top_row[2][XROW];
 };
 
 template <typename T>
@@ -54,8 +56,8 @@ __host__ __device__ inline size_t ws_bytes(int G) {
   b += sizeof(double) * 2 * G;
   b += sizeof(int) * 2 * G;
   b = (b + 15) & ~(size_t)15;
-  b += sizeof(T) * 2 * (size_t)G * MAX_NB;
-  b += sizeof(T) * 2 * MAX_NB;
+  b += sizeof(T) * 2 * (size_t)G * XROW;
+  b += sizeof(T) * 2 * XROW;
   return b;
 }
 template <typename T>
@@ -63,8 +65,8 @@ struct WsView {
   PanelWs<T>* hdr;
   double* cand_key;  // [2][G]
   int* cand_idx;     // [2][G]
-  T* cand_row;       // [2][G][MAX_NB]
-  T* top_row;        // [2][MAX_NB]
+  T* cand_row;       // [2][G][XROW]
+  T* top_row;        // [2][XROW]
 };
 template <typename T>
 __host__ __device__ inline WsView<T> ws_view(void* base, int G) {
@@ -78,7 +80,7 @@ __host__ __device__ inline WsView<T> ws_view(void* base, int G) {
   p += sizeof(int) * 2 * G;
   p = (char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
   v.cand_row = (T*)p;
-  p += sizeof(T) * 2 * (size_t)G * MAX_NB;
+  p += sizeof(T) * 2 * (size_t)G * XROW;
   v.top_row = (T*)p;
   return v;
 }
@@ -108,12 +110,20 @@ __device__ __forceinline__ void key_merge(double& k, int& i, double k2, int i2) 
 
 // ---------------------------------------------------------------------------------------------------------------
 // 1. panel factorisation
+//
+// EXACT = true (used when the whole factorisation is one panel, i.e. min(m,n) <= nb): every element keeps its original
+// value a and a separate running sum s = sum_k l[i][k]*u[k][j] (k ascending, product and sum rounded separately); the
+// value a - s is formed once.  That is the reference's left-looking expression (lu.rs:122-129) evaluated in
+// right-looking order, so the packed LU is BIT-IDENTICAL to the reference's -- in particular exact zeros (singular
+// matrices) are reproduced.  EXACT = false subtracts each separately rounded product immediately (half the shared
+// memory); later panels carry DMMA-rounded trailing updates anyway.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool EXACT>
 __global__ void __launch_bounds__(PANEL_THREADS, 1)
 lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_per_cta, void* ws_base) {
   extern __shared__ __align__(16) unsigned char panel_smem[];
-  T* rows = reinterpret_cast<T*>(panel_smem);  // [rows_per_cta][jb]
+  T* rows = reinterpret_cast<T*>(panel_smem);            // [rows_per_cta][jb]: original values, then final L / U
+  T* sums = rows + (size_t)rows_per_cta * jb;            // [rows_per_cta][jb]: deferred sums (EXACT only)
   __shared__ double wkey[PANEL_WARPS];
   __shared__ int widx[PANEL_WARPS];
 
@@ -124,10 +134,16 @@ lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_pe
   const int nloc = max(0, min(rows_per_cta, m - row_base));     // rows held by this CTA
   const int nq = (jb + 31) >> 5;                                // column groups of 32 per lane
 
+  auto value = [&](int lr, int col) -> T {
+    const T a = rows[(size_t)lr * jb + col];
+    return EXACT ? sub_rn(a, sums[(size_t)lr * jb + col]) : a;
+  };
+
   // ---- load the CTA's rows of the panel into shared memory (row segments of jb contiguous elements) ----
   for (int idx = threadIdx.x; idx < nloc * jb; idx += PANEL_THREADS) {
     const int lr = idx / jb, c = idx - lr * jb;
     rows[idx] = A[(size_t)(row_base + lr) * ld + j0 + c];
+    if (EXACT) sums[idx] = (T)0;
   }
   __syncthreads();
 
@@ -137,7 +153,7 @@ lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_pe
     int ki = INT_MAX;
     for (int lr = warp; lr < nloc; lr += PANEL_WARPS) {
       const int gr = row_base + lr;
-      if (lane == 0) key_merge(k, ki, pivot_key(rows[lr * jb], gr == j0), gr);
+      if (lane == 0) key_merge(k, ki, pivot_key(rows[(size_t)lr * jb], gr == j0), gr);
     }
     if (lane == 0) {
       wkey[warp] = k;
@@ -166,17 +182,23 @@ lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_pe
         ws.cand_idx[par * G + blockIdx.x] = ki;
       }
       if (ki != INT_MAX) {
-        const T* src = rows + (size_t)(ki - row_base) * jb;
-        T* dst = ws.cand_row + ((size_t)par * G + blockIdx.x) * MAX_NB;
+        const size_t off = (size_t)(ki - row_base) * jb;
+        T* dst = ws.cand_row + ((size_t)par * G + blockIdx.x) * XROW;
         for (int q = 0; q < nq; ++q)
-          if (lane + 32 * q < jb) dst[lane + 32 * q] = src[lane + 32 * q];
+          if (lane + 32 * q < jb) {
+            dst[lane + 32 * q] = rows[off + lane + 32 * q];
+            if (EXACT) dst[MAX_NB + lane + 32 * q] = sums[off + lane + 32 * q];
+          }
       }
     } else if (warp == 1) {
       if (diag >= row_base && diag < row_base + nloc) {  // this CTA holds the diagonal row: publish it for the swap
-        const T* src = rows + (size_t)(diag - row_base) * jb;
-        T* dst = ws.top_row + (size_t)par * MAX_NB;
+        const size_t off = (size_t)(diag - row_base) * jb;
+        T* dst = ws.top_row + (size_t)par * XROW;
         for (int q = 0; q < nq; ++q)
-          if (lane + 32 * q < jb) dst[lane + 32 * q] = src[lane + 32 * q];
+          if (lane + 32 * q < jb) {
+            dst[lane + 32 * q] = rows[off + lane + 32 * q];
+            if (EXACT) dst[MAX_NB + lane + 32 * q] = sums[off + lane + 32 * q];
+          }
       }
     }
     __syncthreads();  // (B) publication complete within the CTA
@@ -213,28 +235,39 @@ lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_pe
       }
     }
     // p = absolute pivot row (>= diag), held by CTA pcta
-    const T* prow_g = ws.cand_row + ((size_t)par * G + pcta) * MAX_NB;
-    T prow[MAX_NB / 32];
+    const T* prow_g = ws.cand_row + ((size_t)par * G + pcta) * XROW;
+    T prow[MAX_NB / 32];  // the pivot row as stored (cols < c: final L entries; cols >= c: original values in EXACT)
+    T u[MAX_NB / 32];     // its current values = row c of U for cols >= c
 #pragma unroll
-    for (int q = 0; q < MAX_NB / 32; ++q) prow[q] = (lane + 32 * q < jb) ? __ldcg(&prow_g[lane + 32 * q]) : (T)0;
-    const T pv = __ldcg(&prow_g[c]);
+    for (int q = 0; q < MAX_NB / 32; ++q) {
+      const int col = lane + 32 * q;
+      prow[q] = (col < jb) ? __ldcg(&prow_g[col]) : (T)0;
+      u[q] = prow[q];
+      if (EXACT && col < jb) u[q] = sub_rn(prow[q], __ldcg(&prow_g[MAX_NB + col]));
+    }
+    T pv = __ldcg(&prow_g[c]);
+    if (EXACT) pv = sub_rn(pv, __ldcg(&prow_g[MAX_NB + c]));
 
     if (blockIdx.x == 0 && threadIdx.x == 0) ws.hdr->ipiv[c] = p;
 
     // ---- interchange (whole panel row; the rest of the row is swapped by lu_swap*_kernel) ----
-    if (p != diag) {
-      if (p >= row_base && p < row_base + nloc && ((p - row_base) % PANEL_WARPS) == warp) {
-        const T* trow_g = ws.top_row + (size_t)par * MAX_NB;
-        T* dst = rows + (size_t)(p - row_base) * jb;
+    if (p != diag && p >= row_base && p < row_base + nloc && ((p - row_base) % PANEL_WARPS) == warp) {
+      const T* trow_g = ws.top_row + (size_t)par * XROW;
+      const size_t off = (size_t)(p - row_base) * jb;
 #pragma unroll
-        for (int q = 0; q < MAX_NB / 32; ++q)
-          if (lane + 32 * q < jb) dst[lane + 32 * q] = __ldcg(&trow_g[lane + 32 * q]);
-      }
-      if (diag >= row_base && diag < row_base + nloc && ((diag - row_base) % PANEL_WARPS) == warp) {
-        T* dst = rows + (size_t)(diag - row_base) * jb;
+      for (int q = 0; q < MAX_NB / 32; ++q)
+        if (lane + 32 * q < jb) {
+          rows[off + lane + 32 * q] = __ldcg(&trow_g[lane + 32 * q]);
+          if (EXACT) sums[off + lane + 32 * q] = __ldcg(&trow_g[MAX_NB + lane + 32 * q]);
+        }
+    }
+    if ((p != diag || EXACT) && diag >= row_base && diag < row_base + nloc &&
+        ((diag - row_base) % PANEL_WARPS) == warp) {
+      const size_t off = (size_t)(diag - row_base) * jb;  // the diagonal row becomes final: L for cols < c, U for >= c
 #pragma unroll
-        for (int q = 0; q < MAX_NB / 32; ++q)
-          if (lane + 32 * q < jb) dst[lane + 32 * q] = prow[q];
+      for (int q = 0; q < MAX_NB / 32; ++q) {
+        const int col = lane + 32 * q;
+        if (col < jb) rows[off + col] = (col >= c) ? u[q] : prow[q];
       }
     }
     __syncwarp();
@@ -252,29 +285,36 @@ lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_pe
     }
     for (int lr = lr0; lr < nloc; lr += PANEL_WARPS) {
       T* r = rows + (size_t)lr * jb;
-      T l = r[c];
+      T* sacc = sums + (size_t)lr * jb;
+      T l = value(lr, c);
       if (pv != (T)0) l = l / pv;             // true division, skipped for an exactly-zero pivot (lu.rs:156-160)
-      if (lane == (c & 31)) r[c] = l;
+      __syncwarp();
+      if (lane == (c & 31)) r[c] = l;         // final L entry
       T nv = (T)0;
 #pragma unroll
       for (int q = 0; q < MAX_NB / 32; ++q) {
         const int col = lane + 32 * q;
         if (col > c && col < jb) {
-          const T v = r[col] - l * prow[q];
-          r[col] = v;
+          T v;
+          if (EXACT) {
+            const T sn = add_rn(sacc[col], mul_rn(l, u[q]));  // s = s + l*u, k ascending (lu.rs:125)
+            sacc[col] = sn;
+            v = sub_rn(r[col], sn);
+          } else {
+            v = sub_rn(r[col], mul_rn(l, u[q]));
+            r[col] = v;
+          }
           if (q == qn) nv = v;
         }
       }
       if (track) key_merge(nk, nki, pivot_key(nv, false), row_base + lr);
     }
-    // the row that becomes the next diagonal row (absolute row diag+1) takes part with its own (final) value
+    // the row that becomes the next diagonal row (absolute row diag+1) takes part with its own value as the incumbent
     if (cn < jb) {
       const int nd = diag + 1;
       if (nd >= row_base && nd < row_base + nloc && ((nd - row_base) % PANEL_WARPS) == warp && nd < m) {
-        // nd was updated in the loop above (it is below the current diagonal); re-key it as the incumbent
         if (track) {
-          const T v = rows[(size_t)(nd - row_base) * jb + cn];
-          const double kk = pivot_key(v, true);
+          const double kk = pivot_key(value(nd - row_base, cn), true);
           if (kk == (double)INFINITY) {  // NaN incumbent: never displaced
             nk = kk;
             nki = nd;
@@ -394,16 +434,18 @@ __global__ void __launch_bounds__(256) lu_swap_kernel(T* __restrict__ A, size_t 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// 4. right of the panel: permutation + U12 = L11^-1 * A12 (unit lower triangular solve, lu.rs:122-129 for i <= j)
-//    One CTA per strip of TRSM_W columns; the jb x TRSM_W block lives in shared memory.
+// 4. right of the panel: permutation + U12 = L11^-1 * A12 (the i <= j part of lu.rs:122-129).
+//    One CTA per strip of TRSM_W columns.  Each element keeps its original value and a running sum of separately
+//    rounded products (k ascending); U[i][j] = a - s is formed once -- the reference's expression, bit for bit.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int TRSM_W = 32;
 template <typename T>
 __global__ void __launch_bounds__(256)
 lu_swap_trsm_kernel(T* __restrict__ A, size_t ld, int j0, int jb, int col0, int col1, const void* ws_base, int G) {
   extern __shared__ __align__(16) unsigned char trsm_smem[];
-  T(*X)[TRSM_W] = reinterpret_cast<T(*)[TRSM_W]>(trsm_smem);            // [MAX_NB]: top jb rows of the strip
-  T(*stage)[TRSM_W] = X + MAX_NB;                                       // [MAX_NB]: rows leaving the top block
+  T(*X)[TRSM_W] = reinterpret_cast<T(*)[TRSM_W]>(trsm_smem);            // [MAX_NB]: top jb rows of the strip (a)
+  T(*S)[TRSM_W] = X + MAX_NB;                                           // [MAX_NB]: running sums
+  T(*stage)[TRSM_W] = S + MAX_NB;                                       // [MAX_NB]: rows leaving the top block
   __shared__ int top_src[MAX_NB];
   __shared__ int out_dst[MAX_NB];
   __shared__ int out_src[MAX_NB];
@@ -430,22 +472,24 @@ lu_swap_trsm_kernel(T* __restrict__ A, size_t ld, int j0, int jb, int col0, int 
   __syncthreads();
   const int no = n_out;
   // gather
-  for (int i = warp; i < jb; i += 8) X[i][lane] = ok ? A[(size_t)top_src[i] * ld + col] : (T)0;
+  for (int i = warp; i < jb; i += 8) {
+    X[i][lane] = ok ? A[(size_t)top_src[i] * ld + col] : (T)0;
+    S[i][lane] = (T)0;
+  }
   for (int i = warp; i < no; i += 8) stage[i][lane] = ok ? A[(size_t)out_src[i] * ld + col] : (T)0;
   __syncthreads();
   // rows that left the top block
   for (int i = warp; i < no; i += 8)
     if (ok) A[(size_t)out_dst[i] * ld + col] = stage[i][lane];
 
-  // forward substitution, right-looking: for k: rows i > k: X[i] -= L[i][k] * X[k]
+  // forward substitution, right-looking over k with deferred subtraction
   const T* L = A + (size_t)j0 * ld + j0;  // L11, unit lower, written by the panel kernel
-  for (int k = 0; k < jb - 1; ++k) {
-    const T xk = X[k][lane];
-    for (int i = k + 1 + warp; i < jb; i += 8) X[i][lane] -= __ldg(&L[(size_t)i * ld + k]) * xk;
+  for (int k = 0; k < jb; ++k) {
+    const T xk = sub_rn(X[k][lane], S[k][lane]);  // U[k][col], final
+    if (warp == (k & 7) && ok) A[(size_t)(j0 + k) * ld + col] = xk;
+    for (int i = k + 1 + warp; i < jb; i += 8) S[i][lane] = add_rn(S[i][lane], mul_rn(__ldg(&L[(size_t)i * ld + k]), xk));
     __syncthreads();
   }
-  for (int i = warp; i < jb; i += 8)
-    if (ok) A[(size_t)(j0 + i) * ld + col] = X[i][lane];
 }
 
 template <typename T>
@@ -481,14 +525,18 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
   if (nb > MAX_NB) nb = MAX_NB;
   if (nb < 16)
     return fail(LA_ERR_UNSUPPORTED, "la_lu_factor: %d rows exceed the shared-memory panel capacity of %d SMs", M, sms);
+  // single-panel factorisations run the bit-exact (deferred subtraction) panel when twice the panel fits
+  const bool exact = kmin <= nb && (size_t)2 * rpc_first * kmin * sizeof(T) <= PANEL_SMEM_BUDGET;
 
   void* ws_base = nullptr;
   LA_TRY(scratch_get(ctx->device, 8, ws_bytes<T>(sms), &ws_base));
-  LA_CUDA_TRY(cudaFuncSetAttribute(lu_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  LA_CUDA_TRY(cudaFuncSetAttribute(lu_panel_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)PANEL_SMEM_BUDGET + 2048));
+  LA_CUDA_TRY(cudaFuncSetAttribute(lu_panel_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)PANEL_SMEM_BUDGET + 2048));
 
   const int SWAP_SMEM = (int)(sizeof(T) * MAX_MOVES * SWAP_W);
-  const int TRSM_SMEM = (int)(sizeof(T) * 2 * MAX_NB * TRSM_W);
+  const int TRSM_SMEM = (int)(sizeof(T) * 3 * MAX_NB * TRSM_W);
   LA_CUDA_TRY(cudaFuncSetAttribute(lu_swap_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWAP_SMEM));
   LA_CUDA_TRY(cudaFuncSetAttribute(lu_swap_trsm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM));
 
@@ -501,7 +549,7 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
     int rpc = (R + sms - 1) / sms;
     if (rpc < 8) rpc = 8;  // at least one row per warp; fewer, fuller CTAs make the barrier cheaper
     const int G = (R + rpc - 1) / rpc;
-    const size_t smem = (size_t)rpc * jb * sizeof(T);
+    const size_t smem = (size_t)rpc * jb * sizeof(T) * (exact ? 2 : 1);
 
     LA_CUDA_TRY(cudaMemsetAsync(ws_base, 0, sizeof(unsigned int) * 4, st));
     {
@@ -510,8 +558,8 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
       int mm = M, jj0 = j0, jjb = jb, rr = rpc;
       void* wsb = ws_base;
       void* args[] = {&a, &ld, &mm, &jj0, &jjb, &rr, &wsb};
-      LA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)lu_panel_kernel<T>, dim3(G), dim3(PANEL_THREADS), args, smem,
-                                              st));
+      const void* fn = exact ? (const void*)lu_panel_kernel<T, true> : (const void*)lu_panel_kernel<T, false>;
+      LA_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PANEL_THREADS), args, smem, st));
     }
     lu_perm_kernel<T><<<1, 32, 0, st>>>(ws_base, G, j0, jb, piv_dev, sign_dev);
     LA_CUDA_TRY(cudaGetLastError());

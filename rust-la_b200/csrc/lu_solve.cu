@@ -9,7 +9,8 @@
 // The solve is HBM-bound for few right-hand sides (8*n^2 bytes of LU for 2*n^2*nx flops): it is blocked so that LU is
 // streamed exactly once per sweep in coalesced row segments: for each diagonal block (SB rows) a single-CTA triangular
 // solve in shared memory, then a all-SM rank-SB update of the remaining rows.  Per element the updates arrive in the
-// reference's order (k ascending in the forward sweep, descending in the backward sweep).
+// reference's order (k ascending in the forward sweep, descending in the backward sweep) with separately rounded
+// multiply and subtract, so given the same packed LU and piv the result is BIT-IDENTICAL to the reference's solve.
 #include "la_common.cuh"
 
 namespace la {
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(256) solve_diag_kernel(const T* __restrict__ L
   if (FORWARD) {
     for (int k = 0; k < sb; ++k) {
       const T xk = Xs[k][j];
-      for (int i = k + 1 + rg; i < sb; i += SOLVE_RG) Xs[i][j] -= xk * D[i][k];
+      for (int i = k + 1 + rg; i < sb; i += SOLVE_RG) Xs[i][j] = sub_rn(Xs[i][j], mul_rn(xk, D[i][k]));
       __syncthreads();
     }
   } else {
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(256) solve_diag_kernel(const T* __restrict__ L
       if (rg == 0) Xs[k][j] = Xs[k][j] / D[k][k];  // true division by the diagonal (lu.rs:268)
       __syncthreads();
       const T xk = Xs[k][j];
-      for (int i = rg; i < k; i += SOLVE_RG) Xs[i][j] -= xk * D[i][k];
+      for (int i = rg; i < k; i += SOLVE_RG) Xs[i][j] = sub_rn(Xs[i][j], mul_rn(xk, D[i][k]));
       __syncthreads();
     }
   }
@@ -97,9 +98,9 @@ __global__ void __launch_bounds__(256) solve_update_kernel(const T* __restrict__
       for (int i = rg; i < nrows; i += SOLVE_RG) {
         T acc = X[(size_t)(rbase + i) * nx + c0 + j];
         if (FORWARD) {
-          for (int k = 0; k < kb; ++k) acc -= Xk[k][j] * Ls[i][k];
+          for (int k = 0; k < kb; ++k) acc = sub_rn(acc, mul_rn(Xk[k][j], Ls[i][k]));
         } else {
-          for (int k = kb - 1; k >= 0; --k) acc -= Xk[k][j] * Ls[i][k];
+          for (int k = kb - 1; k >= 0; --k) acc = sub_rn(acc, mul_rn(Xk[k][j], Ls[i][k]));
         }
         X[(size_t)(rbase + i) * nx + c0 + j] = acc;
       }

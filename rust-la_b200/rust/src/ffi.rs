@@ -1,0 +1,91 @@
+//! Raw bindings of include/la_cabi.h.  One `extern "C"` item per header declaration, same order.
+#![allow(non_camel_case_types, dead_code)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct la_buf {
+    _private: [u8; 0],
+}
+
+pub const LA_OK: c_int = 0;
+pub const LA_ERR_INVALID: c_int = 1;
+pub const LA_ERR_CUDA: c_int = 2;
+pub const LA_ERR_NOMEM: c_int = 3;
+pub const LA_ERR_NO_DEVICE: c_int = 4;
+pub const LA_ERR_UNSUPPORTED: c_int = 5;
+
+pub const LA_GEMM_ASSIGN: c_int = 0;
+pub const LA_GEMM_SUB: c_int = 1;
+pub const LA_GEMM_ADD: c_int = 2;
+
+extern "C" {
+    pub fn la_version() -> c_int;
+    pub fn la_last_error() -> *const c_char;
+    pub fn la_device_count(out: *mut c_int) -> c_int;
+    pub fn la_device_sm_count(device: c_int, out: *mut c_int) -> c_int;
+    pub fn la_sync(device: c_int) -> c_int;
+
+    pub fn la_buf_alloc(bytes: usize, device: c_int, out: *mut *mut la_buf) -> c_int;
+    pub fn la_buf_free(buf: *mut la_buf) -> c_int;
+    pub fn la_buf_upload(dst: *mut la_buf, dst_offset_bytes: usize, host: *const c_void, bytes: usize) -> c_int;
+    pub fn la_buf_download(src: *const la_buf, src_offset_bytes: usize, host: *mut c_void, bytes: usize) -> c_int;
+    pub fn la_buf_copy(dst: *mut la_buf, src: *const la_buf, bytes: usize) -> c_int;
+    pub fn la_buf_device_ptr(buf: *const la_buf) -> *mut c_void;
+    pub fn la_buf_bytes(buf: *const la_buf) -> usize;
+    pub fn la_buf_device(buf: *const la_buf) -> c_int;
+    pub fn la_host_alloc(bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn la_host_free(ptr: *mut c_void) -> c_int;
+
+    pub fn la_gemm_f64(a: *const la_buf, b: *const la_buf, c: *mut la_buf, m: usize, k: usize, n: usize) -> c_int;
+    pub fn la_gemm_f32(a: *const la_buf, b: *const la_buf, c: *mut la_buf, m: usize, k: usize, n: usize) -> c_int;
+    pub fn la_gemm_f64_host(a: *const f64, b: *const f64, c: *mut f64, m: usize, k: usize, n: usize) -> c_int;
+    pub fn la_gemm_f32_host(a: *const f32, b: *const f32, c: *mut f32, m: usize, k: usize, n: usize) -> c_int;
+    pub fn la_gemm_i64_host(a: *const i64, b: *const i64, c: *mut i64, m: usize, k: usize, n: usize) -> c_int;
+    pub fn la_gemm_f64_dev(a: *const f64, lda: usize, b: *const f64, ldb: usize, c: *mut f64, ldc: usize,
+                           m: usize, k: usize, n: usize, mode: c_int, cuda_stream: *mut c_void) -> c_int;
+    pub fn la_gemm_f32_dev(a: *const f32, lda: usize, b: *const f32, ldb: usize, c: *mut f32, ldc: usize,
+                           m: usize, k: usize, n: usize, mode: c_int, cuda_stream: *mut c_void) -> c_int;
+
+    pub fn la_lu_factor_f64(lu: *mut la_buf, m: usize, n: usize, piv_out: *mut u64, pospivsign_out: *mut c_int) -> c_int;
+    pub fn la_lu_factor_f32(lu: *mut la_buf, m: usize, n: usize, piv_out: *mut u64, pospivsign_out: *mut c_int) -> c_int;
+    pub fn la_lu_factor_f64_host(a: *const f64, lu_out: *mut f64, m: usize, n: usize, piv_out: *mut u64,
+                                 pospivsign_out: *mut c_int) -> c_int;
+    pub fn la_lu_factor_f32_host(a: *const f32, lu_out: *mut f32, m: usize, n: usize, piv_out: *mut u64,
+                                 pospivsign_out: *mut c_int) -> c_int;
+    pub fn la_lu_factor_f64_dev(lu: *mut f64, m: usize, n: usize, piv_dev: *mut u64, sign_dev: *mut c_int,
+                                cuda_stream: *mut c_void) -> c_int;
+    pub fn la_lu_factor_f32_dev(lu: *mut f32, m: usize, n: usize, piv_dev: *mut u64, sign_dev: *mut c_int,
+                                cuda_stream: *mut c_void) -> c_int;
+
+    pub fn la_lu_is_nonsingular_f64(lu: *const la_buf, n: usize, out: *mut c_int) -> c_int;
+    pub fn la_lu_is_nonsingular_f32(lu: *const la_buf, n: usize, out: *mut c_int) -> c_int;
+    pub fn la_lu_det_f64(lu: *const la_buf, n: usize, pospivsign: c_int, out: *mut f64) -> c_int;
+    pub fn la_lu_det_f32(lu: *const la_buf, n: usize, pospivsign: c_int, out: *mut f32) -> c_int;
+    pub fn la_lu_solve_f64(lu: *const la_buf, m: usize, n: usize, piv: *const u64, b: *const la_buf, nx: usize,
+                           x: *mut la_buf) -> c_int;
+    pub fn la_lu_solve_f32(lu: *const la_buf, m: usize, n: usize, piv: *const u64, b: *const la_buf, nx: usize,
+                           x: *mut la_buf) -> c_int;
+    pub fn la_lu_solve_f64_host(lu: *const f64, m: usize, n: usize, piv: *const u64, b: *const f64, nx: usize,
+                                x: *mut f64) -> c_int;
+    pub fn la_lu_solve_f32_host(lu: *const f32, m: usize, n: usize, piv: *const u64, b: *const f32, nx: usize,
+                                x: *mut f32) -> c_int;
+    pub fn la_lu_solve_f64_dev(lu: *const f64, n: usize, piv_dev: *const u64, b: *const f64, nx: usize, x: *mut f64,
+                               cuda_stream: *mut c_void) -> c_int;
+    pub fn la_lu_solve_f32_dev(lu: *const f32, n: usize, piv_dev: *const u64, b: *const f32, nx: usize, x: *mut f32,
+                               cuda_stream: *mut c_void) -> c_int;
+
+    pub fn la_identity_f64(dst: *mut la_buf, n: usize) -> c_int;
+    pub fn la_identity_f32(dst: *mut la_buf, n: usize) -> c_int;
+    pub fn la_fill_hash_f64_dev(dst: *mut f64, count: usize, seed: u64, first_idx: u64, cuda_stream: *mut c_void) -> c_int;
+    pub fn la_fill_hash_f32_dev(dst: *mut f32, count: usize, seed: u64, first_idx: u64, cuda_stream: *mut c_void) -> c_int;
+    pub fn la_debug_set_gemm_path(path: c_int) -> c_int;
+}
+
+/// Panics with the library's message when `status != LA_OK` -- contract violations panic in the reference too
+/// (`assert!`, src/matrix/mod.rs:961; src/decomp/lu.rs:225,240).
+pub fn check(status: c_int) {
+    if status != LA_OK {
+        let msg = unsafe { std::ffi::CStr::from_ptr(la_last_error()) }.to_string_lossy().into_owned();
+        panic!("la_b200 status {}: {}", status, msg);
+    }
+}

@@ -136,7 +136,7 @@ def test_solve_given_reference_factors_matches_oracle(oracle):
     ref_x = oracle.lu_solve(ref_lu, ref_piv, b)
     x = np.empty((n, nx))
     check(lib().la_lu_solve_f64_host(ref_lu.ctypes.data, n, n, ref_piv.ctypes.data, b.ctypes.data, nx, x.ctypes.data))
-    assert np.max(np.abs(x - ref_x) / np.maximum(np.abs(ref_x), np.max(np.abs(ref_x)) * 1e-3)) <= 1e-9
+    assert np.array_equal(x.view(np.uint64), ref_x.view(np.uint64))  # same order, separately rounded ops: bit-exact
 
 
 def test_det_parity_and_overflow_order(oracle):
@@ -184,3 +184,35 @@ def test_lu_reconstruction_property_2048(oracle):
     amax = 1.0
     err = np.max(np.abs(lu - ref_lu) / np.maximum(np.abs(ref_lu), amax))
     assert err <= 1e-12 * n
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 3), (17, 17), (64, 64), (100, 100), (128, 128), (90, 40), (40, 90), (128, 300)])
+def test_single_panel_lu_is_bit_exact(oracle, shape):
+    """min(m,n) <= 128: the deferred-subtraction panel + TRSM reproduce the reference bit for bit (incl. exact zeros)."""
+    for seed, shift in ((1, 0.0), (8, 0.5)):
+        a = oracle.fill(shape, seed) - shift
+        ref_lu, ref_piv, ref_sign = oracle.lu(a, form="canon")
+        lu, piv, sign = factor_host(a)
+        assert np.array_equal(piv, ref_piv) and sign == ref_sign
+        assert np.array_equal(lu.view(np.uint64), ref_lu.view(np.uint64))
+    # an exactly singular integer-valued matrix keeps its exact zero pivot (is_singular parity with the reference)
+    m, n = shape
+    if m == n and m >= 3:
+        s = np.round(oracle.fill(shape, 5) * 8)
+        s[2] = s[0] + s[1]
+        ref_lu, ref_piv, _ = oracle.lu(s, form="canon")
+        lu, piv, _ = factor_host(s)
+        assert np.array_equal(lu.view(np.uint64), ref_lu.view(np.uint64))
+
+
+@pytest.mark.parametrize("shape", [(5, 7, 3), (64, 64, 64), (100, 130, 90), (128, 128, 128)])
+def test_small_gemm_is_bit_exact(oracle, shape):
+    """Small products run the reference-order CUDA-core kernel: bit-identical to src/matrix/mod.rs:965-973."""
+    m, k, n = shape
+    for dt in (np.float64, np.float32):
+        a = oracle.fill((m, k), 1, dt) - dt(0.5)
+        b = oracle.fill((k, n), 2, dt) - dt(0.5)
+        c = np.empty((m, n), dtype=dt)
+        suf = "f64" if dt == np.float64 else "f32"
+        check(getattr(lib(), f"la_gemm_{suf}_host")(a.ctypes.data, b.ctypes.data, c.ctypes.data, m, k, n))
+        assert np.array_equal(c.view(np.uint8), oracle.gemm(a, b, form="canon").view(np.uint8))

@@ -126,11 +126,11 @@ def test_golden_vectors_bit_exact(case):
                 assert x is None
             else:
                 wantx = np.array([float.fromhex(v) for v in d["solve"]["x"]])
-                assert np.allclose(x.get_data(), wantx, rtol=0, atol=1e-15)
+                assert np.array_equal(x.get_data().view(np.uint64), wantx.view(np.uint64))
         if "inverse" in d:
             inv = a.inverse()
             if d["inverse"] is None:
                 assert inv is None
             else:
                 wanti = np.array([float.fromhex(v) for v in d["inverse"]])
-                assert np.allclose(inv.get_data(), wanti, rtol=0, atol=1e-15)
+                assert np.array_equal(inv.get_data().view(np.uint64), wanti.view(np.uint64))
