@@ -429,7 +429,7 @@ int la_fill_hash_f32_dev(float* dst, size_t count, uint64_t seed, uint64_t first
 
 /* test hook: 0 = automatic kernel choice, 1 = force the CUDA-core kernel, 2 = force the TMA/DMMA kernel */
 int la_debug_set_gemm_path(int path) {
-  LA_REQUIRE(path >= 0 && path <= 2, "la_debug_set_gemm_path: bad value %d", path);
+  LA_REQUIRE(path >= 0 && path <= 4, "la_debug_set_gemm_path: bad value %d", path);
   la::debug_set_gemm_path(path);
   return LA_OK;
 }

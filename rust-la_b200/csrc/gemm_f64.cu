@@ -22,22 +22,32 @@
 namespace la {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int BM = 128, BK = 16;
 constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 8;  // 16 KiB: 128 rows x 128 B
-constexpr int B_STAGE_BYTES = BK * BN * 8;  // 16 KiB: 8 boxes of [16 k-rows x 128 B]
-constexpr int B_BOX_BYTES = BK * 16 * 8;    // 2 KiB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int CONSUMER_WARPS = 8;
-// 8 consumer warps (2 warpgroups) + 1 producer warpgroup (only its first lane works).  The register file is split
-// per SM sub-partition (16K regs each), so a 9th warp would cap every thread at 168 registers and spill the 128
-// accumulator registers; instead 12 warps launch at 168 and setmaxnreg moves registers from the producer warpgroup
-// (40) to the consumers (232): 2*232*32 + 40*32 = 16128 <= 16384 per sub-partition.
-constexpr int GEMM_THREADS = (CONSUMER_WARPS + 4) * 32;
-constexpr int CONSUMER_REGS = 232;
-constexpr int PRODUCER_REGS = 40;
-constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;  // + barriers + alignment slack
+constexpr int B_BOX_BYTES = BK * 16 * 8;    // 2 KiB: [16 k-rows x 128 B] holds 16 columns of B
+// Two tile configurations of the same kernel:
+//   BN = 128, 8 consumer warps, 1 CTA/SM : least L2->smem traffic per flop; used for deep K (Mul at large n).
+//   BN =  64, 4 consumer warps, 2 CTA/SM : the epilogue of one CTA (C tile read-modify-write, HBM bound) overlaps the
+//                                           main loop of the other; used for shallow K (the LU trailing update, K = nb).
+// Each configuration adds one producer warpgroup (only its first lane works).  The register file is split per SM
+// sub-partition (16K regs each); the CTA launches at an even split and setmaxnreg moves registers from the producer
+// warpgroup to the consumers (128 accumulator registers + fragments per consumer thread):
+//   BN=128: 12 warps launch at 168 -> consumers 232, producer 40   (2*232 + 40 = 504 = 3*168)
+//   BN= 64:  8 warps launch at 128 -> consumers 216, producer 40   (216 + 40 = 256 = 2*128), twice per SM
+template <int BN_>
+struct TileCfg {
+  static constexpr int CONSUMER_WARPS = BN_ / 16;                 // 2 (M) x BN/32 (N) warps of 64 x 32
+  static constexpr int THREADS = (CONSUMER_WARPS + 4) * 32;
+  static constexpr int CTAS_PER_SM = BN_ == 128 ? 1 : 2;
+  static constexpr int CONSUMER_REGS = BN_ == 128 ? 232 : 216;
+  static constexpr int PRODUCER_REGS = 40;
+  static constexpr int B_STAGE_BYTES = BK * BN_ * 8;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;  // + barriers + alignment slack
+};
 constexpr double SMALL_GEMM_MNK = 128.0 * 128.0 * 128.0;  // <= this many multiply-adds: bit-exact CUDA-core kernel
+constexpr size_t SHALLOW_K = 1024;
 constexpr int GROUP_M = 16;  // tile rasterisation: GROUP_M tile-rows share each B tile-column while it is hot in L2
 
 template <int MODE>
@@ -63,10 +73,14 @@ __device__ __forceinline__ void store_pair(double* __restrict__ C, size_t ldc, i
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int MODE, int BN>
+__global__ void __launch_bounds__(TileCfg<BN>::THREADS, TileCfg<BN>::CTAS_PER_SM)
 gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     double* __restrict__ C, size_t ldc, int M, int N, int K, int tiles_m, int tiles_n) {
+  using Cfg = TileCfg<BN>;
+  constexpr int CONSUMER_WARPS = Cfg::CONSUMER_WARPS;
+  constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr int WARPS_N = BN / 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -100,7 +114,7 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp >= CONSUMER_WARPS) {
     // ===== TMA producer warpgroup: one elected lane works, the rest only donate registers =====
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::PRODUCER_REGS));
     if (warp == CONSUMER_WARPS && lane == 0) {
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
@@ -120,10 +134,10 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     return;
   }
 
-  // ===== consumers: 8 warps, 2 (M) x 4 (N), warp tile 64 x 32 =====
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
-  const int wm = warp >> 2;
-  const int wn = warp & 3;
+  // ===== consumers: 2 (M) x BN/32 (N) warps, warp tile 64 x 32 =====
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::CONSUMER_REGS));
+  const int wm = warp / WARPS_N;
+  const int wn = warp % WARPS_N;
   const int g = lane >> 2;
   const int t = lane & 3;
   const int x = (g >> 1) | ((g & 1) << 2);  // row of the 8-row MMA tile this lane's group supplies
@@ -194,18 +208,28 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-int g_gemm_path = 0;  // 0 auto, 1 force SIMT, 2 force TMA/DMMA (test hook)
+int g_gemm_path = 0;  // test hook: 0 auto, 1 SIMT, 2 TMA/DMMA (auto tile), 3 TMA/DMMA BN=64, 4 TMA/DMMA BN=128
 
-template <int MODE>
+template <int MODE, int BN>
 int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, size_t ldc, int M, int N, int K,
                cudaStream_t st) {
-  LA_CUDA_TRY(cudaFuncSetAttribute(gemm_f64_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   GEMM_SMEM_BYTES));
+  using Cfg = TileCfg<BN>;
+  LA_CUDA_TRY(cudaFuncSetAttribute(gemm_f64_tma_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::SMEM_BYTES));
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
-  gemm_f64_tma_kernel<MODE><<<tiles_m * tiles_n, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(tmA, tmB, C, ldc, M, N, K, tiles_m,
-                                                                                    tiles_n);
+  gemm_f64_tma_kernel<MODE, BN><<<tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, C, ldc, M, N, K,
+                                                                                        tiles_m, tiles_n);
   LA_CUDA_TRY(cudaGetLastError());
   return LA_OK;
+}
+template <int BN>
+int launch_tma_mode(int mode, const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, size_t ldc, int M, int N,
+                    int K, cudaStream_t st) {
+  switch (mode) {
+    case LA_GEMM_ASSIGN: return launch_tma<LA_GEMM_ASSIGN, BN>(tmA, tmB, C, ldc, M, N, K, st);
+    case LA_GEMM_SUB: return launch_tma<LA_GEMM_SUB, BN>(tmA, tmB, C, ldc, M, N, K, st);
+    default: return launch_tma<LA_GEMM_ADD, BN>(tmA, tmB, C, ldc, M, N, K, st);
+  }
 }
 
 }  // namespace
@@ -224,14 +248,14 @@ int gemm_f64_dev(const double* A, size_t lda, const double* B, size_t ldb, doubl
 
   const bool aligned = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0) &&
                        lda % 2 == 0 && ldb % 2 == 0 && ldc % 2 == 0;
-  const bool tiles_ok = (m + BM - 1) / BM * ((n + BN - 1) / BN) < (size_t)1 << 31;
+  const bool tiles_ok = (m + BM - 1) / BM * ((n + 63) / 64) < (size_t)1 << 31;
   // Small products go to the CUDA-core kernel, which keeps the reference's exact per-element operation order (so the
   // reference's own `==` unit tests hold bit-for-bit); the tensor path takes over where throughput matters.
   const bool small = (double)m * (double)n * (double)k <= (double)SMALL_GEMM_MNK;
   bool use_tma = aligned && tiles_ok && !small;
-  if (g_gemm_path == 2) use_tma = aligned && tiles_ok;
+  if (g_gemm_path >= 2) use_tma = aligned && tiles_ok;
   if (g_gemm_path == 1) use_tma = false;
-  if (g_gemm_path == 2 && !use_tma) return fail(LA_ERR_INVALID, "la_gemm_f64: TMA path forced but operands are unaligned");
+  if (g_gemm_path >= 2 && !use_tma) return fail(LA_ERR_INVALID, "la_gemm_f64: TMA path forced but operands are unaligned");
   if (!use_tma) return gemm_simt<double>(A, lda, B, ldb, C, ldc, m, k, n, mode, st);
 
   CUtensorMap tmA, tmB;
@@ -239,11 +263,30 @@ int gemm_f64_dev(const double* A, size_t lda, const double* B, size_t ldb, doubl
                               CU_TENSOR_MAP_SWIZZLE_128B));
   LA_TRY(encode_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, B, n, k, ldb * 8, 16, BK,
                               CU_TENSOR_MAP_SWIZZLE_128B));
-  switch (mode) {
-    case LA_GEMM_ASSIGN: return launch_tma<LA_GEMM_ASSIGN>(tmA, tmB, C, ldc, (int)m, (int)n, (int)k, st);
-    case LA_GEMM_SUB: return launch_tma<LA_GEMM_SUB>(tmA, tmB, C, ldc, (int)m, (int)n, (int)k, st);
-    default: return launch_tma<LA_GEMM_ADD>(tmA, tmB, C, ldc, (int)m, (int)n, (int)k, st);
-  }
+  // shallow K: the C tile traffic of the epilogue is a first-order cost -> two smaller CTAs per SM overlap it
+  bool narrow = k <= SHALLOW_K;
+  if (g_gemm_path == 3) narrow = true;
+  if (g_gemm_path == 4) narrow = false;
+  return narrow ? launch_tma_mode<64>(mode, tmA, tmB, C, ldc, (int)m, (int)n, (int)k, st)
+                : launch_tma_mode<128>(mode, tmA, tmB, C, ldc, (int)m, (int)n, (int)k, st);
+}
+
+// Tensor kernel regardless of problem size (the LU driver needs its in-place-safe tile structure: with m <= 128 there
+// is one tile row and every CTA consumes its whole column block of B before the epilogue writes C == B).
+int gemm_f64_tensor(const double* A, size_t lda, const double* B, size_t ldb, double* C, size_t ldc, size_t m, size_t k,
+                    size_t n, int mode, cudaStream_t st) {
+  const bool aligned = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0) &&
+                       lda % 2 == 0 && ldb % 2 == 0 && ldc % 2 == 0;
+  if (!aligned || m == 0 || n == 0 || k == 0)
+    return fail(LA_ERR_INVALID, "internal: tensor GEMM requested for operands that are not TMA-addressable");
+  CUtensorMap tmA, tmB;
+  LA_TRY(encode_tensor_map_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, A, k, m, lda * 8, BK, BM,
+                              CU_TENSOR_MAP_SWIZZLE_128B));
+  LA_TRY(encode_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, B, n, k, ldb * 8, 16, BK,
+                              CU_TENSOR_MAP_SWIZZLE_128B));
+  const bool narrow = (k <= SHALLOW_K && g_gemm_path != 4) || g_gemm_path == 3;
+  return narrow ? launch_tma_mode<64>(mode, tmA, tmB, C, ldc, (int)m, (int)n, (int)k, st)
+                : launch_tma_mode<128>(mode, tmA, tmB, C, ldc, (int)m, (int)n, (int)k, st);
 }
 
 template <>

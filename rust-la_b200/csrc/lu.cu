@@ -24,6 +24,8 @@
 #include <float.h>
 #include <limits.h>
 
+#include <type_traits>
+
 #include "la_common.cuh"
 
 namespace la {
@@ -345,17 +347,20 @@ template <typename T>
 __global__ void lu_perm_kernel(void* ws_base, int G, int j0, int jb, uint64_t* __restrict__ piv, int* __restrict__ sign) {
   __shared__ int pos[MAX_MOVES];
   __shared__ int src[MAX_MOVES];
+  __shared__ int ipiv_s[MAX_NB];
+  __shared__ uint64_t pold[MAX_MOVES];
   const WsView<T> ws = ws_view<T>(ws_base, G);
   const int lane = threadIdx.x;
   for (int i = lane; i < jb; i += 32) {
     pos[i] = j0 + i;
     src[i] = j0 + i;
+    ipiv_s[i] = ws.hdr->ipiv[i];
   }
   __syncwarp();
   int count = jb;
   int flips = 0;
   for (int c = 0; c < jb; ++c) {
-    const int p = ws.hdr->ipiv[c];
+    const int p = ipiv_s[c];
     if (p == j0 + c) continue;  // warp-uniform
     ++flips;
     int k;
@@ -385,14 +390,10 @@ __global__ void lu_perm_kernel(void* ws_base, int G, int j0, int jb, uint64_t* _
       const int t = src[c];
       src[c] = src[k];
       src[k] = t;
-      // reference bookkeeping, lu.rs:147-151
-      const uint64_t tp = piv[p];
-      piv[p] = piv[j0 + c];
-      piv[j0 + c] = tp;
     }
     __syncwarp();
   }
-  // compact the rows that actually move
+  // compact the rows that actually move; `piv` is permuted exactly like a matrix column (lu.rs:147-149)
   int nm = 0;
   for (int base = 0; base < count; base += 32) {
     const int i = base + lane;
@@ -402,12 +403,16 @@ __global__ void lu_perm_kernel(void* ws_base, int G, int j0, int jb, uint64_t* _
       const int slot = nm + __popc(mask & ((1u << lane) - 1));
       ws.hdr->move_dst[slot] = pos[i];
       ws.hdr->move_src[slot] = src[i];
+      pold[slot] = piv[src[i]];
     }
     nm += __popc(mask);
+    __syncwarp();
   }
+  __syncwarp();
+  for (int i = lane; i < nm; i += 32) piv[ws.hdr->move_dst[i]] = pold[i];
   if (lane == 0) {
     ws.hdr->n_moves = nm;
-    if (flips & 1) *sign = !*sign;
+    if (flips & 1) *sign = !*sign;  // pospivsign flips once per interchange (lu.rs:151)
   }
 }
 
@@ -415,22 +420,100 @@ __global__ void lu_perm_kernel(void* ws_base, int G, int j0, int jb, uint64_t* _
 // 3. apply the net permutation to a column range [col0, col1) (left of the panel)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SWAP_W = 32;  // columns per CTA strip
+// Columns [col0, col1) EXCLUDING the panel's own columns [skip0, skip1) (already interchanged inside the panel kernel).
 template <typename T>
-__global__ void __launch_bounds__(256) lu_swap_kernel(T* __restrict__ A, size_t ld, int col0, int col1,
-                                                      const void* ws_base, int G) {
+__global__ void __launch_bounds__(256) lu_swap_kernel(T* __restrict__ A, size_t ld, int col0, int col1, int skip0,
+                                                      int skip1, const void* ws_base, int G) {
   extern __shared__ __align__(16) unsigned char swap_smem[];
   T(*stage)[SWAP_W] = reinterpret_cast<T(*)[SWAP_W]>(swap_smem);  // [MAX_MOVES][SWAP_W]
+  __shared__ int mdst[MAX_MOVES];
+  __shared__ int msrc[MAX_MOVES];
   const WsView<T> ws = ws_view<T>(const_cast<void*>(ws_base), G);
   const int nm = ws.hdr->n_moves;
   if (nm == 0) return;
+  for (int i = threadIdx.x; i < nm; i += blockDim.x) {
+    mdst[i] = ws.hdr->move_dst[i];
+    msrc[i] = ws.hdr->move_src[i];
+  }
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col = col0 + blockIdx.x * SWAP_W + lane;
+  int col = col0 + blockIdx.x * SWAP_W + lane;
+  if (col >= skip0) col += skip1 - skip0;
   const bool ok = col < col1;
   for (int i = warp; i < nm; i += 8)
-    if (ok) stage[i][lane] = A[(size_t)ws.hdr->move_src[i] * ld + col];
+    if (ok) stage[i][lane] = A[(size_t)msrc[i] * ld + col];
   __syncthreads();
   for (int i = warp; i < nm; i += 8)
-    if (ok) A[(size_t)ws.hdr->move_dst[i] * ld + col] = stage[i][lane];
+    if (ok) A[(size_t)mdst[i] * ld + col] = stage[i][lane];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3b. W = L11^-1 for the jb x jb unit-lower-triangular diagonal block (one CTA).  Multi-panel factorisations compute
+//     U12 = L11^-1 * A12 as W * A12 on the DMMA GEMM instead of a latency-bound substitution.
+//     Blocked: invert the 32 x 32 diagonal blocks by substitution (one thread per column), then fill the blocks below
+//     the diagonal, distance by distance: W_ij = -W_ii * sum_{k=j}^{i-1} L_ik * W_kj.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int IB = 32;
+constexpr int INVL_LD = MAX_NB + 1;
+template <typename T>
+__global__ void __launch_bounds__(256) lu_invl_kernel(const T* __restrict__ A, size_t ld, int j0, int jb,
+                                                      T* __restrict__ W /* [MAX_NB][MAX_NB] */) {
+  // One padded square in shared memory holds both operands: the lower triangle (with diagonal) is W, the strictly
+  // upper triangle is L11 transposed (L[i][k], k < i, lives at SQ[k][i]).  Products in flight use a separate scratch.
+  extern __shared__ __align__(16) unsigned char invl_smem[];
+  T(*SQ)[INVL_LD] = reinterpret_cast<T(*)[INVL_LD]>(invl_smem);
+  T* scratch = reinterpret_cast<T*>(invl_smem) + (size_t)MAX_NB * INVL_LD;  // [<= 3][IB][IB]
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < MAX_NB * MAX_NB; idx += blockDim.x) {
+    const int i = idx / MAX_NB, k = idx - i * MAX_NB;
+    if (k < i) {
+      SQ[k][i] = (i < jb) ? A[(size_t)(j0 + i) * ld + j0 + k] : (T)0;  // L^T into the upper triangle
+      SQ[i][k] = (T)0;
+    } else if (k == i) {
+      SQ[i][i] = (T)0;
+    }
+  }
+  __syncthreads();
+  auto Lat = [&](int i, int k) -> T { return SQ[k][i]; };  // L[i][k], k < i
+  const int nblk = (jb + IB - 1) / IB;
+  // diagonal blocks: thread (b, j) solves L_bb * w = e_j by forward substitution
+  if (tid < MAX_NB) {
+    const int b = tid / IB, j = tid % IB, o = b * IB;
+    if (o + j < jb) {
+      SQ[o + j][o + j] = (T)1;
+      for (int i = j + 1; i < IB && o + i < jb; ++i) {
+        T acc = (T)0;
+        for (int k = j; k < i; ++k) acc += Lat(o + i, o + k) * SQ[o + k][o + j];
+        SQ[o + i][o + j] = -acc;
+      }
+    }
+  }
+  __syncthreads();
+  for (int d = 1; d < nblk; ++d) {
+    const int pairs = nblk - d;  // blocks (i, j) = (d + pr, pr)
+    // phase 1: T_ij = sum_{k=j}^{i-1} L_ik * W_kj
+    for (int e = tid; e < pairs * IB * IB; e += blockDim.x) {
+      const int pr = e / (IB * IB), r = (e / IB) % IB, c = e % IB;
+      const int i = d + pr, j = pr;
+      T acc = (T)0;
+      for (int kk = j * IB; kk < i * IB; ++kk) acc += Lat(i * IB + r, kk) * SQ[kk][j * IB + c];
+      scratch[e] = acc;
+    }
+    __syncthreads();
+    // phase 2: W_ij = -W_ii * T_ij
+    for (int e = tid; e < pairs * IB * IB; e += blockDim.x) {
+      const int pr = e / (IB * IB), r = (e / IB) % IB, c = e % IB;
+      const int i = d + pr, j = pr;
+      T acc = (T)0;
+      for (int kk = 0; kk <= r; ++kk) acc += SQ[i * IB + r][i * IB + kk] * scratch[pr * IB * IB + kk * IB + c];
+      SQ[i * IB + r][j * IB + c] = -acc;
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < MAX_NB * MAX_NB; idx += blockDim.x) {
+    const int i = idx / MAX_NB, k = idx - i * MAX_NB;
+    W[idx] = (k <= i && i < jb) ? SQ[i][k] : (T)0;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -504,6 +587,31 @@ __global__ void lu_init_piv_kernel(uint64_t* __restrict__ piv, int m, int* __res
 // ---------------------------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------------------------
+namespace {
+// Per host thread and device: the look-ahead stream (highest priority) and the two events that fence it.
+struct LuSide {
+  cudaStream_t sp = nullptr;
+  cudaEvent_t e1 = nullptr, e2 = nullptr;
+};
+int lu_side(int device, LuSide** out) {
+  static thread_local LuSide side[64];
+  LA_REQUIRE(device >= 0 && device < 64, "device ordinal out of range");
+  LuSide& s = side[device];
+  if (!s.sp) {
+    int lo = 0, hi = 0;
+    LA_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    LA_CUDA_TRY(cudaStreamCreateWithPriority(&s.sp, cudaStreamNonBlocking, hi));
+    LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e1, cudaEventDisableTiming));
+    LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e2, cudaEventDisableTiming));
+  }
+  *out = &s;
+  return LA_OK;
+}
+}  // namespace
+
+int gemm_f64_tensor(const double* A, size_t lda, const double* B, size_t ldb, double* C, size_t ldc, size_t m, size_t k,
+                    size_t n, int mode, cudaStream_t st);  // gemm_f64.cu: TMA/DMMA kernel regardless of size
+
 template <typename T>
 int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, cudaStream_t st) {
   const DeviceCtx* ctx;
@@ -527,9 +635,15 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
     return fail(LA_ERR_UNSUPPORTED, "la_lu_factor: %d rows exceed the shared-memory panel capacity of %d SMs", M, sms);
   // single-panel factorisations run the bit-exact (deferred subtraction) panel when twice the panel fits
   const bool exact = kmin <= nb && (size_t)2 * rpc_first * kmin * sizeof(T) <= PANEL_SMEM_BUDGET;
+  // multi-panel fp64 on TMA-addressable storage: look-ahead pipeline with U12 = inv(L11) * A12 on the DMMA GEMM
+  const bool fast = std::is_same<T, double>::value && kmin > nb && (N % 2 == 0) && ((uintptr_t)LU % 16 == 0) &&
+                    (kmin % 2 == 0 || kmin == N);
 
   void* ws_base = nullptr;
   LA_TRY(scratch_get(ctx->device, 8, ws_bytes<T>(sms), &ws_base));
+  void* w_base = nullptr;
+  LA_TRY(scratch_get(ctx->device, 11, sizeof(T) * MAX_NB * MAX_NB, &w_base));
+  T* W = (T*)w_base;
   LA_CUDA_TRY(cudaFuncSetAttribute(lu_panel_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)PANEL_SMEM_BUDGET + 2048));
   LA_CUDA_TRY(cudaFuncSetAttribute(lu_panel_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -537,43 +651,101 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
 
   const int SWAP_SMEM = (int)(sizeof(T) * MAX_MOVES * SWAP_W);
   const int TRSM_SMEM = (int)(sizeof(T) * 3 * MAX_NB * TRSM_W);
+  const int INVL_SMEM = (int)(sizeof(T) * ((size_t)MAX_NB * INVL_LD + 3 * IB * IB));
   LA_CUDA_TRY(cudaFuncSetAttribute(lu_swap_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWAP_SMEM));
   LA_CUDA_TRY(cudaFuncSetAttribute(lu_swap_trsm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM));
+  LA_CUDA_TRY(cudaFuncSetAttribute(lu_invl_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, INVL_SMEM));
 
   lu_init_piv_kernel<T><<<(M + 255) / 256, 256, 0, st>>>(piv_dev, M, sign_dev);
   LA_CUDA_TRY(cudaGetLastError());
 
-  for (int j0 = 0; j0 < kmin; j0 += nb) {
-    const int jb = (kmin - j0 < nb) ? (kmin - j0) : nb;
+  int G_cur = 1;
+  // panel factorisation + net permutation / piv bookkeeping of columns [j0, j0+jb) on stream s
+  auto launch_panel = [&](int j0, int jb, cudaStream_t s) -> int {
     const int R = M - j0;
     int rpc = (R + sms - 1) / sms;
     if (rpc < 8) rpc = 8;  // at least one row per warp; fewer, fuller CTAs make the barrier cheaper
     const int G = (R + rpc - 1) / rpc;
     const size_t smem = (size_t)rpc * jb * sizeof(T) * (exact ? 2 : 1);
-
-    LA_CUDA_TRY(cudaMemsetAsync(ws_base, 0, sizeof(unsigned int) * 4, st));
-    {
-      T* a = LU;
-      size_t ld = n;
-      int mm = M, jj0 = j0, jjb = jb, rr = rpc;
-      void* wsb = ws_base;
-      void* args[] = {&a, &ld, &mm, &jj0, &jjb, &rr, &wsb};
-      const void* fn = exact ? (const void*)lu_panel_kernel<T, true> : (const void*)lu_panel_kernel<T, false>;
-      LA_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PANEL_THREADS), args, smem, st));
-    }
-    lu_perm_kernel<T><<<1, 32, 0, st>>>(ws_base, G, j0, jb, piv_dev, sign_dev);
+    LA_CUDA_TRY(cudaMemsetAsync(ws_base, 0, sizeof(unsigned int) * 4, s));
+    T* a = LU;
+    size_t ld = n;
+    int mm = M, jj0 = j0, jjb = jb, rr = rpc;
+    void* wsb = ws_base;
+    void* args[] = {&a, &ld, &mm, &jj0, &jjb, &rr, &wsb};
+    const void* fn = exact ? (const void*)lu_panel_kernel<T, true> : (const void*)lu_panel_kernel<T, false>;
+    LA_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PANEL_THREADS), args, smem, s));
+    lu_perm_kernel<T><<<1, 32, 0, s>>>(ws_base, G, j0, jb, piv_dev, sign_dev);
     LA_CUDA_TRY(cudaGetLastError());
-    if (j0 > 0) {
-      lu_swap_kernel<T><<<(j0 + SWAP_W - 1) / SWAP_W, 256, SWAP_SMEM, st>>>(LU, n, 0, j0, ws_base, G);
-      LA_CUDA_TRY(cudaGetLastError());
+    G_cur = G;
+    return LA_OK;
+  };
+
+  if (!fast) {
+    // ---- plain right-looking loop (single panel / fp32 / odd leading dimension): substitution TRSM kernel ----
+    for (int j0 = 0; j0 < kmin; j0 += nb) {
+      const int jb = (kmin - j0 < nb) ? (kmin - j0) : nb;
+      LA_TRY(launch_panel(j0, jb, st));
+      if (j0 > 0) {
+        lu_swap_kernel<T><<<(j0 + SWAP_W - 1) / SWAP_W, 256, SWAP_SMEM, st>>>(LU, n, 0, j0, j0, j0, ws_base, G_cur);
+        LA_CUDA_TRY(cudaGetLastError());
+      }
+      const int c1 = j0 + jb;
+      if (c1 < N) {
+        lu_swap_trsm_kernel<T><<<(N - c1 + TRSM_W - 1) / TRSM_W, 256, TRSM_SMEM, st>>>(LU, n, j0, jb, c1, N, ws_base,
+                                                                                     G_cur);
+        LA_CUDA_TRY(cudaGetLastError());
+        if (c1 < M)
+          LA_TRY(gemm_dev<T>(LU + (size_t)c1 * n + j0, n, LU + (size_t)j0 * n + c1, n, LU + (size_t)c1 * n + c1, n,
+                             (size_t)(M - c1), (size_t)jb, (size_t)(N - c1), LA_GEMM_SUB, st));
+      }
     }
-    const int c1 = j0 + jb;
-    if (c1 < N) {
-      lu_swap_trsm_kernel<T><<<(N - c1 + TRSM_W - 1) / TRSM_W, 256, TRSM_SMEM, st>>>(LU, n, j0, jb, c1, N, ws_base, G);
+    return LA_OK;
+  }
+
+  // ---- look-ahead pipeline (fp64) ----
+  // Stream st: row interchanges, inv(L11), U12 = inv(L11)*A12 and the trailing update, next panel's columns FIRST.
+  // Stream sp (highest priority): the next panel's factorisation, overlapping the rest of the trailing update.  The
+  // cooperative panel CTAs (latency-bound, shared-memory resident) co-reside with the DMMA GEMM CTAs on the SMs.
+  if constexpr (std::is_same<T, double>::value) {
+    LuSide* side;
+    LA_TRY(lu_side(ctx->device, &side));
+    double* A = LU;
+    const size_t ld = n;
+    LA_TRY(launch_panel(0, nb, st));
+    for (int j0 = 0; j0 < kmin; j0 += nb) {
+      const int jb = (kmin - j0 < nb) ? (kmin - j0) : nb;
+      const int c1 = j0 + jb;
+      if (N - jb > 0) {
+        lu_swap_kernel<T><<<(N - jb + SWAP_W - 1) / SWAP_W, 256, SWAP_SMEM, st>>>(LU, n, 0, N, j0, c1, ws_base, G_cur);
+        LA_CUDA_TRY(cudaGetLastError());
+      }
+      if (c1 >= N) break;
+      lu_invl_kernel<T><<<1, 256, INVL_SMEM, st>>>(LU, n, j0, jb, W);
       LA_CUDA_TRY(cudaGetLastError());
-      if (c1 < M)
-        LA_TRY(gemm_dev<T>(LU + (size_t)c1 * n + j0, n, LU + (size_t)j0 * n + c1, n, LU + (size_t)c1 * n + c1, n,
-                           (size_t)(M - c1), (size_t)jb, (size_t)(N - c1), LA_GEMM_SUB, st));
+      const double* L21 = A + (size_t)c1 * ld + j0;
+      auto trsm_update = [&](int cb, int ce) -> int {  // columns [cb, ce)
+        double* U12 = A + (size_t)j0 * ld + cb;
+        LA_TRY(gemm_f64_tensor(W, MAX_NB, U12, ld, U12, ld, (size_t)jb, (size_t)jb, (size_t)(ce - cb), LA_GEMM_ASSIGN,
+                               st));  // in place: one tile row, every CTA reads its whole column block first
+        if (c1 < M)
+          LA_TRY(gemm_f64_tensor(L21, ld, U12, ld, A + (size_t)c1 * ld + cb, ld, (size_t)(M - c1), (size_t)jb,
+                                 (size_t)(ce - cb), LA_GEMM_SUB, st));
+        return LA_OK;
+      };
+      if (c1 < kmin) {
+        const int nb2 = (kmin - c1 < nb) ? (kmin - c1) : nb;
+        const int c2 = c1 + nb2;
+        LA_TRY(trsm_update(c1, c2));  // the next panel's columns first
+        LA_CUDA_TRY(cudaEventRecord(side->e1, st));
+        LA_CUDA_TRY(cudaStreamWaitEvent(side->sp, side->e1, 0));
+        LA_TRY(launch_panel(c1, nb2, side->sp));
+        LA_CUDA_TRY(cudaEventRecord(side->e2, side->sp));
+        if (c2 < N) LA_TRY(trsm_update(c2, N));  // overlaps the panel on sp
+        LA_CUDA_TRY(cudaStreamWaitEvent(st, side->e2, 0));
+      } else {
+        LA_TRY(trsm_update(c1, N));
+      }
     }
   }
   return LA_OK;
