@@ -17,6 +17,11 @@
 // bank-conflict free per quarter warp, every load is 16 bytes, and each thread ends up owning 4 CONSECUTIVE output
 // columns (32 contiguous bytes per row in the epilogue).  Rows inside an 8-row MMA tile are permuted
 // (g -> (g>>1)|((g&1)<<2)) for the same reason.
+#include <stdlib.h>
+
+#ifndef LA_GEMM_VARIANT
+#define LA_GEMM_VARIANT 0
+#endif
 #include "la_common.cuh"
 
 namespace la {
@@ -27,21 +32,19 @@ constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 8;  // 16 KiB: 128 rows x 128 B
 constexpr int B_BOX_BYTES = BK * 16 * 8;    // 2 KiB: [16 k-rows x 128 B] holds 16 columns of B
 // Two tile configurations of the same kernel:
-//   BN = 128, 8 consumer warps, 1 CTA/SM : least L2->smem traffic per flop; used for deep K (Mul at large n).
-//   BN =  64, 4 consumer warps, 2 CTA/SM : the epilogue of one CTA (C tile read-modify-write, HBM bound) overlaps the
-//                                           main loop of the other; used for shallow K (the LU trailing update, K = nb).
-// Each configuration adds one producer warpgroup (only its first lane works).  The register file is split per SM
-// sub-partition (16K regs each); the CTA launches at an even split and setmaxnreg moves registers from the producer
-// warpgroup to the consumers (128 accumulator registers + fragments per consumer thread):
-//   BN=128: 12 warps launch at 168 -> consumers 232, producer 40   (2*232 + 40 = 504 = 3*168)
-//   BN= 64:  8 warps launch at 128 -> consumers 216, producer 40   (216 + 40 = 256 = 2*128), twice per SM
+//   BN = 128, 8 warps, 1 CTA/SM : least L2->smem traffic per flop; used for deep K (Mul at large n).
+//   BN =  64, 4 warps, 2 CTA/SM : the epilogue of one CTA (C tile read-modify-write, HBM bound) overlaps the main loop
+//                                 of the other; used for shallow K (the LU trailing update, K = nb).
+// Every warp is a consumer (64 x 32 warp tile, 128 accumulator registers per thread).  The TMA producer role is folded
+// into the consumers: the lane 0 of warp (p mod #warps) issues the loads of k-tile p, STAGES-1 tiles ahead of the
+// math.  (An earlier version used a dedicated producer warpgroup with setmaxnreg register donation; CTAs of that
+// kernel produced corrupted tiles whenever CTAs of ANOTHER kernel were co-resident on the SM -- reproducible with
+// tools/overlap_stress.py -- which rules it out for the LU look-ahead, where the panel kernel shares the SMs.)
 template <int BN_>
 struct TileCfg {
-  static constexpr int CONSUMER_WARPS = BN_ / 16;                 // 2 (M) x BN/32 (N) warps of 64 x 32
-  static constexpr int THREADS = (CONSUMER_WARPS + 4) * 32;
+  static constexpr int WARPS = BN_ / 16;                          // 2 (M) x BN/32 (N) warps of 64 x 32
+  static constexpr int THREADS = WARPS * 32;
   static constexpr int CTAS_PER_SM = BN_ == 128 ? 1 : 2;
-  static constexpr int CONSUMER_REGS = BN_ == 128 ? 232 : 216;
-  static constexpr int PRODUCER_REGS = 40;
   static constexpr int B_STAGE_BYTES = BK * BN_ * 8;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;  // + barriers + alignment slack
@@ -50,26 +53,27 @@ constexpr double SMALL_GEMM_MNK = 128.0 * 128.0 * 128.0;  // <= this many multip
 constexpr size_t SHALLOW_K = 1024;
 constexpr int GROUP_M = 16;  // tile rasterisation: GROUP_M tile-rows share each B tile-column while it is hot in L2
 
-template <int MODE>
-__device__ __forceinline__ void store_pair(double* __restrict__ C, size_t ldc, int row, int col, int N, double v0,
-                                           double v1) {
-  double* p = C + (size_t)row * ldc + col;
-  if (col + 1 < N) {
-    double2 out;
-    if (MODE == LA_GEMM_ASSIGN) {
-      out = make_double2(v0, v1);
-    } else {
-      double2 old = *reinterpret_cast<const double2*>(p);
-      out = (MODE == LA_GEMM_SUB) ? make_double2(old.x - v0, old.y - v1) : make_double2(old.x + v0, old.y + v1);
-    }
-    *reinterpret_cast<double2*>(p) = out;
-  } else if (col < N) {
-    if (MODE == LA_GEMM_ASSIGN)
-      p[0] = v0;
-    else if (MODE == LA_GEMM_SUB)
-      p[0] = p[0] - v0;
-    else
-      p[0] = p[0] + v0;
+// Epilogue helpers.  A lane owns pairs of adjacent columns; `col` is even, so a pair is 16-byte aligned (ldc is even).
+__device__ __forceinline__ double2 load_pair(const double* __restrict__ C, size_t ldc, int row, int col, int M, int N) {
+  double2 v = make_double2(0.0, 0.0);
+  if (row < M) {
+    const double* p = C + (size_t)row * ldc + col;
+    // L2-only loads (ld.global.cg): C was written by other kernels, possibly while a concurrent grid (the LU look-ahead
+    // panel) kept this SM's L1 alive across the kernel boundary; the data is streamed once anyway.
+    if (col + 1 < N)
+      v = __ldcg(reinterpret_cast<const double2*>(p));
+    else if (col < N)
+      v.x = __ldcg(p);
+  }
+  return v;
+}
+__device__ __forceinline__ void store_pair(double* __restrict__ C, size_t ldc, int row, int col, int M, int N, double2 v) {
+  if (row < M) {
+    double* p = C + (size_t)row * ldc + col;
+    if (col + 1 < N)
+      *reinterpret_cast<double2*>(p) = v;
+    else if (col < N)
+      p[0] = v.x;
   }
 }
 
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(TileCfg<BN>::THREADS, TileCfg<BN>::CTAS_PER_SM
 gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     double* __restrict__ C, size_t ldc, int M, int N, int K, int tiles_m, int tiles_n) {
   using Cfg = TileCfg<BN>;
-  constexpr int CONSUMER_WARPS = Cfg::CONSUMER_WARPS;
+  constexpr int WARPS = Cfg::WARPS;
   constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr int WARPS_N = BN / 32;
   extern __shared__ uint8_t smem_raw[];
@@ -103,7 +107,7 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], CONSUMER_WARPS);
+      mbar_init(&empty[s], WARPS);
     }
     mbar_fence_init();
   }
@@ -112,30 +116,24 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int ktiles = (K + BK - 1) / BK;
   const uint32_t smem_base = smem_u32(smem);
 
-  if (warp >= CONSUMER_WARPS) {
-    // ===== TMA producer warpgroup: one elected lane works, the rest only donate registers =====
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::PRODUCER_REGS));
-    if (warp == CONSUMER_WARPS && lane == 0) {
-      tma_prefetch_desc(&tmA);
-      tma_prefetch_desc(&tmB);
-      for (int kt = 0; kt < ktiles; ++kt) {
-        const int s = kt % STAGES;
-        const uint32_t ph = (kt / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* sA = smem + s * STAGE_BYTES;
-        uint8_t* sB = sA + A_STAGE_BYTES;
-        mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-        tma_load_2d(sA, &tmA, &full[s], kt * BK, m0);  // box: 16 k (inner) x 128 rows; OOB -> 0
+  // TMA loads of k-tile p into stage p % STAGES (one elected lane).  A: box 16 k (inner) x 128 rows; B: BN/16 boxes
+  // of 16 n (inner) x 16 k-rows.  Out-of-bounds elements are zero-filled and still counted in the transaction bytes.
+  auto issue_tile = [&](int p) {
+    const int s = p % STAGES;
+    uint8_t* sA = smem + s * STAGE_BYTES;
+    uint8_t* sB = sA + A_STAGE_BYTES;
+    mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+    tma_load_2d(sA, &tmA, &full[s], p * BK, m0);
 #pragma unroll
-        for (int j = 0; j < BN / 16; ++j)              // box: 16 n (inner) x 16 k-rows
-          tma_load_2d(sB + j * B_BOX_BYTES, &tmB, &full[s], n0 + j * 16, kt * BK);
-      }
-    }
-    return;
+    for (int j = 0; j < BN / 16; ++j) tma_load_2d(sB + j * B_BOX_BYTES, &tmB, &full[s], n0 + j * 16, p * BK);
+  };
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int p = 0; p < STAGES - 1 && p < ktiles; ++p) issue_tile(p);  // fresh stages: nothing to wait for
   }
 
-  // ===== consumers: 2 (M) x BN/32 (N) warps, warp tile 64 x 32 =====
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::CONSUMER_REGS));
+  // ===== 2 (M) x BN/32 (N) warps, warp tile 64 x 32 =====
   const int wm = warp / WARPS_N;
   const int wn = warp % WARPS_N;
   const int g = lane >> 2;
@@ -163,47 +161,99 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       b_off[s][h] = (uint32_t)A_STAGE_BYTES + (uint32_t)(wn * 2) * B_BOX_BYTES + (uint32_t)(h * 8 + 2 * t + s) * 128u +
                     (uint32_t)((g ^ (2 * t + s)) << 4);
 
+  // Fragments are double-buffered in registers: while the DMMAs of one 8-wide k-chunk run, the 12 LDS.128 of the next
+  // chunk are already in flight into the other buffer, so no fragment register is rewritten within ~1000 cycles of its
+  // last use and every load has a whole chunk of math to land.
+  double2 af[2][8];
+  double2 bf[2][2][2];
+  auto load_frags = [&](int buf, uint32_t st, int h) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) af[buf][i] = lds_f64x2(st + a_row + i * 1024 + a_chunk[h]);
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int ss = 0; ss < 2; ++ss) bf[buf][j][ss] = lds_f64x2(st + b_off[ss][h] + j * B_BOX_BYTES);
+  };
+  auto mma_chunk = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        dmma884(acc[i][j][0], acc[i][j][2], af[buf][i].x, bf[buf][j][0].x);  // even k, even columns
+        dmma884(acc[i][j][1], acc[i][j][3], af[buf][i].x, bf[buf][j][0].y);  // even k, odd columns
+        dmma884(acc[i][j][0], acc[i][j][2], af[buf][i].y, bf[buf][j][1].x);  // odd k, even columns
+        dmma884(acc[i][j][1], acc[i][j][3], af[buf][i].y, bf[buf][j][1].y);  // odd k, odd columns
+      }
+  };
+
+  mbar_wait(&full[0], 0);
+  load_frags(0, smem_base, 0);
   for (int kt = 0; kt < ktiles; ++kt) {
-    const int s = kt % STAGES;
-    const uint32_t ph = (kt / STAGES) & 1;
-    mbar_wait(&full[s], ph);
-    const uint32_t st = smem_base + (uint32_t)s * STAGE_BYTES;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      double2 af[8];
-      double2 bf[2][2];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) af[i] = lds_f64x2(st + a_row + i * 1024 + a_chunk[h]);
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int ss = 0; ss < 2; ++ss)
-          bf[j][ss] = lds_f64x2(st + b_off[ss][h] + j * B_BOX_BYTES);
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          dmma884(acc[i][j][0], acc[i][j][2], af[i].x, bf[j][0].x);  // even k, even columns
-          dmma884(acc[i][j][1], acc[i][j][3], af[i].x, bf[j][0].y);  // even k, odd columns
-          dmma884(acc[i][j][0], acc[i][j][2], af[i].y, bf[j][1].x);  // odd k, even columns
-          dmma884(acc[i][j][1], acc[i][j][3], af[i].y, bf[j][1].y);  // odd k, odd columns
-        }
+    // producer duty: k-tile p = kt + STAGES - 1 goes into the stage that k-tile kt - 1 occupied; its issuer first waits
+    // until every warp has released that stage
+    {
+      const int p = kt + STAGES - 1;
+      if (p < ktiles && (p % WARPS) == warp && lane == 0) {
+        if (p >= STAGES) mbar_wait(&empty[p % STAGES], ((p / STAGES) - 1) & 1);
+        issue_tile(p);
+      }
+      __syncwarp();
     }
+    const int s = kt % STAGES;
+    const uint32_t st = smem_base + (uint32_t)s * STAGE_BYTES;
+    load_frags(1, st, 1);   // second chunk of this k-tile
+    mma_chunk(0);
+    if (kt + 1 < ktiles) {  // first chunk of the next k-tile
+      const int s1 = (kt + 1) % STAGES;
+      mbar_wait(&full[s1], ((kt + 1) / STAGES) & 1);
+      load_frags(0, smem_base + (uint32_t)s1 * STAGE_BYTES, 0);
+    }
+    mma_chunk(1);
+    // every LDS of stage s was issued a chunk ago and its result has been consumed by the DMMAs above
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
   }
 
-  // ===== epilogue: each lane owns 4 consecutive columns of 8 rows per n-block =====
+  // ===== epilogue: each lane owns 4 consecutive columns (two 16-byte pairs) of 8 rows per 16-column block =====
+  // For C -= P / C += P the old values are fetched in batches of 4 row-tiles (16 independent 16-byte loads in flight per
+  // lane) BEFORE any store of the batch: a load-store-load chain would serialise 32 HBM round trips per tile.
+  const int row0 = m0 + wm * 64 + x;
+  const int col0 = n0 + wn * 32 + 4 * t;
+  if (MODE == LA_GEMM_ASSIGN) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = m0 + wm * 64 + i * 8 + x;
-    if (row < M) {
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int col = n0 + wn * 32 + j * 16 + 4 * t;
-        store_pair<MODE>(C, ldc, row, col, N, acc[i][j][0], acc[i][j][1]);
-        store_pair<MODE>(C, ldc, row, col + 2, N, acc[i][j][2], acc[i][j][3]);
+        store_pair(C, ldc, row0 + i * 8, col0 + j * 16, M, N, make_double2(acc[i][j][0], acc[i][j][1]));
+        store_pair(C, ldc, row0 + i * 8, col0 + j * 16 + 2, M, N, make_double2(acc[i][j][2], acc[i][j][3]));
       }
+  } else {
+#pragma unroll
+    for (int ib = 0; ib < 8; ib += 4) {
+      double2 old[4][2][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          old[i][j][0] = load_pair(C, ldc, row0 + (ib + i) * 8, col0 + j * 16, M, N);
+          old[i][j][1] = load_pair(C, ldc, row0 + (ib + i) * 8, col0 + j * 16 + 2, M, N);
+        }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const double* a4 = acc[ib + i][j];
+          double2 o0 = old[i][j][0], o1 = old[i][j][1];
+          if (MODE == LA_GEMM_SUB) {
+            o0 = make_double2(o0.x - a4[0], o0.y - a4[1]);
+            o1 = make_double2(o1.x - a4[2], o1.y - a4[3]);
+          } else {
+            o0 = make_double2(o0.x + a4[0], o0.y + a4[1]);
+            o1 = make_double2(o1.x + a4[2], o1.y + a4[3]);
+          }
+          store_pair(C, ldc, row0 + (ib + i) * 8, col0 + j * 16, M, N, o0);
+          store_pair(C, ldc, row0 + (ib + i) * 8, col0 + j * 16 + 2, M, N, o1);
+        }
     }
   }
 }
@@ -214,10 +264,13 @@ template <int MODE, int BN>
 int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, size_t ldc, int M, int N, int K,
                cudaStream_t st) {
   using Cfg = TileCfg<BN>;
+  static const int extra_smem = getenv("LA_GEMM_EXTRA_SMEM") ? atoi(getenv("LA_GEMM_EXTRA_SMEM")) : 0;  // debug knob
   LA_CUDA_TRY(cudaFuncSetAttribute(gemm_f64_tma_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   Cfg::SMEM_BYTES));
+                                   Cfg::SMEM_BYTES + extra_smem));
+  LA_CUDA_TRY(cudaFuncSetAttribute(gemm_f64_tma_kernel<MODE, BN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
-  gemm_f64_tma_kernel<MODE, BN><<<tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, C, ldc, M, N, K,
+  gemm_f64_tma_kernel<MODE, BN><<<tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM_BYTES + extra_smem, st>>>(tmA, tmB, C, ldc, M, N, K,
                                                                                         tiles_m, tiles_n);
   LA_CUDA_TRY(cudaGetLastError());
   return LA_OK;

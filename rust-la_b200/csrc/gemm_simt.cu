@@ -93,6 +93,12 @@ int gemm_simt(const T* A, size_t lda, const T* B, size_t ldb, T* C, size_t ldc, 
               cudaStream_t st) {
   dim3 grid((unsigned)((n + TS - 1) / TS), (unsigned)((m + TS - 1) / TS));
   LA_REQUIRE(grid.y <= 65535, "la_gemm (generic kernel): more than 65535 row tiles");
+  LA_CUDA_TRY(cudaFuncSetAttribute(gemm_simt_kernel<T, LA_GEMM_ASSIGN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
+  LA_CUDA_TRY(cudaFuncSetAttribute(gemm_simt_kernel<T, LA_GEMM_SUB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
+  LA_CUDA_TRY(cudaFuncSetAttribute(gemm_simt_kernel<T, LA_GEMM_ADD>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
   switch (mode) {
     case LA_GEMM_ASSIGN:
       gemm_simt_kernel<T, LA_GEMM_ASSIGN><<<grid, TPB, 0, st>>>(A, lda, B, ldb, C, ldc, (int)m, (int)n, (int)k);

@@ -123,7 +123,11 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 }
 __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
   double2 v;
+#if defined(LA_GEMM_VARIANT) && LA_GEMM_VARIANT == 3
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+#else
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+#endif
   return v;
 }
 // D(8x8) += A(8x4, row) * B(4x8, col), fp64.  SASS: DMMA.8x8x4 (the only fp64 MMA shape sm_100a issues).

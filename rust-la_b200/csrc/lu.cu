@@ -23,6 +23,7 @@
 #include <cooperative_groups.h>
 #include <float.h>
 #include <limits.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -144,7 +145,7 @@ lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_pe
   // ---- load the CTA's rows of the panel into shared memory (row segments of jb contiguous elements) ----
   for (int idx = threadIdx.x; idx < nloc * jb; idx += PANEL_THREADS) {
     const int lr = idx / jb, c = idx - lr * jb;
-    rows[idx] = A[(size_t)(row_base + lr) * ld + j0 + c];
+    rows[idx] = __ldcg(&A[(size_t)(row_base + lr) * ld + j0 + c]);
     if (EXACT) sums[idx] = (T)0;
   }
   __syncthreads();
@@ -441,7 +442,7 @@ __global__ void __launch_bounds__(256) lu_swap_kernel(T* __restrict__ A, size_t 
   if (col >= skip0) col += skip1 - skip0;
   const bool ok = col < col1;
   for (int i = warp; i < nm; i += 8)
-    if (ok) stage[i][lane] = A[(size_t)msrc[i] * ld + col];
+    if (ok) stage[i][lane] = __ldcg(&A[(size_t)msrc[i] * ld + col]);
   __syncthreads();
   for (int i = warp; i < nm; i += 8)
     if (ok) A[(size_t)mdst[i] * ld + col] = stage[i][lane];
@@ -467,7 +468,7 @@ __global__ void __launch_bounds__(256) lu_invl_kernel(const T* __restrict__ A, s
   for (int idx = tid; idx < MAX_NB * MAX_NB; idx += blockDim.x) {
     const int i = idx / MAX_NB, k = idx - i * MAX_NB;
     if (k < i) {
-      SQ[k][i] = (i < jb) ? A[(size_t)(j0 + i) * ld + j0 + k] : (T)0;  // L^T into the upper triangle
+      SQ[k][i] = (i < jb) ? __ldcg(&A[(size_t)(j0 + i) * ld + j0 + k]) : (T)0;  // L^T into the upper triangle
       SQ[i][k] = (T)0;
     } else if (k == i) {
       SQ[i][i] = (T)0;
@@ -496,7 +497,8 @@ __global__ void __launch_bounds__(256) lu_invl_kernel(const T* __restrict__ A, s
       const int pr = e / (IB * IB), r = (e / IB) % IB, c = e % IB;
       const int i = d + pr, j = pr;
       T acc = (T)0;
-      for (int kk = j * IB; kk < i * IB; ++kk) acc += Lat(i * IB + r, kk) * SQ[kk][j * IB + c];
+      // W_jj is lower triangular: its entries above the diagonal are zero (that part of SQ holds L^T), so start at c
+      for (int kk = j * IB + c; kk < i * IB; ++kk) acc += Lat(i * IB + r, kk) * SQ[kk][j * IB + c];
       scratch[e] = acc;
     }
     __syncthreads();
@@ -556,10 +558,10 @@ lu_swap_trsm_kernel(T* __restrict__ A, size_t ld, int j0, int jb, int col0, int 
   const int no = n_out;
   // gather
   for (int i = warp; i < jb; i += 8) {
-    X[i][lane] = ok ? A[(size_t)top_src[i] * ld + col] : (T)0;
+    X[i][lane] = ok ? __ldcg(&A[(size_t)top_src[i] * ld + col]) : (T)0;
     S[i][lane] = (T)0;
   }
-  for (int i = warp; i < no; i += 8) stage[i][lane] = ok ? A[(size_t)out_src[i] * ld + col] : (T)0;
+  for (int i = warp; i < no; i += 8) stage[i][lane] = ok ? __ldcg(&A[(size_t)out_src[i] * ld + col]) : (T)0;
   __syncthreads();
   // rows that left the top block
   for (int i = warp; i < no; i += 8)
@@ -570,7 +572,7 @@ lu_swap_trsm_kernel(T* __restrict__ A, size_t ld, int j0, int jb, int col0, int 
   for (int k = 0; k < jb; ++k) {
     const T xk = sub_rn(X[k][lane], S[k][lane]);  // U[k][col], final
     if (warp == (k & 7) && ok) A[(size_t)(j0 + k) * ld + col] = xk;
-    for (int i = k + 1 + warp; i < jb; i += 8) S[i][lane] = add_rn(S[i][lane], mul_rn(__ldg(&L[(size_t)i * ld + k]), xk));
+    for (int i = k + 1 + warp; i < jb; i += 8) S[i][lane] = add_rn(S[i][lane], mul_rn(__ldcg(&L[(size_t)i * ld + k]), xk));
     __syncthreads();
   }
 }
@@ -636,8 +638,9 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
   // single-panel factorisations run the bit-exact (deferred subtraction) panel when twice the panel fits
   const bool exact = kmin <= nb && (size_t)2 * rpc_first * kmin * sizeof(T) <= PANEL_SMEM_BUDGET;
   // multi-panel fp64 on TMA-addressable storage: look-ahead pipeline with U12 = inv(L11) * A12 on the DMMA GEMM
+  static const int dbg = getenv("LA_LU_DEBUG") ? atoi(getenv("LA_LU_DEBUG")) : 0;  // 1: no look-ahead, 2: plain loop
   const bool fast = std::is_same<T, double>::value && kmin > nb && (N % 2 == 0) && ((uintptr_t)LU % 16 == 0) &&
-                    (kmin % 2 == 0 || kmin == N);
+                    (kmin % 2 == 0 || kmin == N) && dbg != 2;
 
   void* ws_base = nullptr;
   LA_TRY(scratch_get(ctx->device, 8, ws_bytes<T>(sms), &ws_base));
@@ -656,6 +659,16 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
   LA_CUDA_TRY(cudaFuncSetAttribute(lu_swap_trsm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM));
   LA_CUDA_TRY(cudaFuncSetAttribute(lu_invl_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, INVL_SMEM));
 
+  {
+    // every kernel of the pipeline prefers the maximum shared-memory carve-out, so co-resident kernels never ask an SM
+    // for a different L1/shared split
+    const void* fns[] = {(const void*)lu_panel_kernel<T, false>, (const void*)lu_panel_kernel<T, true>,
+                         (const void*)lu_perm_kernel<T>,         (const void*)lu_swap_kernel<T>,
+                         (const void*)lu_swap_trsm_kernel<T>,    (const void*)lu_invl_kernel<T>,
+                         (const void*)lu_init_piv_kernel<T>};
+    for (const void* f : fns)
+      LA_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  }
   lu_init_piv_kernel<T><<<(M + 255) / 256, 256, 0, st>>>(piv_dev, M, sign_dev);
   LA_CUDA_TRY(cudaGetLastError());
 
@@ -666,7 +679,8 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
     int rpc = (R + sms - 1) / sms;
     if (rpc < 8) rpc = 8;  // at least one row per warp; fewer, fuller CTAs make the barrier cheaper
     const int G = (R + rpc - 1) / rpc;
-    const size_t smem = (size_t)rpc * jb * sizeof(T) * (exact ? 2 : 1);
+    size_t smem = (size_t)rpc * jb * sizeof(T) * (exact ? 2 : 1);
+    if ((dbg == 6 || dbg == 9) && smem < 150 * 1024) smem = 150 * 1024;  // debug: too big to co-reside with a GEMM CTA
     LA_CUDA_TRY(cudaMemsetAsync(ws_base, 0, sizeof(unsigned int) * 4, s));
     T* a = LU;
     size_t ld = n;
@@ -674,10 +688,14 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
     void* wsb = ws_base;
     void* args[] = {&a, &ld, &mm, &jj0, &jjb, &rr, &wsb};
     const void* fn = exact ? (const void*)lu_panel_kernel<T, true> : (const void*)lu_panel_kernel<T, false>;
-    LA_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PANEL_THREADS), args, smem, s));
+    if (dbg == 8)
+      LA_CUDA_TRY(cudaLaunchKernel(fn, dim3(G), dim3(PANEL_THREADS), args, smem, s));  // debug: plain launch
+    else
+      LA_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PANEL_THREADS), args, smem, s));
+    G_cur = G;
+    if ((dbg == 7 || dbg == 9) && s != st) return LA_OK;  // debug: perm deferred to the main stream
     lu_perm_kernel<T><<<1, 32, 0, s>>>(ws_base, G, j0, jb, piv_dev, sign_dev);
     LA_CUDA_TRY(cudaGetLastError());
-    G_cur = G;
     return LA_OK;
   };
 
@@ -710,10 +728,13 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
   if constexpr (std::is_same<T, double>::value) {
     LuSide* side;
     LA_TRY(lu_side(ctx->device, &side));
+    cudaStream_t sp = dbg == 1 ? st : side->sp;
     double* A = LU;
     const size_t ld = n;
     LA_TRY(launch_panel(0, nb, st));
+    const int stop_iters = getenv("LA_LU_STOP") ? atoi(getenv("LA_LU_STOP")) : (1 << 30);  // debug: truncate the loop
     for (int j0 = 0; j0 < kmin; j0 += nb) {
+      if (j0 / nb >= stop_iters) break;
       const int jb = (kmin - j0 < nb) ? (kmin - j0) : nb;
       const int c1 = j0 + jb;
       if (N - jb > 0) {
@@ -737,12 +758,33 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
         const int nb2 = (kmin - c1 < nb) ? (kmin - c1) : nb;
         const int c2 = c1 + nb2;
         LA_TRY(trsm_update(c1, c2));  // the next panel's columns first
+        if (dbg == 5 && c2 < N) {  // debug: TRSM of the rest before the panel starts, only the update overlaps
+          double* U12r = A + (size_t)j0 * ld + c2;
+          LA_TRY(gemm_f64_tensor(W, MAX_NB, U12r, ld, U12r, ld, (size_t)jb, (size_t)jb, (size_t)(N - c2), LA_GEMM_ASSIGN, st));
+        }
         LA_CUDA_TRY(cudaEventRecord(side->e1, st));
-        LA_CUDA_TRY(cudaStreamWaitEvent(side->sp, side->e1, 0));
-        LA_TRY(launch_panel(c1, nb2, side->sp));
-        LA_CUDA_TRY(cudaEventRecord(side->e2, side->sp));
-        if (c2 < N) LA_TRY(trsm_update(c2, N));  // overlaps the panel on sp
+        LA_CUDA_TRY(cudaStreamWaitEvent(sp, side->e1, 0));
+        LA_TRY(launch_panel(c1, nb2, sp));
+        LA_CUDA_TRY(cudaEventRecord(side->e2, sp));
+        if (dbg == 3) LA_CUDA_TRY(cudaStreamWaitEvent(st, side->e2, 0));  // debug: two streams, no overlap
+        if (c2 < N) {
+          if (dbg == 4 || dbg == 5) {
+            double* U12r = A + (size_t)j0 * ld + c2;
+            if (dbg == 4) {  // debug: only the TRSM overlaps
+              LA_TRY(gemm_f64_tensor(W, MAX_NB, U12r, ld, U12r, ld, (size_t)jb, (size_t)jb, (size_t)(N - c2), LA_GEMM_ASSIGN, st));
+              LA_CUDA_TRY(cudaStreamWaitEvent(st, side->e2, 0));
+            }
+            LA_TRY(gemm_f64_tensor(L21, ld, U12r, ld, A + (size_t)c1 * ld + c2, ld, (size_t)(M - c1), (size_t)jb,
+                                   (size_t)(N - c2), LA_GEMM_SUB, st));
+          } else {
+            LA_TRY(trsm_update(c2, N));  // overlaps the panel on sp
+          }
+        }
         LA_CUDA_TRY(cudaStreamWaitEvent(st, side->e2, 0));
+        if (dbg == 7 || dbg == 9) {
+          lu_perm_kernel<T><<<1, 32, 0, st>>>(ws_base, G_cur, c1, nb2, piv_dev, sign_dev);
+          LA_CUDA_TRY(cudaGetLastError());
+        }
       } else {
         LA_TRY(trsm_update(c1, N));
       }

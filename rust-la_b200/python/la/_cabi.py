@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_PKG, "..", "..", "libla_b200.so"))
+LIB_PATH = os.environ.get("LA_B200_LIB") or os.path.normpath(os.path.join(_PKG, "..", "..", "libla_b200.so"))
 
 LA_OK, LA_ERR_INVALID, LA_ERR_CUDA, LA_ERR_NOMEM, LA_ERR_NO_DEVICE, LA_ERR_UNSUPPORTED = range(6)
 LA_GEMM_ASSIGN, LA_GEMM_SUB, LA_GEMM_ADD = 0, 1, 2
