@@ -80,8 +80,14 @@ __device__ __forceinline__ void store_pair(double* __restrict__ C, size_t ldc, i
 template <int MODE, int BN>
 __global__ void __launch_bounds__(TileCfg<BN>::THREADS, TileCfg<BN>::CTAS_PER_SM)
 gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    double* __restrict__ C, size_t ldc, int M, int N, int K, int tiles_m, int tiles_n) {
+                    double* __restrict__ C, size_t ldc, int M, int N, int K, int tiles_m, int tiles_n, int stagger_lo,
+                    int stagger_hi, unsigned stagger_ns) {
   using Cfg = TileCfg<BN>;
+  // Shallow-K launches run two CTAs per SM so that one CTA's epilogue (HBM-bound C tile read-modify-write) overlaps the
+  // other's main loop -- which only works if the two are out of phase.  CTAs launched together stay in lock step, so
+  // the second resident slot of the first wave starts half a tile late; every later CTA inherits the phase of the CTA
+  // whose slot it takes over.
+  if ((int)blockIdx.x >= stagger_lo && (int)blockIdx.x < stagger_hi) __nanosleep(stagger_ns);
   constexpr int WARPS = Cfg::WARPS;
   constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr int WARPS_N = BN / 32;
@@ -115,6 +121,15 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int ktiles = (K + BK - 1) / BK;
   const uint32_t smem_base = smem_u32(smem);
+
+  // C -= P / C += P: pull the C tile into L2 now so the epilogue's loads do not pay an HBM round trip
+  if (MODE != LA_GEMM_ASSIGN) {
+    constexpr int LINES_PER_ROW = BN * 8 / 128;
+    for (int idx = threadIdx.x; idx < BM * LINES_PER_ROW; idx += Cfg::THREADS) {
+      const int r = m0 + idx / LINES_PER_ROW, c = n0 + (idx % LINES_PER_ROW) * 16;
+      if (r < M && c < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(C + (size_t)r * ldc + c));
+    }
+  }
 
   // TMA loads of k-tile p into stage p % STAGES (one elected lane).  A: box 16 k (inner) x 128 rows; B: BN/16 boxes
   // of 16 n (inner) x 16 k-rows.  Out-of-bounds elements are zero-filled and still counted in the transaction bytes.
@@ -258,6 +273,7 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+int g_stagger = getenv("LA_GEMM_NO_STAGGER") ? 0 : 1;  // debug knob
 int g_gemm_path = 0;  // test hook: 0 auto, 1 SIMT, 2 TMA/DMMA (auto tile), 3 TMA/DMMA BN=64, 4 TMA/DMMA BN=128
 
 template <int MODE, int BN>
@@ -270,8 +286,18 @@ int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, size_t
   LA_CUDA_TRY(cudaFuncSetAttribute(gemm_f64_tma_kernel<MODE, BN>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                    cudaSharedmemCarveoutMaxShared));
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
-  gemm_f64_tma_kernel<MODE, BN><<<tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM_BYTES + extra_smem, st>>>(tmA, tmB, C, ldc, M, N, K,
-                                                                                        tiles_m, tiles_n);
+  const int ktiles = (K + BK - 1) / BK;
+  int stagger_lo = 0, stagger_hi = 0;
+  unsigned stagger_ns = 0;
+  if (Cfg::CTAS_PER_SM == 2 && ktiles <= 128 && g_stagger) {
+    const DeviceCtx* ctx;
+    LA_TRY(current_device_ctx(&ctx));
+    stagger_lo = ctx->sm_count;
+    stagger_hi = 2 * ctx->sm_count;
+    stagger_ns = (unsigned)(ktiles * 520 + 2000);  // ~half of (main loop at full DMMA rate + prologue + epilogue)
+  }
+  gemm_f64_tma_kernel<MODE, BN><<<tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM_BYTES + extra_smem, st>>>(
+      tmA, tmB, C, ldc, M, N, K, tiles_m, tiles_n, stagger_lo, stagger_hi, stagger_ns);
   LA_CUDA_TRY(cudaGetLastError());
   return LA_OK;
 }

@@ -41,56 +41,105 @@ constexpr size_t PANEL_SMEM_BUDGET = 200 * 1024;
 // Global workspace of one factorisation (per stream use; lives in the scratch pool).
 // Exchange rows carry 2*MAX_NB values: the row itself and (EXACT mode) its deferred-subtraction sums.
 constexpr int XROW = 2 * MAX_NB;
+constexpr int ROW_REPLICAS = 4;  // copies of every candidate row (spreads the readers of the winner's row)
+// Net permutation of one panel's interchanges: row dst[i] receives old row src[i].  Two lists (panel parity): the
+// bulk stream may still be applying panel i's list to the far columns while the chain stream builds panel i+1's.
+struct MoveList {
+  int n_moves;
+  int pad[3];
+  int dst[MAX_MOVES];
+  int src[MAX_MOVES];
+};
+// Flagged ("LL") exchange words: every 4-byte half of a value travels next to a 4-byte tag in the same naturally
+// atomic 8-byte unit, so a reader that sees the expected tag has the data -- no fence, no atomic, no grid barrier.
+// All accesses are RELAXED at gpu scope (served by L2, free to overlap): volatile ones would be kept in program
+// order by the hardware, which serialises a poll of n words into n L2 round trips.
+__device__ __forceinline__ void st_relaxed_2x64(void* p, unsigned long long a, unsigned long long b) {
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld_relaxed_2x64(const void* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_pack(unsigned v, unsigned tag) {
+  return ((unsigned long long)tag << 32) | v;
+}
+template <typename T>
+struct LL;
+template <>
+struct LL<double> {
+  typedef uint4 word;
+  static __device__ __forceinline__ void store(word* p, double v, unsigned tag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    st_relaxed_2x64(p, ll_pack((unsigned)b, tag), ll_pack((unsigned)(b >> 32), tag));
+  }
+  static __device__ __forceinline__ bool load(const word* p, unsigned tag, double& v) {
+    unsigned long long a, b;
+    ld_relaxed_2x64(p, a, b);
+    v = __longlong_as_double((long long)((b << 32) | (a & 0xffffffffull)));
+    return (unsigned)(a >> 32) == tag && (unsigned)(b >> 32) == tag;
+  }
+};
+template <>
+struct LL<float> {
+  typedef uint2 word;
+  static __device__ __forceinline__ void store(word* p, float v, unsigned tag) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(ll_pack(__float_as_uint(v), tag)) : "memory");
+  }
+  static __device__ __forceinline__ bool load(const word* p, unsigned tag, float& v) {
+    unsigned long long a;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
+    v = __uint_as_float((unsigned)a);
+    return (unsigned)(a >> 32) == tag;
+  }
+};
+// One candidate record per CTA and step: |pivot candidate| as a double and its absolute row, packed into two
+// self-validating 8-byte units (16 bytes, one load per record): {key.hi32 | row.hi16 | tag16}, {key.lo32 | row.lo16 |
+// tag16}.  A 16-bit tag suffices here: a slot is rewritten at the same step of every panel, so the only stale values
+// a reader can meet are one panel (or two steps) old.
+struct Rec {
+  unsigned long long a, b;
+};
+__device__ __forceinline__ unsigned long long rec_pack(unsigned key32, unsigned row16, unsigned tag16) {
+  return ((unsigned long long)key32 << 32) | ((unsigned long long)(row16 & 0xffffu) << 16) | (tag16 & 0xffffu);
+}
+
 template <typename T>
 struct PanelWs {
-  unsigned int barrier;  // grid barrier counter, zeroed before every panel launch
-  int n_moves;
-  int pad[2];
-  int ipiv[MAX_NB];             // absolute pivot row chosen for column j0 + c
-  int move_dst[MAX_MOVES];      // net permutation of the panel: row move_dst[i] receives old row move_src[i]
-  int move_src[MAX_MOVES];
-  // double-buffered per-step exchange area, laid out after the struct:
-  //   double cand_key[2][G]; int cand_idx[2][G]; T cand_row[2][G][XROW]; T top_row[2][XROW];
+  int ipiv[MAX_NB];  // absolute pivot row chosen for column j0 + c
+  MoveList moves[2];
+  // double-buffered (step parity) exchange area, laid out after the struct:
+  //   Rec inbox[2][G reader][G writer]; LL<T>::word cand_row[2][G][XROW]; LL<T>::word top_row[2][XROW];
+  // Every CTA pushes its record into each reader's PRIVATE inbox and polls only its own: an all-to-all in which no
+  // cache line has more than one poller (148 CTAs spinning on the same 37 lines cost ~9000 cycles per column).
 };
 
 template <typename T>
+__host__ __device__ inline size_t ws_hdr_bytes() {
+  return (sizeof(PanelWs<T>) + 31) & ~(size_t)31;
+}
+template <typename T>
 __host__ __device__ inline size_t ws_bytes(int G) {
-  size_t b = sizeof(PanelWs<T>);
-  b += sizeof(double) * 2 * G;
-  b += sizeof(int) * 2 * G;
-  b = (b + 15) & ~(size_t)15;
-  b += sizeof(T) * 2 * (size_t)G * XROW;
-  b += sizeof(T) * 2 * XROW;
-  return b;
+  return ws_hdr_bytes<T>() + sizeof(Rec) * 2 * (size_t)G * G +
+         sizeof(typename LL<T>::word) * (2 * (size_t)ROW_REPLICAS * G * XROW + 2 * XROW);
 }
 template <typename T>
 struct WsView {
   PanelWs<T>* hdr;
-  double* cand_key;  // [2][G]
-  int* cand_idx;     // [2][G]
-  T* cand_row;       // [2][G][XROW]
-  T* top_row;        // [2][XROW]
+  Rec* rec;                         // [2][G][G]
+  typename LL<T>::word* cand_row;   // [2][ROW_REPLICAS][G][XROW]
+  typename LL<T>::word* top_row;    // [2][XROW]
 };
 template <typename T>
 __host__ __device__ inline WsView<T> ws_view(void* base, int G) {
   WsView<T> v;
   char* p = (char*)base;
   v.hdr = (PanelWs<T>*)p;
-  p += sizeof(PanelWs<T>);
-  v.cand_key = (double*)p;
-  p += sizeof(double) * 2 * G;
-  v.cand_idx = (int*)p;
-  p += sizeof(int) * 2 * G;
-  p = (char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
-  v.cand_row = (T*)p;
-  p += sizeof(T) * 2 * (size_t)G * XROW;
-  v.top_row = (T*)p;
-  return v;
-}
-
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  p += ws_hdr_bytes<T>();
+  v.rec = (Rec*)p;
+  p += sizeof(Rec) * 2 * (size_t)G * G;
+  v.cand_row = (typename LL<T>::word*)p;
+  p += sizeof(typename LL<T>::word) * 2 * (size_t)ROW_REPLICAS * G * XROW;
+  v.top_row = (typename LL<T>::word*)p;
   return v;
 }
 
@@ -123,12 +172,15 @@ __device__ __forceinline__ void key_merge(double& k, int& i, double k2, int i2) 
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, bool EXACT>
 __global__ void __launch_bounds__(PANEL_THREADS, 1)
-lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_per_cta, void* ws_base) {
+lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_per_cta, void* ws_base, unsigned epoch) {
+  typedef typename LL<T>::word llw;
   extern __shared__ __align__(16) unsigned char panel_smem[];
   T* rows = reinterpret_cast<T*>(panel_smem);            // [rows_per_cta][jb]: original values, then final L / U
   T* sums = rows + (size_t)rows_per_cta * jb;            // [rows_per_cta][jb]: deferred sums (EXACT only)
   __shared__ double wkey[PANEL_WARPS];
   __shared__ int widx[PANEL_WARPS];
+  __shared__ T s_prow[MAX_NB];  // the step's pivot row as stored / its current values (row c of U)
+  __shared__ T s_u[MAX_NB];
 
   const int G = gridDim.x;
   const WsView<T> ws = ws_view<T>(ws_base, G);
@@ -164,172 +216,266 @@ lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_pe
     }
   }
 
-  unsigned int bar_target = 0;
+  // Per column c (no grid barrier, no atomics -- everything crosses CTAs as flagged words):
+  //   (A) CTA sync: all rows updated, per-warp arg-max of column c in wkey/widx.
+  //       Every warp reduces the 8 partial arg-maxes; warps 0..3 each publish one REPLICA of the CTA's candidate row
+  //       (readers spread over the replicas, so the winner's row is not one 148-reader hot spot in L2); the owner warp
+  //       of the diagonal row publishes it.  Warp 0 then pushes the CTA's record into every reader's private inbox,
+  //       polls its own inbox (one poller per CTA: polling traffic delays the very stores it is waiting for), picks the
+  //       winner and fetches the winner's row into shared memory.
+  //   (B) CTA sync: interchange, multipliers (lanes <-> rows), rank-1 update (lanes <-> columns), arg-max of column c+1.
+  // The exchange area is double-buffered by step parity: a CTA can publish step c+2 only after it has read every step
+  // c+1 record, and those exist only once every CTA has finished reading step c.
+  __shared__ int s_p;
   for (int c = 0; c < jb; ++c) {
     const int par = c & 1;
     const int diag = j0 + c;  // absolute row/col index of this step's diagonal
-    __syncthreads();          // (A) all rows updated, wkey/widx written
-    if (warp == 0) {
+    const unsigned tag = (epoch << 8) | (unsigned)(c + 1);
+    const unsigned tag16 = tag & 0xffffu;
+    __syncthreads();          // (A)
+    const bool own_diag = diag >= row_base && diag < row_base + nloc;
+    if (own_diag && ((diag - row_base) % PANEL_WARPS) == warp) {
+      // the diagonal row, published by the warp that will overwrite it in the interchange below
+      const size_t off = (size_t)(diag - row_base) * jb;
+      llw* dst = ws.top_row + (size_t)par * XROW;
+      for (int q = 0; q < nq; ++q)
+        if (lane + 32 * q < jb) {
+          LL<T>::store(&dst[lane + 32 * q], rows[off + lane + 32 * q], tag);
+          if (EXACT) LL<T>::store(&dst[MAX_NB + lane + 32 * q], sums[off + lane + 32 * q], tag);
+        }
+    }
+    if (warp < ROW_REPLICAS) {
+      // CTA-wide candidate
       double k = (lane < PANEL_WARPS) ? wkey[lane] : -2.0;
       int ki = (lane < PANEL_WARPS) ? widx[lane] : INT_MAX;
 #pragma unroll
       for (int off = 4; off > 0; off >>= 1) {
-        double k2 = __shfl_down_sync(0xffffffffu, k, off);
-        int i2 = __shfl_down_sync(0xffffffffu, ki, off);
+        const double k2 = __shfl_xor_sync(0xffffffffu, k, off);
+        const int i2 = __shfl_xor_sync(0xffffffffu, ki, off);
         key_merge(k, ki, k2, i2);
       }
       k = __shfl_sync(0xffffffffu, k, 0);
       ki = __shfl_sync(0xffffffffu, ki, 0);
-      if (lane == 0) {
-        ws.cand_key[par * G + blockIdx.x] = k;
-        ws.cand_idx[par * G + blockIdx.x] = ki;
-      }
-      if (ki != INT_MAX) {
+      if (ki != INT_MAX) {  // replica `warp` of the candidate row
         const size_t off = (size_t)(ki - row_base) * jb;
-        T* dst = ws.cand_row + ((size_t)par * G + blockIdx.x) * XROW;
+        llw* dst = ws.cand_row + (((size_t)par * ROW_REPLICAS + warp) * G + blockIdx.x) * XROW;
         for (int q = 0; q < nq; ++q)
           if (lane + 32 * q < jb) {
-            dst[lane + 32 * q] = rows[off + lane + 32 * q];
-            if (EXACT) dst[MAX_NB + lane + 32 * q] = sums[off + lane + 32 * q];
+            LL<T>::store(&dst[lane + 32 * q], rows[off + lane + 32 * q], tag);
+            if (EXACT) LL<T>::store(&dst[MAX_NB + lane + 32 * q], sums[off + lane + 32 * q], tag);
           }
       }
-    } else if (warp == 1) {
-      if (diag >= row_base && diag < row_base + nloc) {  // this CTA holds the diagonal row: publish it for the swap
-        const size_t off = (size_t)(diag - row_base) * jb;
-        T* dst = ws.top_row + (size_t)par * XROW;
-        for (int q = 0; q < nq; ++q)
-          if (lane + 32 * q < jb) {
-            dst[lane + 32 * q] = rows[off + lane + 32 * q];
-            if (EXACT) dst[MAX_NB + lane + 32 * q] = sums[off + lane + 32 * q];
-          }
-      }
-    }
-    __syncthreads();  // (B) publication complete within the CTA
-    bar_target += G;
-    if (threadIdx.x == 0) {
-      __threadfence();
-      atomicAdd(&ws.hdr->barrier, 1u);
-      while (ld_acquire_u32(&ws.hdr->barrier) < bar_target) {
-      }
-    }
-    __syncthreads();  // (C) every CTA's candidates are visible
-
-    // ---- every warp redundantly reduces the G candidates (L1 is not coherent: read through L2) ----
-    double k = -2.0;
-    int p = INT_MAX, pcta = 0;
-    for (int b = lane; b < G; b += 32) {
-      const double k2 = __ldcg(&ws.cand_key[par * G + b]);
-      const int i2 = __ldcg(&ws.cand_idx[par * G + b]);
-      if (k2 > k || (k2 == k && i2 < p)) {
-        k = k2;
-        p = i2;
-        pcta = b;
-      }
-    }
+      if (warp == 0) {
+        const unsigned long long kb = (unsigned long long)__double_as_longlong(k);
+        for (int rd = lane; rd < G; rd += 32)  // one copy into every reader's inbox
+          st_relaxed_2x64(&ws.rec[((size_t)par * G + rd) * G + blockIdx.x],
+                          rec_pack((unsigned)(kb >> 32), (unsigned)ki >> 16, tag), rec_pack((unsigned)kb, (unsigned)ki, tag));
+        // poll the own inbox: all loads of a pass are in flight together
+        double bk = -2.0;
+        int bp = INT_MAX, bcta = 0;
+        constexpr int RPL = 5;
+        for (int base = 0; base < G; base += 32 * RPL) {
+          unsigned long long ra[RPL], rb[RPL];
+          bool ok[RPL];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double k2 = __shfl_xor_sync(0xffffffffu, k, off);
-      const int i2 = __shfl_xor_sync(0xffffffffu, p, off);
-      const int c2 = __shfl_xor_sync(0xffffffffu, pcta, off);
-      if (k2 > k || (k2 == k && i2 < p)) {
-        k = k2;
-        p = i2;
-        pcta = c2;
+          for (int i = 0; i < RPL; ++i) ok[i] = base + lane + 32 * i >= G;
+          bool all;
+          do {
+#pragma unroll
+            for (int i = 0; i < RPL; ++i)
+              if (!ok[i]) ld_relaxed_2x64(&ws.rec[((size_t)par * G + blockIdx.x) * G + base + lane + 32 * i], ra[i], rb[i]);
+            all = true;
+#pragma unroll
+            for (int i = 0; i < RPL; ++i)
+              if (!ok[i]) {
+                ok[i] = (unsigned)(ra[i] & 0xffffu) == tag16 && (unsigned)(rb[i] & 0xffffu) == tag16;
+                all &= ok[i];
+              }
+          } while (!all);
+#pragma unroll
+          for (int i = 0; i < RPL; ++i) {
+            const int b = base + lane + 32 * i;
+            if (b < G) {
+              const double k2 = __longlong_as_double((long long)((ra[i] & 0xffffffff00000000ull) | (rb[i] >> 32)));
+              const int i2 = (int)((((unsigned)(ra[i] >> 16) & 0xffffu) << 16) | ((unsigned)(rb[i] >> 16) & 0xffffu));
+              if (k2 > bk || (k2 == bk && i2 < bp)) {
+                bk = k2;
+                bp = i2;
+                bcta = b;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const double k2 = __shfl_xor_sync(0xffffffffu, bk, off);
+          const int i2 = __shfl_xor_sync(0xffffffffu, bp, off);
+          const int c2 = __shfl_xor_sync(0xffffffffu, bcta, off);
+          if (k2 > bk || (k2 == bk && i2 < bp)) {
+            bk = k2;
+            bp = i2;
+            bcta = c2;
+          }
+        }
+        // bp = absolute pivot row (>= diag), held by CTA bcta: fetch its row from "our" replica
+        const llw* prow_g =
+            ws.cand_row + (((size_t)par * ROW_REPLICAS + (blockIdx.x % ROW_REPLICAS)) * G + bcta) * XROW;
+        T pa[MAX_NB / 32], ps[MAX_NB / 32];
+        bool ok[MAX_NB / 32];
+#pragma unroll
+        for (int q = 0; q < MAX_NB / 32; ++q) {
+          ok[q] = lane + 32 * q >= jb;
+          pa[q] = (T)0;
+          ps[q] = (T)0;
+        }
+        bool all;
+        do {
+          all = true;
+#pragma unroll
+          for (int q = 0; q < MAX_NB / 32; ++q)
+            if (!ok[q]) {
+              bool v = LL<T>::load(&prow_g[lane + 32 * q], tag, pa[q]);
+              if (EXACT) v &= LL<T>::load(&prow_g[MAX_NB + lane + 32 * q], tag, ps[q]);
+              ok[q] = v;
+              all &= v;
+            }
+        } while (!all);
+#pragma unroll
+        for (int q = 0; q < MAX_NB / 32; ++q) {
+          const int col = lane + 32 * q;
+          if (col < jb) {
+            s_prow[col] = pa[q];
+            s_u[col] = EXACT ? sub_rn(pa[q], ps[q]) : pa[q];
+          }
+        }
+        if (lane == 0) s_p = bp;
       }
     }
-    // p = absolute pivot row (>= diag), held by CTA pcta
-    const T* prow_g = ws.cand_row + ((size_t)par * G + pcta) * XROW;
+    __syncthreads();  // (B) winner and pivot row are in shared memory
+    const int p = s_p;
     T prow[MAX_NB / 32];  // the pivot row as stored (cols < c: final L entries; cols >= c: original values in EXACT)
     T u[MAX_NB / 32];     // its current values = row c of U for cols >= c
 #pragma unroll
     for (int q = 0; q < MAX_NB / 32; ++q) {
       const int col = lane + 32 * q;
-      prow[q] = (col < jb) ? __ldcg(&prow_g[col]) : (T)0;
-      u[q] = prow[q];
-      if (EXACT && col < jb) u[q] = sub_rn(prow[q], __ldcg(&prow_g[MAX_NB + col]));
+      prow[q] = (col < jb) ? s_prow[col] : (T)0;
+      u[q] = (col > c && col < jb) ? s_u[col] : (T)0;  // zero outside the update range: no predicates in the loop
     }
-    T pv = __ldcg(&prow_g[c]);
-    if (EXACT) pv = sub_rn(pv, __ldcg(&prow_g[MAX_NB + c]));
+    const T pv = s_u[c];
 
     if (blockIdx.x == 0 && threadIdx.x == 0) ws.hdr->ipiv[c] = p;
 
     // ---- interchange (whole panel row; the rest of the row is swapped by lu_swap*_kernel) ----
     if (p != diag && p >= row_base && p < row_base + nloc && ((p - row_base) % PANEL_WARPS) == warp) {
-      const T* trow_g = ws.top_row + (size_t)par * XROW;
+      const llw* trow_g = ws.top_row + (size_t)par * XROW;
       const size_t off = (size_t)(p - row_base) * jb;
+      T ta[MAX_NB / 32], ts[MAX_NB / 32];
+      bool ok[MAX_NB / 32];
+#pragma unroll
+      for (int q = 0; q < MAX_NB / 32; ++q) {
+        ok[q] = lane + 32 * q >= jb;
+        ta[q] = (T)0;
+        ts[q] = (T)0;
+      }
+      bool all;
+      do {
+        all = true;
+#pragma unroll
+        for (int q = 0; q < MAX_NB / 32; ++q)
+          if (!ok[q]) {
+            bool v = LL<T>::load(&trow_g[lane + 32 * q], tag, ta[q]);
+            if (EXACT) v &= LL<T>::load(&trow_g[MAX_NB + lane + 32 * q], tag, ts[q]);
+            ok[q] = v;
+            all &= v;
+          }
+      } while (!all);
 #pragma unroll
       for (int q = 0; q < MAX_NB / 32; ++q)
         if (lane + 32 * q < jb) {
-          rows[off + lane + 32 * q] = __ldcg(&trow_g[lane + 32 * q]);
-          if (EXACT) sums[off + lane + 32 * q] = __ldcg(&trow_g[MAX_NB + lane + 32 * q]);
+          rows[off + lane + 32 * q] = ta[q];
+          if (EXACT) sums[off + lane + 32 * q] = ts[q];
         }
     }
-    if ((p != diag || EXACT) && diag >= row_base && diag < row_base + nloc &&
-        ((diag - row_base) % PANEL_WARPS) == warp) {
+    if ((p != diag || EXACT) && own_diag && ((diag - row_base) % PANEL_WARPS) == warp) {
       const size_t off = (size_t)(diag - row_base) * jb;  // the diagonal row becomes final: L for cols < c, U for >= c
 #pragma unroll
       for (int q = 0; q < MAX_NB / 32; ++q) {
         const int col = lane + 32 * q;
-        if (col < jb) rows[off + col] = (col >= c) ? u[q] : prow[q];
+        if (col < jb) rows[off + col] = (col >= c) ? s_u[col] : prow[q];
       }
     }
     __syncwarp();
 
-    // ---- scale column c and rank-1 update of the warp's rows below the diagonal; track arg-max of column c+1 ----
-    double nk = -2.0;
-    int nki = INT_MAX;
-    const int cn = c + 1;                     // next column
-    const bool track = (cn < jb) && (lane == (cn & 31));
-    const int qn = cn >> 5;
+    // ---- multipliers, rank-1 update of the warp's rows below the diagonal, arg-max of column c+1 ----
+    const int cn = c + 1;  // next column
     int lr0 = warp;
     if (row_base <= diag) {                   // skip rows at or above the diagonal
       const int first = diag + 1 - row_base;  // first local row strictly below the diagonal
       lr0 = first + ((warp - first) % PANEL_WARPS + PANEL_WARPS) % PANEL_WARPS;
     }
-    for (int lr = lr0; lr < nloc; lr += PANEL_WARPS) {
-      T* r = rows + (size_t)lr * jb;
-      T* sacc = sums + (size_t)lr * jb;
-      T l = value(lr, c);
-      if (pv != (T)0) l = l / pv;             // true division, skipped for an exactly-zero pivot (lu.rs:156-160)
+    // EXACT keeps the reference's true division (lu.rs:158); the multi-panel path multiplies by the reciprocal of the
+    // pivot (<= 1.5 ulp from the quotient, far inside the 1e-12*n element bar): a double division is a ~30 instruction
+    // dependent sequence on the column's critical path.
+    const T rcp = EXACT ? (T)0 : (T)1 / pv;
+    double nk = -2.0;
+    int nki = INT_MAX;
+    for (int lrc = lr0; lrc < nloc; lrc += 32 * PANEL_WARPS) {
+      // phase 1, lanes <-> rows: the multipliers l = a[i][c] / pivot of up to 32 rows at once
+      const int mylr = lrc + lane * PANEL_WARPS;
+      T l = (T)0;
+      if (mylr < nloc) {
+        l = value(mylr, c);
+        if (pv != (T)0) l = EXACT ? l / pv : l * rcp;  // skipped for an exactly-zero pivot (lu.rs:156-160)
+      }
       __syncwarp();
-      if (lane == (c & 31)) r[c] = l;         // final L entry
-      T nv = (T)0;
+      if (mylr < nloc) rows[(size_t)mylr * jb + c] = l;  // final L entry
+      // phase 2, lanes <-> columns: stream the rows, multiplier broadcast by shuffle.  u[] is zero outside (c, jb), so
+      // the loop body carries no column predicates (columns <= c are rewritten with their own value).
+      const int cnt = min(32, (nloc - lrc + PANEL_WARPS - 1) / PANEL_WARPS);
+      T* r = rows + (size_t)lrc * jb + lane;
+      T* sa = sums + (size_t)lrc * jb + lane;
+      const size_t rstep = (size_t)PANEL_WARPS * jb;
+#pragma unroll 4
+      for (int i = 0; i < cnt; ++i) {
+        const T li = __shfl_sync(0xffffffffu, l, i);
 #pragma unroll
-      for (int q = 0; q < MAX_NB / 32; ++q) {
-        const int col = lane + 32 * q;
-        if (col > c && col < jb) {
-          T v;
-          if (EXACT) {
-            const T sn = add_rn(sacc[col], mul_rn(l, u[q]));  // s = s + l*u, k ascending (lu.rs:125)
-            sacc[col] = sn;
-            v = sub_rn(r[col], sn);
-          } else {
-            v = sub_rn(r[col], mul_rn(l, u[q]));
-            r[col] = v;
+        for (int q = 0; q < MAX_NB / 32; ++q) {
+          if (32 * q < jb) {
+            const int col = lane + 32 * q;
+            if (col > c && col < jb) {
+              if (EXACT) {
+                sa[32 * q] = add_rn(sa[32 * q], mul_rn(li, u[q]));  // s = s + l*u, k ascending (lu.rs:125)
+              } else {
+                r[32 * q] = sub_rn(r[32 * q], mul_rn(li, u[q]));
+              }
+            }
           }
-          if (q == qn) nv = v;
         }
+        r += rstep;
+        sa += rstep;
       }
-      if (track) key_merge(nk, nki, pivot_key(nv, false), row_base + lr);
+      // phase 3, lanes <-> rows again: arg-max of the next column over these rows (strict '>' + lowest row == the
+      // reference's first maximum)
+      if (cn < jb) {
+        __syncwarp();
+        double kk = -2.0;
+        int kr = INT_MAX;
+        if (mylr < nloc) {
+          kk = pivot_key(value(mylr, cn), row_base + mylr == diag + 1);
+          kr = row_base + mylr;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const double k2 = __shfl_xor_sync(0xffffffffu, kk, off);
+          const int i2 = __shfl_xor_sync(0xffffffffu, kr, off);
+          key_merge(kk, kr, k2, i2);
+        }
+        key_merge(nk, nki, kk, kr);
+      }
     }
-    // the row that becomes the next diagonal row (absolute row diag+1) takes part with its own value as the incumbent
-    if (cn < jb) {
-      const int nd = diag + 1;
-      if (nd >= row_base && nd < row_base + nloc && ((nd - row_base) % PANEL_WARPS) == warp && nd < m) {
-        if (track) {
-          const double kk = pivot_key(value(nd - row_base, cn), true);
-          if (kk == (double)INFINITY) {  // NaN incumbent: never displaced
-            nk = kk;
-            nki = nd;
-          }
-        }
-      }
-      nk = __shfl_sync(0xffffffffu, nk, cn & 31);
-      nki = __shfl_sync(0xffffffffu, nki, cn & 31);
-      if (lane == 0) {
-        wkey[warp] = nk;
-        widx[warp] = nki;
-      }
+    if (cn < jb && lane == 0) {
+      wkey[warp] = nk;
+      widx[warp] = nki;
     }
   }
   __syncthreads();
@@ -345,75 +491,52 @@ lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_pe
 // 2. net permutation of the panel's interchanges + piv / sign bookkeeping (one warp)
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void lu_perm_kernel(void* ws_base, int G, int j0, int jb, uint64_t* __restrict__ piv, int* __restrict__ sign) {
-  __shared__ int pos[MAX_MOVES];
-  __shared__ int src[MAX_MOVES];
+__global__ void __launch_bounds__(2 * MAX_NB)
+lu_perm_kernel(void* ws_base, int G, int parity, int j0, int jb, uint64_t* __restrict__ piv, int* __restrict__ sign) {
+  // One thread per position that can change: the jb top rows and the (distinct) pivot rows below them.  The content
+  // that ends up at position q is the original row reached by tracing q BACKWARDS through the jb transpositions.
   __shared__ int ipiv_s[MAX_NB];
-  __shared__ uint64_t pold[MAX_MOVES];
+  __shared__ int nm;
+  __shared__ int flips;
   const WsView<T> ws = ws_view<T>(ws_base, G);
-  const int lane = threadIdx.x;
-  for (int i = lane; i < jb; i += 32) {
-    pos[i] = j0 + i;
-    src[i] = j0 + i;
-    ipiv_s[i] = ws.hdr->ipiv[i];
+  MoveList* ml = &ws.hdr->moves[parity];
+  const int tid = threadIdx.x;
+  if (tid < jb) ipiv_s[tid] = ws.hdr->ipiv[tid];
+  if (tid == 0) {
+    nm = 0;
+    flips = 0;
   }
-  __syncwarp();
-  int count = jb;
-  int flips = 0;
-  for (int c = 0; c < jb; ++c) {
-    const int p = ipiv_s[c];
-    if (p == j0 + c) continue;  // warp-uniform
-    ++flips;
-    int k;
-    if (p < j0 + jb) {
-      k = p - j0;
-    } else {
-      int found = -1;
-      for (int base = jb; base < count; base += 32) {
-        const int i = base + lane;
-        const unsigned hit = __ballot_sync(0xffffffffu, i < count && pos[i] == p);
-        if (hit) {
-          found = base + __ffs(hit) - 1;
-          break;
-        }
-      }
-      if (found < 0) {
-        if (lane == 0) {
-          pos[count] = p;
-          src[count] = p;
-        }
-        found = count++;
-      }
-      k = found;
-    }
-    __syncwarp();
-    if (lane == 0) {
-      const int t = src[c];
-      src[c] = src[k];
-      src[k] = t;
-    }
-    __syncwarp();
+  __syncthreads();
+  int q = -1;
+  if (tid < jb) {
+    q = j0 + tid;
+    if (ipiv_s[tid] != q) atomicAdd(&flips, 1);  // one sign flip per actual interchange (lu.rs:151)
+  } else if (tid < 2 * jb) {
+    const int c = tid - jb, p = ipiv_s[c];
+    bool first = p >= j0 + jb;  // pivot rows inside the top block are already covered
+    for (int c2 = 0; c2 < c && first; ++c2) first = ipiv_s[c2] != p;
+    if (first) q = p;
   }
-  // compact the rows that actually move; `piv` is permuted exactly like a matrix column (lu.rs:147-149)
-  int nm = 0;
-  for (int base = 0; base < count; base += 32) {
-    const int i = base + lane;
-    const bool mv = i < count && pos[i] != src[i];
-    const unsigned mask = __ballot_sync(0xffffffffu, mv);
-    if (mv) {
-      const int slot = nm + __popc(mask & ((1u << lane) - 1));
-      ws.hdr->move_dst[slot] = pos[i];
-      ws.hdr->move_src[slot] = src[i];
-      pold[slot] = piv[src[i]];
+  int r = q;
+  if (q >= 0) {
+    for (int c = jb - 1; c >= 0; --c) {
+      const int top = j0 + c, p = ipiv_s[c];
+      r = (r == top) ? p : ((r == p) ? top : r);
     }
-    nm += __popc(mask);
-    __syncwarp();
   }
-  __syncwarp();
-  for (int i = lane; i < nm; i += 32) piv[ws.hdr->move_dst[i]] = pold[i];
-  if (lane == 0) {
-    ws.hdr->n_moves = nm;
-    if (flips & 1) *sign = !*sign;  // pospivsign flips once per interchange (lu.rs:151)
+  uint64_t pold = 0;
+  int slot = -1;
+  if (q >= 0 && r != q) {
+    slot = atomicAdd(&nm, 1);
+    ml->dst[slot] = q;
+    ml->src[slot] = r;
+    pold = piv[r];  // `piv` is permuted exactly like a matrix column (lu.rs:147-149)
+  }
+  __syncthreads();
+  if (slot >= 0) piv[q] = pold;
+  if (tid == 0) {
+    ml->n_moves = nm;
+    if (flips & 1) *sign = !*sign;
   }
 }
 
@@ -424,17 +547,18 @@ constexpr int SWAP_W = 32;  // columns per CTA strip
 // Columns [col0, col1) EXCLUDING the panel's own columns [skip0, skip1) (already interchanged inside the panel kernel).
 template <typename T>
 __global__ void __launch_bounds__(256) lu_swap_kernel(T* __restrict__ A, size_t ld, int col0, int col1, int skip0,
-                                                      int skip1, const void* ws_base, int G) {
+                                                      int skip1, const void* ws_base, int G, int parity) {
   extern __shared__ __align__(16) unsigned char swap_smem[];
   T(*stage)[SWAP_W] = reinterpret_cast<T(*)[SWAP_W]>(swap_smem);  // [MAX_MOVES][SWAP_W]
   __shared__ int mdst[MAX_MOVES];
   __shared__ int msrc[MAX_MOVES];
   const WsView<T> ws = ws_view<T>(const_cast<void*>(ws_base), G);
-  const int nm = ws.hdr->n_moves;
+  const MoveList* ml = &ws.hdr->moves[parity];
+  const int nm = ml->n_moves;
   if (nm == 0) return;
   for (int i = threadIdx.x; i < nm; i += blockDim.x) {
-    mdst[i] = ws.hdr->move_dst[i];
-    msrc[i] = ws.hdr->move_src[i];
+    mdst[i] = ml->dst[i];
+    msrc[i] = ml->src[i];
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -456,16 +580,17 @@ __global__ void __launch_bounds__(256) lu_swap_kernel(T* __restrict__ A, size_t 
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int IB = 32;
 constexpr int INVL_LD = MAX_NB + 1;
+constexpr int INVL_THREADS = 512;
 template <typename T>
-__global__ void __launch_bounds__(256) lu_invl_kernel(const T* __restrict__ A, size_t ld, int j0, int jb,
-                                                      T* __restrict__ W /* [MAX_NB][MAX_NB] */) {
+__global__ void __launch_bounds__(INVL_THREADS) lu_invl_kernel(const T* __restrict__ A, size_t ld, int j0, int jb,
+                                                               T* __restrict__ W /* [MAX_NB][MAX_NB] */) {
   // One padded square in shared memory holds both operands: the lower triangle (with diagonal) is W, the strictly
   // upper triangle is L11 transposed (L[i][k], k < i, lives at SQ[k][i]).  Products in flight use a separate scratch.
   extern __shared__ __align__(16) unsigned char invl_smem[];
   T(*SQ)[INVL_LD] = reinterpret_cast<T(*)[INVL_LD]>(invl_smem);
   T* scratch = reinterpret_cast<T*>(invl_smem) + (size_t)MAX_NB * INVL_LD;  // [<= 3][IB][IB]
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < MAX_NB * MAX_NB; idx += blockDim.x) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int idx = tid; idx < MAX_NB * MAX_NB; idx += INVL_THREADS) {
     const int i = idx / MAX_NB, k = idx - i * MAX_NB;
     if (k < i) {
       SQ[k][i] = (i < jb) ? __ldcg(&A[(size_t)(j0 + i) * ld + j0 + k]) : (T)0;  // L^T into the upper triangle
@@ -477,33 +602,42 @@ __global__ void __launch_bounds__(256) lu_invl_kernel(const T* __restrict__ A, s
   __syncthreads();
   auto Lat = [&](int i, int k) -> T { return SQ[k][i]; };  // L[i][k], k < i
   const int nblk = (jb + IB - 1) / IB;
-  // diagonal blocks: thread (b, j) solves L_bb * w = e_j by forward substitution
-  if (tid < MAX_NB) {
-    const int b = tid / IB, j = tid % IB, o = b * IB;
-    if (o + j < jb) {
-      SQ[o + j][o + j] = (T)1;
-      for (int i = j + 1; i < IB && o + i < jb; ++i) {
-        T acc = (T)0;
-        for (int k = j; k < i; ++k) acc += Lat(o + i, o + k) * SQ[o + k][o + j];
-        SQ[o + i][o + j] = -acc;
-      }
+  // diagonal blocks: warp b, lane j solves L_bb * w = e_j by right-looking substitution held in registers
+  if (warp < nblk) {
+    const int o = warp * IB, j = lane;
+    T w[IB];
+#pragma unroll
+    for (int i = 0; i < IB; ++i) w[i] = (i == j) ? (T)1 : (T)0;
+#pragma unroll
+    for (int k = 0; k < IB - 1; ++k) {
+      const T wk = w[k];
+#pragma unroll
+      for (int i = k + 1; i < IB; ++i) w[i] -= Lat(o + i, o + k) * wk;  // Lat is a warp-wide broadcast
     }
+#pragma unroll
+    for (int i = 0; i < IB; ++i)
+      if (i >= j) SQ[o + i][o + j] = w[i];  // only the lower part: the upper triangle of SQ is L^T
   }
   __syncthreads();
   for (int d = 1; d < nblk; ++d) {
     const int pairs = nblk - d;  // blocks (i, j) = (d + pr, pr)
     // phase 1: T_ij = sum_{k=j}^{i-1} L_ik * W_kj
-    for (int e = tid; e < pairs * IB * IB; e += blockDim.x) {
+    for (int e = tid; e < pairs * IB * IB; e += INVL_THREADS) {
       const int pr = e / (IB * IB), r = (e / IB) % IB, c = e % IB;
       const int i = d + pr, j = pr;
-      T acc = (T)0;
+      T acc0 = (T)0, acc1 = (T)0;
       // W_jj is lower triangular: its entries above the diagonal are zero (that part of SQ holds L^T), so start at c
-      for (int kk = j * IB + c; kk < i * IB; ++kk) acc += Lat(i * IB + r, kk) * SQ[kk][j * IB + c];
-      scratch[e] = acc;
+      int kk = j * IB + c;
+      for (; kk + 1 < i * IB; kk += 2) {
+        acc0 += Lat(i * IB + r, kk) * SQ[kk][j * IB + c];
+        acc1 += Lat(i * IB + r, kk + 1) * SQ[kk + 1][j * IB + c];
+      }
+      if (kk < i * IB) acc0 += Lat(i * IB + r, kk) * SQ[kk][j * IB + c];
+      scratch[e] = acc0 + acc1;
     }
     __syncthreads();
     // phase 2: W_ij = -W_ii * T_ij
-    for (int e = tid; e < pairs * IB * IB; e += blockDim.x) {
+    for (int e = tid; e < pairs * IB * IB; e += INVL_THREADS) {
       const int pr = e / (IB * IB), r = (e / IB) % IB, c = e % IB;
       const int i = d + pr, j = pr;
       T acc = (T)0;
@@ -512,7 +646,7 @@ __global__ void __launch_bounds__(256) lu_invl_kernel(const T* __restrict__ A, s
     }
     __syncthreads();
   }
-  for (int idx = tid; idx < MAX_NB * MAX_NB; idx += blockDim.x) {
+  for (int idx = tid; idx < MAX_NB * MAX_NB; idx += INVL_THREADS) {
     const int i = idx / MAX_NB, k = idx - i * MAX_NB;
     W[idx] = (k <= i && i < jb) ? SQ[i][k] : (T)0;
   }
@@ -526,7 +660,8 @@ __global__ void __launch_bounds__(256) lu_invl_kernel(const T* __restrict__ A, s
 constexpr int TRSM_W = 32;
 template <typename T>
 __global__ void __launch_bounds__(256)
-lu_swap_trsm_kernel(T* __restrict__ A, size_t ld, int j0, int jb, int col0, int col1, const void* ws_base, int G) {
+lu_swap_trsm_kernel(T* __restrict__ A, size_t ld, int j0, int jb, int col0, int col1, const void* ws_base, int G,
+                    int parity) {
   extern __shared__ __align__(16) unsigned char trsm_smem[];
   T(*X)[TRSM_W] = reinterpret_cast<T(*)[TRSM_W]>(trsm_smem);            // [MAX_NB]: top jb rows of the strip (a)
   T(*S)[TRSM_W] = X + MAX_NB;                                           // [MAX_NB]: running sums
@@ -543,9 +678,10 @@ lu_swap_trsm_kernel(T* __restrict__ A, size_t ld, int j0, int jb, int col0, int 
   for (int i = threadIdx.x; i < jb; i += blockDim.x) top_src[i] = j0 + i;
   if (threadIdx.x == 0) n_out = 0;
   __syncthreads();
-  const int nm = ws.hdr->n_moves;
+  const MoveList* ml = &ws.hdr->moves[parity];
+  const int nm = ml->n_moves;
   for (int i = threadIdx.x; i < nm; i += blockDim.x) {
-    const int d = ws.hdr->move_dst[i], s = ws.hdr->move_src[i];
+    const int d = ml->dst[i], s = ml->src[i];
     if (d < j0 + jb) {
       top_src[d - j0] = s;
     } else {
@@ -590,10 +726,10 @@ __global__ void lu_init_piv_kernel(uint64_t* __restrict__ piv, int m, int* __res
 // host driver
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
-// Per host thread and device: the look-ahead stream (highest priority) and the two events that fence it.
+// Per host thread and device: the chain stream (highest priority) and the events that fence it against the bulk stream.
 struct LuSide {
   cudaStream_t sp = nullptr;
-  cudaEvent_t e1 = nullptr, e2 = nullptr;
+  cudaEvent_t e_in = nullptr, e_head = nullptr, e_bulk = nullptr;
 };
 int lu_side(int device, LuSide** out) {
   static thread_local LuSide side[64];
@@ -603,8 +739,9 @@ int lu_side(int device, LuSide** out) {
     int lo = 0, hi = 0;
     LA_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     LA_CUDA_TRY(cudaStreamCreateWithPriority(&s.sp, cudaStreamNonBlocking, hi));
-    LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e1, cudaEventDisableTiming));
-    LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e2, cudaEventDisableTiming));
+    LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e_in, cudaEventDisableTiming));
+    LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e_head, cudaEventDisableTiming));
+    LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e_bulk, cudaEventDisableTiming));
   }
   *out = &s;
   return LA_OK;
@@ -638,63 +775,62 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
   // single-panel factorisations run the bit-exact (deferred subtraction) panel when twice the panel fits
   const bool exact = kmin <= nb && (size_t)2 * rpc_first * kmin * sizeof(T) <= PANEL_SMEM_BUDGET;
   // multi-panel fp64 on TMA-addressable storage: look-ahead pipeline with U12 = inv(L11) * A12 on the DMMA GEMM
-  static const int dbg = getenv("LA_LU_DEBUG") ? atoi(getenv("LA_LU_DEBUG")) : 0;  // 1: no look-ahead, 2: plain loop
+  static const int dbg = getenv("LA_LU_DEBUG") ? atoi(getenv("LA_LU_DEBUG")) : 0;  // 1: one stream, 2: plain loop
   const bool fast = std::is_same<T, double>::value && kmin > nb && (N % 2 == 0) && ((uintptr_t)LU % 16 == 0) &&
                     (kmin % 2 == 0 || kmin == N) && dbg != 2;
 
   void* ws_base = nullptr;
   LA_TRY(scratch_get(ctx->device, 8, ws_bytes<T>(sms), &ws_base));
   void* w_base = nullptr;
-  LA_TRY(scratch_get(ctx->device, 11, sizeof(T) * MAX_NB * MAX_NB, &w_base));
-  T* W = (T*)w_base;
-  LA_CUDA_TRY(cudaFuncSetAttribute(lu_panel_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)PANEL_SMEM_BUDGET + 2048));
-  LA_CUDA_TRY(cudaFuncSetAttribute(lu_panel_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)PANEL_SMEM_BUDGET + 2048));
+  LA_TRY(scratch_get(ctx->device, 11, sizeof(T) * 2 * MAX_NB * MAX_NB, &w_base));
+  T* Wbuf[2] = {(T*)w_base, (T*)w_base + MAX_NB * MAX_NB};
 
   const int SWAP_SMEM = (int)(sizeof(T) * MAX_MOVES * SWAP_W);
   const int TRSM_SMEM = (int)(sizeof(T) * 3 * MAX_NB * TRSM_W);
   const int INVL_SMEM = (int)(sizeof(T) * ((size_t)MAX_NB * INVL_LD + 3 * IB * IB));
+  LA_CUDA_TRY(cudaFuncSetAttribute(lu_panel_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)PANEL_SMEM_BUDGET + 2048));
+  LA_CUDA_TRY(cudaFuncSetAttribute(lu_panel_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)PANEL_SMEM_BUDGET + 2048));
   LA_CUDA_TRY(cudaFuncSetAttribute(lu_swap_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWAP_SMEM));
   LA_CUDA_TRY(cudaFuncSetAttribute(lu_swap_trsm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM));
   LA_CUDA_TRY(cudaFuncSetAttribute(lu_invl_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, INVL_SMEM));
 
-  {
-    // every kernel of the pipeline prefers the maximum shared-memory carve-out, so co-resident kernels never ask an SM
-    // for a different L1/shared split
-    const void* fns[] = {(const void*)lu_panel_kernel<T, false>, (const void*)lu_panel_kernel<T, true>,
-                         (const void*)lu_perm_kernel<T>,         (const void*)lu_swap_kernel<T>,
-                         (const void*)lu_swap_trsm_kernel<T>,    (const void*)lu_invl_kernel<T>,
-                         (const void*)lu_init_piv_kernel<T>};
-    for (const void* f : fns)
-      LA_CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  }
   lu_init_piv_kernel<T><<<(M + 255) / 256, 256, 0, st>>>(piv_dev, M, sign_dev);
   LA_CUDA_TRY(cudaGetLastError());
+  // all tags invalid (0) before the first panel; epochs then count up within this factorisation (< 2^24 panels)
+  LA_CUDA_TRY(cudaMemsetAsync((char*)ws_base + ws_hdr_bytes<T>(), 0, ws_bytes<T>(sms) - ws_hdr_bytes<T>(), st));
+  unsigned epoch = 0;
 
   int G_cur = 1;
-  // panel factorisation + net permutation / piv bookkeeping of columns [j0, j0+jb) on stream s
+  // panel factorisation of columns [j0, j0+jb) on stream s (ipiv lands in the workspace header)
   auto launch_panel = [&](int j0, int jb, cudaStream_t s) -> int {
     const int R = M - j0;
     int rpc = (R + sms - 1) / sms;
     if (rpc < 8) rpc = 8;  // at least one row per warp; fewer, fuller CTAs make the barrier cheaper
     const int G = (R + rpc - 1) / rpc;
-    size_t smem = (size_t)rpc * jb * sizeof(T) * (exact ? 2 : 1);
-    if ((dbg == 6 || dbg == 9) && smem < 150 * 1024) smem = 150 * 1024;  // debug: too big to co-reside with a GEMM CTA
-    LA_CUDA_TRY(cudaMemsetAsync(ws_base, 0, sizeof(unsigned int) * 4, s));
+    const size_t smem = (size_t)rpc * jb * sizeof(T) * (exact ? 2 : 1);
     T* a = LU;
     size_t ld = n;
     int mm = M, jj0 = j0, jjb = jb, rr = rpc;
     void* wsb = ws_base;
-    void* args[] = {&a, &ld, &mm, &jj0, &jjb, &rr, &wsb};
+    unsigned ep = ++epoch;  // distinguishes this panel's flagged words from every earlier panel's
+    void* args[] = {&a, &ld, &mm, &jj0, &jjb, &rr, &wsb, &ep};
     const void* fn = exact ? (const void*)lu_panel_kernel<T, true> : (const void*)lu_panel_kernel<T, false>;
-    if (dbg == 8)
-      LA_CUDA_TRY(cudaLaunchKernel(fn, dim3(G), dim3(PANEL_THREADS), args, smem, s));  // debug: plain launch
-    else
-      LA_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PANEL_THREADS), args, smem, s));
+    LA_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PANEL_THREADS), args, smem, s));
     G_cur = G;
-    if ((dbg == 7 || dbg == 9) && s != st) return LA_OK;  // debug: perm deferred to the main stream
-    lu_perm_kernel<T><<<1, 32, 0, s>>>(ws_base, G, j0, jb, piv_dev, sign_dev);
+    return LA_OK;
+  };
+  // net permutation + piv / sign bookkeeping of the panel just factored
+  auto launch_perm = [&](int j0, int jb, int parity, cudaStream_t s) -> int {
+    lu_perm_kernel<T><<<1, 2 * MAX_NB, 0, s>>>(ws_base, G_cur, parity, j0, jb, piv_dev, sign_dev);
+    LA_CUDA_TRY(cudaGetLastError());
+    return LA_OK;
+  };
+  auto launch_swap = [&](int col0, int col1, int parity, cudaStream_t s) -> int {
+    if (col1 <= col0) return LA_OK;
+    lu_swap_kernel<T><<<(col1 - col0 + SWAP_W - 1) / SWAP_W, 256, SWAP_SMEM, s>>>(LU, n, col0, col1, col1, col1, ws_base,
+                                                                                G_cur, parity);
     LA_CUDA_TRY(cudaGetLastError());
     return LA_OK;
   };
@@ -704,14 +840,12 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
     for (int j0 = 0; j0 < kmin; j0 += nb) {
       const int jb = (kmin - j0 < nb) ? (kmin - j0) : nb;
       LA_TRY(launch_panel(j0, jb, st));
-      if (j0 > 0) {
-        lu_swap_kernel<T><<<(j0 + SWAP_W - 1) / SWAP_W, 256, SWAP_SMEM, st>>>(LU, n, 0, j0, j0, j0, ws_base, G_cur);
-        LA_CUDA_TRY(cudaGetLastError());
-      }
+      LA_TRY(launch_perm(j0, jb, 0, st));
+      LA_TRY(launch_swap(0, j0, 0, st));
       const int c1 = j0 + jb;
       if (c1 < N) {
         lu_swap_trsm_kernel<T><<<(N - c1 + TRSM_W - 1) / TRSM_W, 256, TRSM_SMEM, st>>>(LU, n, j0, jb, c1, N, ws_base,
-                                                                                     G_cur);
+                                                                                     G_cur, 0);
         LA_CUDA_TRY(cudaGetLastError());
         if (c1 < M)
           LA_TRY(gemm_dev<T>(LU + (size_t)c1 * n + j0, n, LU + (size_t)j0 * n + c1, n, LU + (size_t)c1 * n + c1, n,
@@ -721,74 +855,65 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
     return LA_OK;
   }
 
-  // ---- look-ahead pipeline (fp64) ----
-  // Stream st: row interchanges, inv(L11), U12 = inv(L11)*A12 and the trailing update, next panel's columns FIRST.
-  // Stream sp (highest priority): the next panel's factorisation, overlapping the rest of the trailing update.  The
-  // cooperative panel CTAs (latency-bound, shared-memory resident) co-reside with the DMMA GEMM CTAs on the SMs.
+  // ---- look-ahead pipeline (fp64) -------------------------------------------------------------------------------
+  // chain stream sp (highest priority), per panel i:  perm(i) -> [wait bulk(i-1)] -> row interchanges of the NEXT
+  //   panel's columns -> W = inv(L11) -> U12/trailing update of the next panel's columns -> panel(i+1)
+  // bulk stream st (the caller's), per panel i:       [wait W(i)] -> row interchanges of all other columns ->
+  //   U12 = W * A12 and A22 -= L21 * U12 for the columns right of the next panel
+  // The critical path is the chain; the bulk GEMMs fill the SMs underneath it (the cooperative panel CTAs are
+  // latency-bound and co-reside with the DMMA CTAs).  W and the move lists are double-buffered by panel parity.
   if constexpr (std::is_same<T, double>::value) {
     LuSide* side;
     LA_TRY(lu_side(ctx->device, &side));
     cudaStream_t sp = dbg == 1 ? st : side->sp;
     double* A = LU;
     const size_t ld = n;
-    LA_TRY(launch_panel(0, nb, st));
-    const int stop_iters = getenv("LA_LU_STOP") ? atoi(getenv("LA_LU_STOP")) : (1 << 30);  // debug: truncate the loop
-    for (int j0 = 0; j0 < kmin; j0 += nb) {
-      if (j0 / nb >= stop_iters) break;
+    LA_CUDA_TRY(cudaEventRecord(side->e_in, st));
+    LA_CUDA_TRY(cudaStreamWaitEvent(sp, side->e_in, 0));
+    LA_TRY(launch_panel(0, nb, sp));
+    int it = 0;
+    for (int j0 = 0; j0 < kmin; j0 += nb, ++it) {
       const int jb = (kmin - j0 < nb) ? (kmin - j0) : nb;
       const int c1 = j0 + jb;
-      if (N - jb > 0) {
-        lu_swap_kernel<T><<<(N - jb + SWAP_W - 1) / SWAP_W, 256, SWAP_SMEM, st>>>(LU, n, 0, N, j0, c1, ws_base, G_cur);
-        LA_CUDA_TRY(cudaGetLastError());
-      }
-      if (c1 >= N) break;
-      lu_invl_kernel<T><<<1, 256, INVL_SMEM, st>>>(LU, n, j0, jb, W);
-      LA_CUDA_TRY(cudaGetLastError());
+      const int parity = it & 1;
+      const bool has_next = c1 < kmin;
+      const int nb2 = has_next ? ((kmin - c1 < nb) ? (kmin - c1) : nb) : 0;
+      const int c2 = c1 + nb2;
+      double* W = Wbuf[parity];
       const double* L21 = A + (size_t)c1 * ld + j0;
-      auto trsm_update = [&](int cb, int ce) -> int {  // columns [cb, ce)
+      auto trsm_update = [&](int cb, int ce, cudaStream_t s) -> int {  // columns [cb, ce)
+        if (ce <= cb) return LA_OK;
         double* U12 = A + (size_t)j0 * ld + cb;
         LA_TRY(gemm_f64_tensor(W, MAX_NB, U12, ld, U12, ld, (size_t)jb, (size_t)jb, (size_t)(ce - cb), LA_GEMM_ASSIGN,
-                               st));  // in place: one tile row, every CTA reads its whole column block first
+                               s));  // in place: one tile row, every CTA reads its whole column block first
         if (c1 < M)
           LA_TRY(gemm_f64_tensor(L21, ld, U12, ld, A + (size_t)c1 * ld + cb, ld, (size_t)(M - c1), (size_t)jb,
-                                 (size_t)(ce - cb), LA_GEMM_SUB, st));
+                                 (size_t)(ce - cb), LA_GEMM_SUB, s));
         return LA_OK;
       };
-      if (c1 < kmin) {
-        const int nb2 = (kmin - c1 < nb) ? (kmin - c1) : nb;
-        const int c2 = c1 + nb2;
-        LA_TRY(trsm_update(c1, c2));  // the next panel's columns first
-        if (dbg == 5 && c2 < N) {  // debug: TRSM of the rest before the panel starts, only the update overlaps
-          double* U12r = A + (size_t)j0 * ld + c2;
-          LA_TRY(gemm_f64_tensor(W, MAX_NB, U12r, ld, U12r, ld, (size_t)jb, (size_t)jb, (size_t)(N - c2), LA_GEMM_ASSIGN, st));
-        }
-        LA_CUDA_TRY(cudaEventRecord(side->e1, st));
-        LA_CUDA_TRY(cudaStreamWaitEvent(sp, side->e1, 0));
-        LA_TRY(launch_panel(c1, nb2, sp));
-        LA_CUDA_TRY(cudaEventRecord(side->e2, sp));
-        if (dbg == 3) LA_CUDA_TRY(cudaStreamWaitEvent(st, side->e2, 0));  // debug: two streams, no overlap
-        if (c2 < N) {
-          if (dbg == 4 || dbg == 5) {
-            double* U12r = A + (size_t)j0 * ld + c2;
-            if (dbg == 4) {  // debug: only the TRSM overlaps
-              LA_TRY(gemm_f64_tensor(W, MAX_NB, U12r, ld, U12r, ld, (size_t)jb, (size_t)jb, (size_t)(N - c2), LA_GEMM_ASSIGN, st));
-              LA_CUDA_TRY(cudaStreamWaitEvent(st, side->e2, 0));
-            }
-            LA_TRY(gemm_f64_tensor(L21, ld, U12r, ld, A + (size_t)c1 * ld + c2, ld, (size_t)(M - c1), (size_t)jb,
-                                   (size_t)(N - c2), LA_GEMM_SUB, st));
-          } else {
-            LA_TRY(trsm_update(c2, N));  // overlaps the panel on sp
-          }
-        }
-        LA_CUDA_TRY(cudaStreamWaitEvent(st, side->e2, 0));
-        if (dbg == 7 || dbg == 9) {
-          lu_perm_kernel<T><<<1, 32, 0, st>>>(ws_base, G_cur, c1, nb2, piv_dev, sign_dev);
-          LA_CUDA_TRY(cudaGetLastError());
-        }
-      } else {
-        LA_TRY(trsm_update(c1, N));
+      // ---- chain ----
+      LA_TRY(launch_perm(j0, jb, parity, sp));
+      if (c1 < N) {
+        if (it > 0) LA_CUDA_TRY(cudaStreamWaitEvent(sp, side->e_bulk, 0));  // bulk(i-1) updated every column >= c1
+        LA_TRY(launch_swap(c1, c2, parity, sp));
+        lu_invl_kernel<T><<<1, INVL_THREADS, INVL_SMEM, sp>>>(LU, n, j0, jb, W);
+        LA_CUDA_TRY(cudaGetLastError());
       }
+      LA_CUDA_TRY(cudaEventRecord(side->e_head, sp));
+      if (has_next) {
+        LA_TRY(trsm_update(c1, c2, sp));
+        LA_TRY(launch_panel(c1, nb2, sp));
+      }
+      // ---- bulk ----
+      LA_CUDA_TRY(cudaStreamWaitEvent(st, side->e_head, 0));
+      LA_TRY(launch_swap(0, j0, parity, st));
+      LA_TRY(launch_swap(c2, N, parity, st));
+      LA_TRY(trsm_update(c2, N, st));
+      LA_CUDA_TRY(cudaEventRecord(side->e_bulk, st));
     }
+    // the caller's stream must also cover the tail of the chain stream
+    LA_CUDA_TRY(cudaEventRecord(side->e_head, sp));
+    LA_CUDA_TRY(cudaStreamWaitEvent(st, side->e_head, 0));
   }
   return LA_OK;
 }
