@@ -101,7 +101,7 @@ int main(int argc, char** argv) {
     CK(cudaEventCreate(&e1));
     int launches = 0;
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < 400; ++i) { dmma_loop<ACCS><<<sms * ctas, 256>>>(out, iters * 4); ++launches; }
+    for (int i = 0; i < 120; ++i) { dmma_loop<ACCS><<<sms * ctas, 256>>>(out, iters * 4); ++launches; }
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms;
@@ -120,7 +120,7 @@ int main(int argc, char** argv) {
             "{\"gpu_name\": \"%s\", \"sms\": %d, \"sm_max_mhz\": %d, \"dmma_tflops\": %.3f, \"dmma_warps_per_sm\": %d, "
             "\"dmma_tflops_sustained\": %.3f, \"dfma_tflops\": %.3f, \"dfma_warps_per_sm\": %d, "
             "\"how\": \"register-resident mma.sync.m8n8k4.f64 / fma.rn.f64 loops, 16 independent accumulators per thread, "
-            "best of 5, CUDA events; sustained = 400 back-to-back launches\"}\n",
+            "best of 5, CUDA events; sustained = 120 back-to-back launches (~2.5 s)\"}\n",
             p.name, sms, clk_khz / 1000, best_dmma, best_dmma_w, sustained, best_dfma, best_dfma_w);
     fclose(f);
   }

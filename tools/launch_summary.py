@@ -13,7 +13,7 @@ for r in csv.DictReader(lines):
     v = float(r["Metric Value"].replace(",", ""))
     unit = r["Metric Unit"]
     v = {"ns": v / 1e3, "us": v, "ms": v * 1e3, "s": v * 1e6}.get(unit, v)
-    short = re.sub(r"<.*", "", r["Kernel Name"]).split("::")[-1].replace("void ", "")
+    short = re.sub(r"<.*", "", r["Kernel Name"].replace("<unnamed>::", "")).split("::")[-1].replace("void ", "")
     agg[short][0] += 1
     agg[short][1] += v
     seq.append((short, v))
