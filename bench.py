@@ -375,7 +375,9 @@ def main():
         lu["frac_of_nominal_40"] = lu["lu_tflops"] / NOMINAL_FP64_TFLOPS
 
     cpu = None
-    if not args.skip_cpu:
+    if n_gpus > 1:
+        roofline["traffic"] = None  # the ncu capture is of the 1-GPU 8192^3 launch
+    if not args.skip_cpu and n_gpus == 1:  # the CPU baseline is a rank-0, N=1 figure
         threads = os.cpu_count() or 1
         rows = min(8192, 2 * threads)
         v, dt = cpu_reference_sample(8192, rows, threads)

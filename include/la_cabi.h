@@ -138,9 +138,12 @@ LA_API int la_identity_f32(la_buf* dst, size_t n);
 LA_API int la_fill_hash_f64_dev(double* dst, size_t count, uint64_t seed, uint64_t first_idx, void* cuda_stream);
 LA_API int la_fill_hash_f32_dev(float* dst, size_t count, uint64_t seed, uint64_t first_idx, void* cuda_stream);
 
-/* Test hook (not part of the drop-in surface): 0 = automatic kernel choice, 1 = force the generic CUDA-core GEMM,
- * 2 = force the TMA/DMMA GEMM (fails with LA_ERR_INVALID when the operands are not TMA-addressable). */
+/* Test hooks (not part of the drop-in surface).  fp64: 0 = automatic kernel choice, 1 = force the generic CUDA-core GEMM,
+ * 2 = force the TMA/DMMA GEMM (fails with LA_ERR_INVALID when the operands are not TMA-addressable), 3 / 4 = force its
+ * 128x64 / 128x128 tile configuration. */
 LA_API int la_debug_set_gemm_path(int path);
+/* fp32: 0 = automatic, 1 = force the CUDA-core kernel, 2 = force the tcgen05 TF32 kernel */
+LA_API int la_debug_set_gemm_f32_path(int path);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,7 @@ struct la_buf {
 
 namespace la {
 void debug_set_gemm_path(int p);
+void debug_set_gemm_f32_path(int p);
 }
 
 namespace {
@@ -431,6 +432,13 @@ int la_fill_hash_f32_dev(float* dst, size_t count, uint64_t seed, uint64_t first
 int la_debug_set_gemm_path(int path) {
   LA_REQUIRE(path >= 0 && path <= 4, "la_debug_set_gemm_path: bad value %d", path);
   la::debug_set_gemm_path(path);
+  return LA_OK;
+}
+
+/* test hook: 0 = automatic, 1 = force the CUDA-core fp32 kernel, 2 = force the tcgen05 TF32 kernel */
+int la_debug_set_gemm_f32_path(int path) {
+  LA_REQUIRE(path >= 0 && path <= 2, "la_debug_set_gemm_f32_path: bad value %d", path);
+  la::debug_set_gemm_f32_path(path);
   return LA_OK;
 }
 

@@ -1,12 +1,241 @@
-// gemm_f32.cu -- fp32 GEMM entry point.  Replaces the reference loops src/matrix/mod.rs:965-973 with T = f32
-// (and src/matrix/simd.rs:189-219, which has the same per-element order).
+// gemm_f32.cu -- fp32 GEMM: C[m x n] (=, +=) A[m x k] * B[k x n], row-major, for sm_100a.
 //
-// Round-1 state: fp32 runs on the CUDA-core kernel (gemm_simt.cu, FFMA, full fp32 accuracy).  The tcgen05
-// kind::tf32 kernel (TMEM accumulators, TMA-fed) is the next step; the fp32 LU trailing update must stay on an
-// fp32-accurate path (FFMA or 3xTF32) to keep the backward error within 10x of the reference's.
+// Replaces the reference loops src/matrix/mod.rs:965-973 with T = f32 (and src/matrix/simd.rs:189-219, which has the same
+// per-element order).  Two paths:
+//   * tcgen05 TF32 kernel (this file): 5th-generation tensor cores, `tcgen05.mma.cta_group::1.kind::tf32` (SASS UTCHMMA)
+//     issued by ONE thread, accumulators in TENSOR MEMORY (128 lanes x 256 fp32 columns), operands fed by TMA into a
+//     4-stage shared-memory ring, epilogue `tcgen05.ld` -> registers -> 128-byte row segments.  TF32 keeps 10 mantissa bits
+//     of each operand (relative error <= 2^-10 per factor), inside the 1e-4*k parity bar for k >= 32; shallower or
+//     unaligned problems and the fp32 LU trailing update (which needs fp32-grade accuracy: LA_GEMM_SUB) stay on
+//   * the CUDA-core kernel (gemm_simt.cu): exact fp32, reference summation order.
+//
+// Tile: 128 (M) x 256 (N) x 32 (K, = 128 bytes of fp32 = one swizzle row).  Per stage: A box 32 k x 128 rows and B^T box
+// 32 k x 256 rows, both K-major with SWIZZLE_128B.  Row-major B has N contiguous, i.e. it is an "MN-major" operand; the
+// instruction descriptor has a bit for that, but kind::tf32 with an MN-major B returned all-zero accumulators on this
+// toolchain/driver for every LBO/SBO choice (measured, round 1), so B is transposed once per call into a scratch buffer
+// (B^T, K-major) by a bandwidth-bound tile kernel (<= 6 % of the GEMM time at 8192^3, 1 % at the 65536x1024x16384 config).
+// One MMA = M128 N256 K8; four per stage.  Warp roles (192 threads): warp 0 lane 0 = TMA producer, warp 1 = TMEM
+// allocator + MMA issuer (one elected lane), warps 2-5 = epilogue (TMEM lane quarter = warp % 4).
+#include <stdlib.h>
+
 #include "la_common.cuh"
 
 namespace la {
+namespace {
+
+constexpr int TBM = 128, TBN = 256, TBK = 32;
+constexpr int TSTAGES = 4;
+constexpr int TA_BYTES = TBM * TBK * 4;        // 16 KiB
+constexpr int TB_BYTES = TBK * TBN * 4;        // 32 KiB
+constexpr int TSTAGE_BYTES = TA_BYTES + TB_BYTES;
+constexpr int TF32_THREADS = 192;
+constexpr int TF32_SMEM = TSTAGES * TSTAGE_BYTES + 256 + 1024;  // stages + barriers/tmem slot + alignment slack
+constexpr int TMEM_COLS = 256;
+constexpr size_t TF32_MIN_K = 32;  // below this TF32's 2^-10 input rounding is not covered by the 1e-4*k parity bar
+
+// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading/stride byte offsets (all
+// >> 4), version 1 (Blackwell), layout type SWIZZLE_128B = 2 in bits [61,64).
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // version_
+  d |= (uint64_t)2 << 61;  // layout_type_ = SWIZZLE_128B
+  return d;
+}
+// 32-bit instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4)                       // c_format = F32
+         | (2u << 7) | (2u << 10)        // a_format = b_format = TF32
+         | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16)
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {  // arrives on `bar` when all prior MMAs of this thread finish
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TF32_THREADS, 1)
+gemm_f32_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     float* __restrict__ C, size_t ldc, int M, int N, int K, int tiles_m, int tiles_n) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TSTAGES * TSTAGE_BYTES);
+  uint64_t* empty = full + TSTAGES;
+  uint64_t* accum_full = empty + TSTAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // rasterise m fastest inside groups of 8 tile rows: the group shares each B tile column while it is hot in L2
+  constexpr int GROUP = 8;
+  const int tile = blockIdx.x;
+  const int per_group = GROUP * tiles_n;
+  const int first_m = (tile / per_group) * GROUP;
+  const int rows_here = min(GROUP, tiles_m - first_m);
+  const int tile_m = first_m + (tile % per_group) % rows_here;
+  const int tile_n = (tile % per_group) / rows_here;
+  const int m0 = tile_m * TBM, n0 = tile_n * TBN;
+  const int ktiles = (K + TBK - 1) / TBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TSTAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {  // TMEM allocation is warp-wide; the base address lands in shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      for (int kt = 0; kt < ktiles; ++kt) {
+        const int s = kt % TSTAGES;
+        mbar_wait(&empty[s], ((kt / TSTAGES) & 1) ^ 1);
+        uint8_t* sA = smem + s * TSTAGE_BYTES;
+        uint8_t* sB = sA + TA_BYTES;
+        mbar_arrive_expect_tx(&full[s], TSTAGE_BYTES);
+        tma_load_2d(sA, &tmA, &full[s], kt * TBK, m0);  // 32 k (inner, 128 B) x 128 rows
+        tma_load_2d(sB, &tmB, &full[s], kt * TBK, n0);  // B^T: 32 k (inner, 128 B) x 256 n-rows
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: a single thread drives the tensor core =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(TBM, TBN, /*A K-major*/ 0, /*B^T K-major*/ 0);
+      for (int kt = 0; kt < ktiles; ++kt) {
+        const int s = kt % TSTAGES;
+        mbar_wait(&full[s], (kt / TSTAGES) & 1);
+        tcgen05_fence_after();
+        const uint32_t sA = smem_u32(smem + s * TSTAGE_BYTES);
+        const uint32_t sB = sA + TA_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < TBK / 8; ++kk) {
+          // A, K-major: 8 k = 32 bytes further along the 128-byte swizzled row; 8-row groups are 1024 B apart (SBO)
+          const uint64_t adesc = umma_smem_desc(sA + kk * 32, 16, 1024);
+          const uint64_t bdesc = umma_smem_desc(sB + kk * 32, 16, 1024);  // B^T: same K-major layout as A
+          umma_tf32(tmem_base, adesc, bdesc, idesc, (kt | kk) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
+      }
+      umma_commit(accum_full);   // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global.  Warp w reads TMEM lanes [32*(w%4), +32): lane == tile row =====
+    const int quarter = warp & 3;
+    mbar_wait(accum_full, 0);
+    tcgen05_fence_after();
+    const int row = m0 + quarter * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < TBN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+      const int col = n0 + c0;
+      if (row < M && col < N) {
+        float* p = C + (size_t)row * ldc + col;
+        if (col + 32 <= N) {
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            float4 o = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                                   __uint_as_float(r[4 * v + 3]));
+            if (MODE == LA_GEMM_ADD) {
+              const float4 old = __ldcg(reinterpret_cast<const float4*>(p) + v);
+              o.x += old.x;
+              o.y += old.y;
+              o.z += old.z;
+              o.w += old.w;
+            }
+            reinterpret_cast<float4*>(p)[v] = o;
+          }
+        } else {
+          for (int v = 0; v < 32 && col + v < N; ++v) {
+            float o = __uint_as_float(r[v]);
+            if (MODE == LA_GEMM_ADD) o += p[v];
+            p[v] = o;
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// B^T[n][k] = B[k][n] through 32 x 33 shared-memory tiles: both the read and the write are coalesced 128-byte rows.
+__global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restrict__ B, size_t ldb, float* __restrict__ BT,
+                                                            size_t ldt, int K, int N) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int r = 0; r < 32; r += 8) {
+    const int kk = k0 + ty + r, nn = n0 + tx;
+    tile[ty + r][tx] = (kk < K && nn < N) ? B[(size_t)kk * ldb + nn] : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 32; r += 8) {
+    const int nn = n0 + ty + r, kk = k0 + tx;
+    if (nn < N && kk < K) BT[(size_t)nn * ldt + kk] = tile[tx][ty + r];
+  }
+}
+
+int g_f32_path = getenv("LA_GEMM_F32_PATH") ? atoi(getenv("LA_GEMM_F32_PATH")) : 0;  // 0 auto, 1 CUDA-core, 2 tcgen05
+
+template <int MODE>
+int launch_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, size_t ldc, int M, int N, int K,
+                cudaStream_t st) {
+  LA_CUDA_TRY(cudaFuncSetAttribute(gemm_f32_tf32_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF32_SMEM));
+  const int tiles_m = (M + TBM - 1) / TBM, tiles_n = (N + TBN - 1) / TBN;
+  gemm_f32_tf32_kernel<MODE><<<tiles_m * tiles_n, TF32_THREADS, TF32_SMEM, st>>>(tmA, tmB, C, ldc, M, N, K, tiles_m, tiles_n);
+  LA_CUDA_TRY(cudaGetLastError());
+  return LA_OK;
+}
+
+}  // namespace
+
+void debug_set_gemm_f32_path(int p) { g_f32_path = p; }
 
 int gemm_f32_dev(const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, size_t m, size_t k,
                  size_t n, int mode, cudaStream_t st) {
@@ -17,7 +246,36 @@ int gemm_f32_dev(const float* A, size_t lda, const float* B, size_t ldb, float* 
   LA_REQUIRE(lda >= k && ldb >= n && ldc >= n, "la_gemm_f32: leading dimension smaller than row length");
   LA_REQUIRE(mode == LA_GEMM_ASSIGN || mode == LA_GEMM_SUB || mode == LA_GEMM_ADD, "la_gemm_f32: bad mode %d", mode);
   LA_REQUIRE(m < (1u << 30) && n < (1u << 30) && k < (1u << 30), "la_gemm_f32: dimension too large");
-  return gemm_simt<float>(A, lda, B, ldb, C, ldc, m, k, n, mode, st);
+
+  const bool aligned = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0) &&
+                       lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0;
+  const bool small = (double)m * (double)n * (double)k <= 128.0 * 128.0 * 128.0;  // bit-exact reference-order kernel
+  bool use_tc = aligned && !small && k >= TF32_MIN_K && mode != LA_GEMM_SUB;
+  if (g_f32_path == 1) use_tc = false;
+  if (g_f32_path == 2) {
+    if (!aligned || mode == LA_GEMM_SUB)
+      return fail(LA_ERR_INVALID, "la_gemm_f32: tcgen05 path forced but operands are unaligned or mode is SUB");
+    use_tc = true;
+  }
+  if (!use_tc) return gemm_simt<float>(A, lda, B, ldb, C, ldc, m, k, n, mode, st);
+
+  // B^T into scratch (K-major operand for the tensor core), leading dimension padded to 16 bytes
+  const size_t ldt = (k + 3) & ~(size_t)3;
+  void* bt = nullptr;
+  LA_TRY(scratch_get(ctx->device, 12, n * ldt * sizeof(float), &bt));
+  {
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((k + 31) / 32));
+    LA_REQUIRE(grid.y <= 65535, "la_gemm_f32: inner dimension too large for the transpose grid");
+    transpose_f32_kernel<<<grid, 256, 0, st>>>(B, ldb, (float*)bt, ldt, (int)k, (int)n);
+    LA_CUDA_TRY(cudaGetLastError());
+  }
+  CUtensorMap tmA, tmB;
+  LA_TRY(encode_tensor_map_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, k, m, lda * 4, TBK, TBM,
+                              CU_TENSOR_MAP_SWIZZLE_128B));
+  LA_TRY(encode_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, bt, k, n, ldt * 4, TBK, TBN,
+                              CU_TENSOR_MAP_SWIZZLE_128B));
+  if (mode == LA_GEMM_ASSIGN) return launch_tf32<LA_GEMM_ASSIGN>(tmA, tmB, C, ldc, (int)m, (int)n, (int)k, st);
+  return launch_tf32<LA_GEMM_ADD>(tmA, tmB, C, ldc, (int)m, (int)n, (int)k, st);
 }
 
 template <>

@@ -68,6 +68,7 @@ SIGNATURES = {
     "la_fill_hash_f64_dev": ([_p, _sz, _u64, _u64, _p], _i),
     "la_fill_hash_f32_dev": ([_p, _sz, _u64, _u64, _p], _i),
     "la_debug_set_gemm_path": ([_i], _i),
+    "la_debug_set_gemm_f32_path": ([_i], _i),
 }
 
 _lib = None

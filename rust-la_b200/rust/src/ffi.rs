@@ -79,6 +79,7 @@ extern "C" {
     pub fn la_fill_hash_f64_dev(dst: *mut f64, count: usize, seed: u64, first_idx: u64, cuda_stream: *mut c_void) -> c_int;
     pub fn la_fill_hash_f32_dev(dst: *mut f32, count: usize, seed: u64, first_idx: u64, cuda_stream: *mut c_void) -> c_int;
     pub fn la_debug_set_gemm_path(path: c_int) -> c_int;
+    pub fn la_debug_set_gemm_f32_path(path: c_int) -> c_int;
 }
 
 /// Panics with the library's message when `status != LA_OK` -- contract violations panic in the reference too

@@ -46,6 +46,29 @@ def test_gemm_f32_host_api(oracle, shape):
     assert max_rel_err(c, ref) <= F32_TOL * k
 
 
+@pytest.mark.parametrize("shape", [(128, 32, 256), (512, 1024, 256), (1000, 520, 768), (640, 100, 328), (130, 64, 260),
+                                   (2048, 1024, 2048), (256, 36, 512)])
+@pytest.mark.parametrize("mode", [0, 2])
+def test_gemm_f32_tcgen05_tf32(oracle, shape, mode):
+    """The tcgen05 kind::tf32 kernel (TMEM accumulators, TMA-fed), forced, vs the fp32 oracle: <= 1e-4 * k relative."""
+    m, k, n = shape
+    a = oracle.fill((m, k), 1, np.float32)
+    b = oracle.fill((k, n), 2, np.float32)
+    c0 = oracle.fill((m, n), 4, np.float32)
+    ref = oracle.gemm(a, b)
+    want = ref if mode == 0 else (c0.astype(np.float64) + ref.astype(np.float64))
+    da, db, dc = DevBuf.from_array(a), DevBuf.from_array(b), DevBuf.from_array(c0)
+    check(lib().la_debug_set_gemm_f32_path(2))
+    try:
+        gemm_dev(da, k, db, n, dc, n, m, k, n, mode, np.float32)
+        sync()
+    finally:
+        lib().la_debug_set_gemm_f32_path(0)
+    got = dc.to_array((m, n), np.float32)
+    assert np.all(np.isfinite(got))
+    assert max_rel_err(got, want) <= F32_TOL * k
+
+
 def test_gemm_signed_inputs_absolute_error(oracle):
     """Inputs in [-0.5, 0.5): sums cancel, so compare against the norm-wise bound k * eps * |a|.|b| instead."""
     m, k, n = 192, 777 * 2, 320
