@@ -26,6 +26,8 @@
 #include <stdlib.h>
 
 #include <type_traits>
+#include <vector>
+#include <stdio.h>
 
 #include "la_common.cuh"
 
@@ -170,312 +172,377 @@ __device__ __forceinline__ void key_merge(double& k, int& i, double k2, int i2) 
 // matrices) are reproduced.  EXACT = false subtracts each separately rounded product immediately (half the shared
 // memory); later panels carry DMMA-rounded trailing updates anyway.
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// Per column c the CTAs must agree on the pivot (a grid-wide arg-max) and every CTA needs the pivot row: two dependent
+// trips through L2.  The rank-1 update of column c is therefore split (look-ahead INSIDE the panel):
+//   urgent : multipliers of column c, update of column c+1 only, arg-max of column c+1, and the full update of the two
+//            rows that are published for step c+1 (the CTA's candidate row and, if it lives here, the next diagonal row);
+//   bulk   : columns c+2.. of all other rows -- done by warps 1..7 WHILE warp 0 runs the exchange of step c+1.
+// so the column time is max(exchange latency, update time) instead of their sum.
 template <typename T, bool EXACT>
 __global__ void __launch_bounds__(PANEL_THREADS, 1)
 lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_per_cta, void* ws_base, unsigned epoch) {
   typedef typename LL<T>::word llw;
+  constexpr int Q = MAX_NB / 32;
   extern __shared__ __align__(16) unsigned char panel_smem[];
-  T* rows = reinterpret_cast<T*>(panel_smem);            // [rows_per_cta][jb]: original values, then final L / U
-  T* sums = rows + (size_t)rows_per_cta * jb;            // [rows_per_cta][jb]: deferred sums (EXACT only)
+  const int ldr = jb | 1;  // odd row stride: column walks (lanes <-> rows) and row walks are both conflict-free
+  T* rows = reinterpret_cast<T*>(panel_smem);            // [rows_per_cta][ldr]: original values, then final L / U
+  T* sums = rows + (size_t)rows_per_cta * ldr;           // [rows_per_cta][ldr]: deferred sums (EXACT only)
   __shared__ double wkey[PANEL_WARPS];
   __shared__ int widx[PANEL_WARPS];
-  __shared__ T s_prow[MAX_NB];  // the step's pivot row as stored / its current values (row c of U)
-  __shared__ T s_u[MAX_NB];
+  // per step parity: the pivot row as stored / its current values (row c of U) / the diagonal row it trades places with
+  __shared__ T s_prow[2][MAX_NB];
+  __shared__ T s_u[2][MAX_NB];
+  __shared__ T s_trow[2][XROW];
+  __shared__ int s_p[2];
 
   const int G = gridDim.x;
   const WsView<T> ws = ws_view<T>(ws_base, G);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_base = j0 + blockIdx.x * rows_per_cta;          // first absolute row of this CTA
   const int nloc = max(0, min(rows_per_cta, m - row_base));     // rows held by this CTA
-  const int nq = (jb + 31) >> 5;                                // column groups of 32 per lane
+  const int WB = (nloc + PANEL_WARPS - 1) / PANEL_WARPS;        // urgent phase: warp w owns rows [w*WB, (w+1)*WB)
 
   auto value = [&](int lr, int col) -> T {
-    const T a = rows[(size_t)lr * jb + col];
-    return EXACT ? sub_rn(a, sums[(size_t)lr * jb + col]) : a;
+    const T a = rows[(size_t)lr * ldr + col];
+    return EXACT ? sub_rn(a, sums[(size_t)lr * ldr + col]) : a;
   };
 
   // ---- load the CTA's rows of the panel into shared memory (row segments of jb contiguous elements) ----
   for (int idx = threadIdx.x; idx < nloc * jb; idx += PANEL_THREADS) {
     const int lr = idx / jb, c = idx - lr * jb;
-    rows[idx] = __ldcg(&A[(size_t)(row_base + lr) * ld + j0 + c]);
-    if (EXACT) sums[idx] = (T)0;
+    rows[(size_t)lr * ldr + c] = __ldcg(&A[(size_t)(row_base + lr) * ld + j0 + c]);
+    if (EXACT) sums[(size_t)lr * ldr + c] = (T)0;
   }
   __syncthreads();
 
-  // ---- initial per-warp arg-max of column 0 ----
+  // ---- per-warp arg-max of column 0 ----
   {
     double k = -2.0;
     int ki = INT_MAX;
-    for (int lr = warp; lr < nloc; lr += PANEL_WARPS) {
-      const int gr = row_base + lr;
-      if (lane == 0) key_merge(k, ki, pivot_key(rows[(size_t)lr * jb], gr == j0), gr);
+    for (int l = lane; l < WB; l += 32) {
+      const int lr = warp * WB + l;
+      if (lr < nloc) key_merge(k, ki, pivot_key(rows[(size_t)lr * ldr], row_base + lr == j0), row_base + lr);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double k2 = __shfl_xor_sync(0xffffffffu, k, off);
+      const int i2 = __shfl_xor_sync(0xffffffffu, ki, off);
+      key_merge(k, ki, k2, i2);
     }
     if (lane == 0) {
       wkey[warp] = k;
       widx[warp] = ki;
     }
   }
+  __syncthreads();
 
-  // Per column c (no grid barrier, no atomics -- everything crosses CTAs as flagged words):
-  //   (A) CTA sync: all rows updated, per-warp arg-max of column c in wkey/widx.
-  //       Every warp reduces the 8 partial arg-maxes; warps 0..3 each publish one REPLICA of the CTA's candidate row
-  //       (readers spread over the replicas, so the winner's row is not one 148-reader hot spot in L2); the owner warp
-  //       of the diagonal row publishes it.  Warp 0 then pushes the CTA's record into every reader's private inbox,
-  //       polls its own inbox (one poller per CTA: polling traffic delays the very stores it is waiting for), picks the
-  //       winner and fetches the winner's row into shared memory.
-  //   (B) CTA sync: interchange, multipliers (lanes <-> rows), rank-1 update (lanes <-> columns), arg-max of column c+1.
-  // The exchange area is double-buffered by step parity: a CTA can publish step c+2 only after it has read every step
-  // c+1 record, and those exist only once every CTA has finished reading step c.
-  __shared__ int s_p;
-  for (int c = 0; c < jb; ++c) {
-    const int par = c & 1;
-    const int diag = j0 + c;  // absolute row/col index of this step's diagonal
-    const unsigned tag = (epoch << 8) | (unsigned)(c + 1);
+  // Publishes this CTA's contribution to step cn and (warp 0) runs the exchange; everything crosses CTAs as flagged
+  // words -- no grid barrier, no atomics.  `c` = cn - 1 is the step whose rank-1 update is still pending on the two
+  // published rows (c < 0: none).  Warps 0..3 each publish one REPLICA of the candidate row (readers spread over the
+  // replicas, so the winner's row is not one 148-reader hot spot in L2); warp 1 also publishes the next diagonal row
+  // and writes the two updated rows back once the other replica warps have read them (named barrier 1).
+  // Returns (to every warp) the local indices of the rows the bulk update must skip.
+  // The exchange area is double-buffered by step parity: a CTA publishes step cn+1 only after it has read every step
+  // cn record, and those exist only once every CTA has finished reading step cn-1.
+  auto publish_and_exchange = [&](int cn, int& skip_a, int& skip_b) {
+    const int c = cn - 1;
+    const int par = cn & 1;
+    const int diag = j0 + cn;  // absolute row/col index of step cn's diagonal
+    const unsigned tag = (epoch << 8) | (unsigned)(cn + 1);
     const unsigned tag16 = tag & 0xffffu;
-    __syncthreads();          // (A)
+    // CTA-wide candidate (every warp)
+    double k = (lane < PANEL_WARPS) ? wkey[lane] : -2.0;
+    int ki = (lane < PANEL_WARPS) ? widx[lane] : INT_MAX;
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) {
+      const double k2 = __shfl_xor_sync(0xffffffffu, k, off);
+      const int i2 = __shfl_xor_sync(0xffffffffu, ki, off);
+      key_merge(k, ki, k2, i2);
+    }
+    k = __shfl_sync(0xffffffffu, k, 0);
+    ki = __shfl_sync(0xffffffffu, ki, 0);
     const bool own_diag = diag >= row_base && diag < row_base + nloc;
-    if (own_diag && ((diag - row_base) % PANEL_WARPS) == warp) {
-      // the diagonal row, published by the warp that will overwrite it in the interchange below
-      const size_t off = (size_t)(diag - row_base) * jb;
-      llw* dst = ws.top_row + (size_t)par * XROW;
-      for (int q = 0; q < nq; ++q)
+    skip_a = (ki != INT_MAX) ? ki - row_base : -1;
+    skip_b = own_diag ? diag - row_base : -1;
+    if (warp >= ROW_REPLICAS) return;
+
+    if (warp == 0) {  // the records first: they are what every other CTA is waiting for
+      const unsigned long long kb = (unsigned long long)__double_as_longlong(k);
+      for (int rd = lane; rd < G; rd += 32)  // one copy into every reader's inbox
+        st_relaxed_2x64(&ws.rec[((size_t)par * G + rd) * G + blockIdx.x],
+                        rec_pack((unsigned)(kb >> 32), (unsigned)ki >> 16, tag), rec_pack((unsigned)kb, (unsigned)ki, tag));
+    }
+    // a row with the pending update of step c applied (columns > cn; column cn was updated in the urgent phase)
+    const T* uc = s_u[c & 1];
+    auto updated_row = [&](int lr, T (&va)[Q], T (&vs)[Q]) {
+      const size_t off = (size_t)lr * ldr;
+      const T lk = (c >= 0) ? rows[off + c] : (T)0;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const int col = lane + 32 * q;
+        va[q] = vs[q] = (T)0;
+        if (col < jb) {
+          va[q] = rows[off + col];
+          if (EXACT) vs[q] = sums[off + col];
+          if (c >= 0 && col > cn) {
+            if (EXACT) vs[q] = add_rn(vs[q], mul_rn(lk, uc[col]));  // s = s + l*u, k ascending (lu.rs:125)
+            else va[q] = sub_rn(va[q], mul_rn(lk, uc[col]));
+          }
+        }
+      }
+    };
+    auto publish_row = [&](llw* dst, const T (&va)[Q], const T (&vs)[Q]) {
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
         if (lane + 32 * q < jb) {
-          LL<T>::store(&dst[lane + 32 * q], rows[off + lane + 32 * q], tag);
-          if (EXACT) LL<T>::store(&dst[MAX_NB + lane + 32 * q], sums[off + lane + 32 * q], tag);
+          LL<T>::store(&dst[lane + 32 * q], va[q], tag);
+          if (EXACT) LL<T>::store(&dst[MAX_NB + lane + 32 * q], vs[q], tag);
         }
-    }
-    if (warp < ROW_REPLICAS) {
-      // CTA-wide candidate
-      double k = (lane < PANEL_WARPS) ? wkey[lane] : -2.0;
-      int ki = (lane < PANEL_WARPS) ? widx[lane] : INT_MAX;
+    };
+    auto write_back = [&](int lr, const T (&va)[Q], const T (&vs)[Q]) {
+      const size_t off = (size_t)lr * ldr;
 #pragma unroll
-      for (int off = 4; off > 0; off >>= 1) {
-        const double k2 = __shfl_xor_sync(0xffffffffu, k, off);
-        const int i2 = __shfl_xor_sync(0xffffffffu, ki, off);
-        key_merge(k, ki, k2, i2);
+      for (int q = 0; q < Q; ++q) {
+        const int col = lane + 32 * q;
+        if (col < jb && col > cn) {
+          if (EXACT) sums[off + col] = vs[q];
+          else rows[off + col] = va[q];
+        }
       }
-      k = __shfl_sync(0xffffffffu, k, 0);
-      ki = __shfl_sync(0xffffffffu, ki, 0);
-      if (ki != INT_MAX) {  // replica `warp` of the candidate row
-        const size_t off = (size_t)(ki - row_base) * jb;
-        llw* dst = ws.cand_row + (((size_t)par * ROW_REPLICAS + warp) * G + blockIdx.x) * XROW;
-        for (int q = 0; q < nq; ++q)
-          if (lane + 32 * q < jb) {
-            LL<T>::store(&dst[lane + 32 * q], rows[off + lane + 32 * q], tag);
-            if (EXACT) LL<T>::store(&dst[MAX_NB + lane + 32 * q], sums[off + lane + 32 * q], tag);
-          }
-      }
-      if (warp == 0) {
-        const unsigned long long kb = (unsigned long long)__double_as_longlong(k);
-        for (int rd = lane; rd < G; rd += 32)  // one copy into every reader's inbox
-          st_relaxed_2x64(&ws.rec[((size_t)par * G + rd) * G + blockIdx.x],
-                          rec_pack((unsigned)(kb >> 32), (unsigned)ki >> 16, tag), rec_pack((unsigned)kb, (unsigned)ki, tag));
-        // poll the own inbox: all loads of a pass are in flight together
-        double bk = -2.0;
-        int bp = INT_MAX, bcta = 0;
-        constexpr int RPL = 5;
-        for (int base = 0; base < G; base += 32 * RPL) {
-          unsigned long long ra[RPL], rb[RPL];
-          bool ok[RPL];
-#pragma unroll
-          for (int i = 0; i < RPL; ++i) ok[i] = base + lane + 32 * i >= G;
-          bool all;
-          do {
-#pragma unroll
-            for (int i = 0; i < RPL; ++i)
-              if (!ok[i]) ld_relaxed_2x64(&ws.rec[((size_t)par * G + blockIdx.x) * G + base + lane + 32 * i], ra[i], rb[i]);
-            all = true;
-#pragma unroll
-            for (int i = 0; i < RPL; ++i)
-              if (!ok[i]) {
-                ok[i] = (unsigned)(ra[i] & 0xffffu) == tag16 && (unsigned)(rb[i] & 0xffffu) == tag16;
-                all &= ok[i];
-              }
-          } while (!all);
-#pragma unroll
-          for (int i = 0; i < RPL; ++i) {
-            const int b = base + lane + 32 * i;
-            if (b < G) {
-              const double k2 = __longlong_as_double((long long)((ra[i] & 0xffffffff00000000ull) | (rb[i] >> 32)));
-              const int i2 = (int)((((unsigned)(ra[i] >> 16) & 0xffffu) << 16) | ((unsigned)(rb[i] >> 16) & 0xffffu));
-              if (k2 > bk || (k2 == bk && i2 < bp)) {
-                bk = k2;
-                bp = i2;
-                bcta = b;
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          const double k2 = __shfl_xor_sync(0xffffffffu, bk, off);
-          const int i2 = __shfl_xor_sync(0xffffffffu, bp, off);
-          const int c2 = __shfl_xor_sync(0xffffffffu, bcta, off);
-          if (k2 > bk || (k2 == bk && i2 < bp)) {
-            bk = k2;
-            bp = i2;
-            bcta = c2;
-          }
-        }
-        // bp = absolute pivot row (>= diag), held by CTA bcta: fetch its row from "our" replica
-        const llw* prow_g =
-            ws.cand_row + (((size_t)par * ROW_REPLICAS + (blockIdx.x % ROW_REPLICAS)) * G + bcta) * XROW;
-        T pa[MAX_NB / 32], ps[MAX_NB / 32];
-        bool ok[MAX_NB / 32];
-#pragma unroll
-        for (int q = 0; q < MAX_NB / 32; ++q) {
-          ok[q] = lane + 32 * q >= jb;
-          pa[q] = (T)0;
-          ps[q] = (T)0;
-        }
-        bool all;
-        do {
-          all = true;
-#pragma unroll
-          for (int q = 0; q < MAX_NB / 32; ++q)
-            if (!ok[q]) {
-              bool v = LL<T>::load(&prow_g[lane + 32 * q], tag, pa[q]);
-              if (EXACT) v &= LL<T>::load(&prow_g[MAX_NB + lane + 32 * q], tag, ps[q]);
-              ok[q] = v;
-              all &= v;
-            }
-        } while (!all);
-#pragma unroll
-        for (int q = 0; q < MAX_NB / 32; ++q) {
-          const int col = lane + 32 * q;
-          if (col < jb) {
-            s_prow[col] = pa[q];
-            s_u[col] = EXACT ? sub_rn(pa[q], ps[q]) : pa[q];
-          }
-        }
-        if (lane == 0) s_p = bp;
-      }
+    };
+    T ca[Q], cs[Q];
+    if (skip_a >= 0) {
+      updated_row(skip_a, ca, cs);
+      if (c >= 0 && warp != 1) named_bar_arrive(1, 32 * ROW_REPLICAS);  // our read of the row is done
+      publish_row(ws.cand_row + (((size_t)par * ROW_REPLICAS + warp) * G + blockIdx.x) * XROW, ca, cs);
     }
-    __syncthreads();  // (B) winner and pivot row are in shared memory
-    const int p = s_p;
-    T prow[MAX_NB / 32];  // the pivot row as stored (cols < c: final L entries; cols >= c: original values in EXACT)
-    T u[MAX_NB / 32];     // its current values = row c of U for cols >= c
-#pragma unroll
-    for (int q = 0; q < MAX_NB / 32; ++q) {
-      const int col = lane + 32 * q;
-      prow[q] = (col < jb) ? s_prow[col] : (T)0;
-      u[q] = (col > c && col < jb) ? s_u[col] : (T)0;  // zero outside the update range: no predicates in the loop
+    if (warp == 1) {
+      T da[Q], ds[Q];
+      if (skip_b >= 0) {
+        updated_row(skip_b, da, ds);  // == the candidate row when skip_b == skip_a (not yet written back)
+        publish_row(ws.top_row + (size_t)par * XROW, da, ds);
+      }
+      if (c >= 0) {
+        if (skip_a >= 0) named_bar_sync(1, 32 * ROW_REPLICAS);  // warps 0, 2, 3 have read the candidate row
+        if (skip_a >= 0) write_back(skip_a, ca, cs);
+        if (skip_b >= 0 && skip_b != skip_a) write_back(skip_b, da, ds);
+      }
+      return;
     }
-    const T pv = s_u[c];
+    if (warp != 0) return;
 
-    if (blockIdx.x == 0 && threadIdx.x == 0) ws.hdr->ipiv[c] = p;
-
-    // ---- interchange (whole panel row; the rest of the row is swapped by lu_swap*_kernel) ----
-    if (p != diag && p >= row_base && p < row_base + nloc && ((p - row_base) % PANEL_WARPS) == warp) {
-      const llw* trow_g = ws.top_row + (size_t)par * XROW;
-      const size_t off = (size_t)(p - row_base) * jb;
-      T ta[MAX_NB / 32], ts[MAX_NB / 32];
-      bool ok[MAX_NB / 32];
+    // ---- warp 0: poll the own inbox (one poller per CTA: polling traffic delays the very stores it is waiting for);
+    //      all loads of a pass are in flight together ----
+    double bk = -2.0;
+    int bp = INT_MAX, bcta = 0;
+    constexpr int RPL = 5;
+    for (int base = 0; base < G; base += 32 * RPL) {
+      unsigned long long ra[RPL], rb[RPL];
+      bool ok[RPL];
 #pragma unroll
-      for (int q = 0; q < MAX_NB / 32; ++q) {
-        ok[q] = lane + 32 * q >= jb;
-        ta[q] = (T)0;
-        ts[q] = (T)0;
-      }
+      for (int i = 0; i < RPL; ++i) ok[i] = base + lane + 32 * i >= G;
       bool all;
       do {
+#pragma unroll
+        for (int i = 0; i < RPL; ++i)
+          if (!ok[i]) ld_relaxed_2x64(&ws.rec[((size_t)par * G + blockIdx.x) * G + base + lane + 32 * i], ra[i], rb[i]);
         all = true;
 #pragma unroll
-        for (int q = 0; q < MAX_NB / 32; ++q)
-          if (!ok[q]) {
-            bool v = LL<T>::load(&trow_g[lane + 32 * q], tag, ta[q]);
-            if (EXACT) v &= LL<T>::load(&trow_g[MAX_NB + lane + 32 * q], tag, ts[q]);
-            ok[q] = v;
-            all &= v;
+        for (int i = 0; i < RPL; ++i)
+          if (!ok[i]) {
+            ok[i] = (unsigned)(ra[i] & 0xffffu) == tag16 && (unsigned)(rb[i] & 0xffffu) == tag16;
+            all &= ok[i];
           }
       } while (!all);
 #pragma unroll
-      for (int q = 0; q < MAX_NB / 32; ++q)
+      for (int i = 0; i < RPL; ++i) {
+        const int b = base + lane + 32 * i;
+        if (b < G) {
+          const double k2 = __longlong_as_double((long long)((ra[i] & 0xffffffff00000000ull) | (rb[i] >> 32)));
+          const int i2 = (int)((((unsigned)(ra[i] >> 16) & 0xffffu) << 16) | ((unsigned)(rb[i] >> 16) & 0xffffu));
+          if (k2 > bk || (k2 == bk && i2 < bp)) {
+            bk = k2;
+            bp = i2;
+            bcta = b;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double k2 = __shfl_xor_sync(0xffffffffu, bk, off);
+      const int i2 = __shfl_xor_sync(0xffffffffu, bp, off);
+      const int c2 = __shfl_xor_sync(0xffffffffu, bcta, off);
+      if (k2 > bk || (k2 == bk && i2 < bp)) {
+        bk = k2;
+        bp = i2;
+        bcta = c2;
+      }
+    }
+    // bp = absolute pivot row (>= diag), held by CTA bcta: fetch its row from "our" replica.  If the pivot row is one
+    // of OURS (and an interchange is due) the diagonal row it trades places with is fetched in the same round trip --
+    // every other CTA waits for this one in the next step.
+    const llw* prow_g = ws.cand_row + (((size_t)par * ROW_REPLICAS + (blockIdx.x % ROW_REPLICAS)) * G + bcta) * XROW;
+    const llw* trow_g = ws.top_row + (size_t)par * XROW;
+    const bool own_p = bp != diag && bp >= row_base && bp < row_base + nloc;
+    T pa[Q], ps[Q], ta[Q], ts[Q];
+    bool ok[Q], okt[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      ok[q] = lane + 32 * q >= jb;
+      okt[q] = ok[q] || !own_p;
+      pa[q] = ps[q] = ta[q] = ts[q] = (T)0;
+    }
+    bool all;
+    do {
+      all = true;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        if (!ok[q]) {
+          bool v = LL<T>::load(&prow_g[lane + 32 * q], tag, pa[q]);
+          if (EXACT) v &= LL<T>::load(&prow_g[MAX_NB + lane + 32 * q], tag, ps[q]);
+          ok[q] = v;
+          all &= v;
+        }
+        if (!okt[q]) {
+          bool v = LL<T>::load(&trow_g[lane + 32 * q], tag, ta[q]);
+          if (EXACT) v &= LL<T>::load(&trow_g[MAX_NB + lane + 32 * q], tag, ts[q]);
+          okt[q] = v;
+          all &= v;
+        }
+      }
+    } while (!all);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int col = lane + 32 * q;
+      if (col < jb) {
+        s_prow[par][col] = pa[q];
+        s_u[par][col] = EXACT ? sub_rn(pa[q], ps[q]) : pa[q];
+        if (own_p) {
+          s_trow[par][col] = ta[q];
+          if (EXACT) s_trow[par][MAX_NB + col] = ts[q];
+        }
+      }
+    }
+    if (lane == 0) s_p[par] = bp;
+  };
+
+  {
+    int sa, sb;
+    publish_and_exchange(0, sa, sb);
+  }
+
+  for (int c = 0; c < jb; ++c) {
+    const int par = c & 1;
+    const int diag = j0 + c;
+    const int cn = c + 1;  // next column
+    __syncthreads();       // (A) step c's pivot row is in shared memory; the bulk update of step c-1 is complete
+    const int p = s_p[par];
+    const T pv = s_u[par][c];
+    if (blockIdx.x == 0 && threadIdx.x == 0) ws.hdr->ipiv[c] = p;
+
+    // ---- interchange (whole panel row; the rest of the row is swapped by lu_swap/lu_head kernels), by the warp that
+    //      owns the row in the urgent phase below ----
+    if (p != diag && p >= row_base && p < row_base + nloc && (p - row_base) / WB == warp) {
+      const size_t off = (size_t)(p - row_base) * ldr;  // the old diagonal row (fetched by warp 0) moves down here
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
         if (lane + 32 * q < jb) {
-          rows[off + lane + 32 * q] = ta[q];
-          if (EXACT) sums[off + lane + 32 * q] = ts[q];
+          rows[off + lane + 32 * q] = s_trow[par][lane + 32 * q];
+          if (EXACT) sums[off + lane + 32 * q] = s_trow[par][MAX_NB + lane + 32 * q];
         }
     }
-    if ((p != diag || EXACT) && own_diag && ((diag - row_base) % PANEL_WARPS) == warp) {
-      const size_t off = (size_t)(diag - row_base) * jb;  // the diagonal row becomes final: L for cols < c, U for >= c
+    const bool own_diag = diag >= row_base && diag < row_base + nloc;
+    if ((p != diag || EXACT) && own_diag && (diag - row_base) / WB == warp) {
+      const size_t off = (size_t)(diag - row_base) * ldr;  // the diagonal row becomes final: L for cols < c, U for >= c
 #pragma unroll
-      for (int q = 0; q < MAX_NB / 32; ++q) {
+      for (int q = 0; q < Q; ++q) {
         const int col = lane + 32 * q;
-        if (col < jb) rows[off + col] = (col >= c) ? s_u[col] : prow[q];
+        if (col < jb) rows[off + col] = (col >= c) ? s_u[par][col] : s_prow[par][col];
       }
     }
     __syncwarp();
 
-    // ---- multipliers, rank-1 update of the warp's rows below the diagonal, arg-max of column c+1 ----
-    const int cn = c + 1;  // next column
-    int lr0 = warp;
-    if (row_base <= diag) {                   // skip rows at or above the diagonal
-      const int first = diag + 1 - row_base;  // first local row strictly below the diagonal
-      lr0 = first + ((warp - first) % PANEL_WARPS + PANEL_WARPS) % PANEL_WARPS;
-    }
+    // ---- urgent (lanes <-> rows): multipliers of column c, update of column c+1, arg-max of column c+1 ----
     // EXACT keeps the reference's true division (lu.rs:158); the multi-panel path multiplies by the reciprocal of the
     // pivot (<= 1.5 ulp from the quotient, far inside the 1e-12*n element bar): a double division is a ~30 instruction
     // dependent sequence on the column's critical path.
-    const T rcp = EXACT ? (T)0 : (T)1 / pv;
-    double nk = -2.0;
-    int nki = INT_MAX;
-    for (int lrc = lr0; lrc < nloc; lrc += 32 * PANEL_WARPS) {
-      // phase 1, lanes <-> rows: the multipliers l = a[i][c] / pivot of up to 32 rows at once
-      const int mylr = lrc + lane * PANEL_WARPS;
-      T l = (T)0;
-      if (mylr < nloc) {
-        l = value(mylr, c);
-        if (pv != (T)0) l = EXACT ? l / pv : l * rcp;  // skipped for an exactly-zero pivot (lu.rs:156-160)
-      }
-      __syncwarp();
-      if (mylr < nloc) rows[(size_t)mylr * jb + c] = l;  // final L entry
-      // phase 2, lanes <-> columns: stream the rows, multiplier broadcast by shuffle.  u[] is zero outside (c, jb), so
-      // the loop body carries no column predicates (columns <= c are rewritten with their own value).
-      const int cnt = min(32, (nloc - lrc + PANEL_WARPS - 1) / PANEL_WARPS);
-      T* r = rows + (size_t)lrc * jb + lane;
-      T* sa = sums + (size_t)lrc * jb + lane;
-      const size_t rstep = (size_t)PANEL_WARPS * jb;
-#pragma unroll 4
-      for (int i = 0; i < cnt; ++i) {
-        const T li = __shfl_sync(0xffffffffu, l, i);
-#pragma unroll
-        for (int q = 0; q < MAX_NB / 32; ++q) {
-          if (32 * q < jb) {
-            const int col = lane + 32 * q;
-            if (col > c && col < jb) {
-              if (EXACT) {
-                sa[32 * q] = add_rn(sa[32 * q], mul_rn(li, u[q]));  // s = s + l*u, k ascending (lu.rs:125)
-              } else {
-                r[32 * q] = sub_rn(r[32 * q], mul_rn(li, u[q]));
-              }
+    {
+      const T rcp = EXACT ? (T)0 : (T)1 / pv;
+      const T ucn = (cn < jb) ? s_u[par][cn] : (T)0;
+      double nk = -2.0;
+      int nki = INT_MAX;
+      for (int l = lane; l < WB; l += 32) {
+        const int lr = warp * WB + l;
+        if (lr < nloc && row_base + lr > diag) {
+          const size_t off = (size_t)lr * ldr;
+          T lv = value(lr, c);
+          if (pv != (T)0) lv = EXACT ? lv / pv : lv * rcp;  // skipped for an exactly-zero pivot (lu.rs:156-160)
+          rows[off + c] = lv;                                // final L entry
+          if (cn < jb) {
+            T v;
+            if (EXACT) {
+              const T sv = add_rn(sums[off + cn], mul_rn(lv, ucn));
+              sums[off + cn] = sv;
+              v = sub_rn(rows[off + cn], sv);
+            } else {
+              v = sub_rn(rows[off + cn], mul_rn(lv, ucn));
+              rows[off + cn] = v;
             }
+            // strict '>' + lowest row == the reference's first maximum
+            key_merge(nk, nki, pivot_key(v, row_base + lr == diag + 1), row_base + lr);
           }
         }
-        r += rstep;
-        sa += rstep;
       }
-      // phase 3, lanes <-> rows again: arg-max of the next column over these rows (strict '>' + lowest row == the
-      // reference's first maximum)
       if (cn < jb) {
-        __syncwarp();
-        double kk = -2.0;
-        int kr = INT_MAX;
-        if (mylr < nloc) {
-          kk = pivot_key(value(mylr, cn), row_base + mylr == diag + 1);
-          kr = row_base + mylr;
-        }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
-          const double k2 = __shfl_xor_sync(0xffffffffu, kk, off);
-          const int i2 = __shfl_xor_sync(0xffffffffu, kr, off);
-          key_merge(kk, kr, k2, i2);
+          const double k2 = __shfl_xor_sync(0xffffffffu, nk, off);
+          const int i2 = __shfl_xor_sync(0xffffffffu, nki, off);
+          key_merge(nk, nki, k2, i2);
         }
-        key_merge(nk, nki, kk, kr);
+        if (lane == 0) {
+          wkey[warp] = nk;
+          widx[warp] = nki;
+        }
       }
     }
-    if (cn < jb && lane == 0) {
-      wkey[warp] = nk;
-      widx[warp] = nki;
+    if (cn >= jb) break;
+    __syncthreads();  // (B) column c of L, column c+1 and its per-warp arg-max are in shared memory
+
+    int skip_a, skip_b;
+    publish_and_exchange(cn, skip_a, skip_b);
+
+    // ---- bulk (lanes <-> columns), warps 1..7, under the exchange: columns > c+1 of the rows below the diagonal ----
+    if (warp > 0 && cn + 1 < jb) {
+      T u[Q];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const int col = lane + 32 * q;
+        u[q] = (col > cn && col < jb) ? s_u[par][col] : (T)0;
+      }
+      const int first = max(0, diag + 1 - row_base);
+      const int q0 = (cn + 1) >> 5;  // first column group with work left
+      for (int lr = first + warp - 1; lr < nloc; lr += PANEL_WARPS - 1) {
+        if (lr == skip_a || lr == skip_b) continue;
+        const size_t off = (size_t)lr * ldr;
+        const T li = rows[off + c];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const int col = lane + 32 * q;
+          if (q >= q0 && col > cn && col < jb) {
+            if (EXACT) sums[off + col] = add_rn(sums[off + col], mul_rn(li, u[q]));
+            else rows[off + col] = sub_rn(rows[off + col], mul_rn(li, u[q]));
+          }
+        }
+      }
     }
   }
   __syncthreads();
@@ -483,7 +550,7 @@ lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_pe
   // ---- write the factored panel back ----
   for (int idx = threadIdx.x; idx < nloc * jb; idx += PANEL_THREADS) {
     const int lr = idx / jb, c = idx - lr * jb;
-    A[(size_t)(row_base + lr) * ld + j0 + c] = rows[idx];
+    A[(size_t)(row_base + lr) * ld + j0 + c] = rows[(size_t)lr * ldr + c];
   }
 }
 
@@ -713,6 +780,98 @@ lu_swap_trsm_kernel(T* __restrict__ A, size_t ld, int j0, int jb, int col0, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 4b. look-ahead head: row interchanges + U12 = L11^-1 * A12 for the NEXT panel's columns only (<= MAX_NB of them), by
+//     substitution with L11 resident in shared memory.  It sits on the critical chain (panel -> head -> panel), so it
+//     must not wait for inv(L11) (which only the bulk stream needs): one warp owns two columns, keeps them in registers
+//     (lane <-> rows lane, lane+32, ...), broadcasts x_k by shuffle and streams row k of L^T from shared memory --
+//     128 dependent steps of ~40 cycles instead of a 60 us triangular inversion plus a GEMM launch.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int HEAD_COLS = 16;  // columns per CTA (8 warps x 2)
+constexpr int HEAD_LD = MAX_NB + 1;
+template <typename T>
+__global__ void __launch_bounds__(256)
+lu_head_kernel(T* __restrict__ A, size_t ld, int j0, int jb, int col0, int col1, const void* ws_base, int G, int parity) {
+  extern __shared__ __align__(16) unsigned char head_smem[];
+  T(*LT)[HEAD_LD] = reinterpret_cast<T(*)[HEAD_LD]>(head_smem);                  // [MAX_NB]: LT[k][i] = L11[i][k]
+  T(*X)[HEAD_COLS + 1] = reinterpret_cast<T(*)[HEAD_COLS + 1]>(LT + MAX_NB);     // [MAX_NB]: top jb rows of the strip
+  T(*stage)[HEAD_COLS] = reinterpret_cast<T(*)[HEAD_COLS]>(X + MAX_NB);          // [MAX_NB]: rows leaving the top block
+  __shared__ int top_src[MAX_NB];
+  __shared__ int out_dst[MAX_NB];
+  __shared__ int out_src[MAX_NB];
+  __shared__ int n_out;
+  const WsView<T> ws = ws_view<T>(const_cast<void*>(ws_base), G);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tx = tid & (HEAD_COLS - 1), ty = tid / HEAD_COLS;  // 16 columns x 16 rows per pass
+  const int col = col0 + blockIdx.x * HEAD_COLS + tx;
+  const bool ok = col < col1;
+
+  for (int i = tid; i < MAX_NB; i += blockDim.x) top_src[i] = j0 + i;
+  if (tid == 0) n_out = 0;
+  __syncthreads();
+  const MoveList* ml = &ws.hdr->moves[parity];
+  const int nm = ml->n_moves;
+  for (int i = tid; i < nm; i += blockDim.x) {
+    const int d = ml->dst[i], s = ml->src[i];
+    if (d < j0 + jb) {
+      top_src[d - j0] = s;
+    } else {
+      const int slot = atomicAdd(&n_out, 1);
+      out_dst[slot] = d;
+      out_src[slot] = s;
+    }
+  }
+  __syncthreads();
+  const int no = n_out;
+  for (int i = ty; i < MAX_NB; i += 256 / HEAD_COLS)
+    X[i][tx] = (ok && i < jb) ? __ldcg(&A[(size_t)top_src[i] * ld + col]) : (T)0;
+  for (int i = ty; i < no; i += 256 / HEAD_COLS) stage[i][tx] = ok ? __ldcg(&A[(size_t)out_src[i] * ld + col]) : (T)0;
+  // L11 (strictly lower part), transposed so that step k reads one contiguous shared-memory row
+  for (int idx = tid; idx < MAX_NB * MAX_NB; idx += 256) {
+    const int i = idx / MAX_NB, k = idx - i * MAX_NB;
+    LT[k][i] = (i < jb && k < i) ? __ldcg(&A[(size_t)(j0 + i) * ld + j0 + k]) : (T)0;
+  }
+  __syncthreads();
+  for (int i = ty; i < no; i += 256 / HEAD_COLS)
+    if (ok) A[(size_t)out_dst[i] * ld + col] = stage[i][tx];
+
+  // forward substitution (unit diagonal), k ascending
+  constexpr int Q = MAX_NB / 32;
+  T x[Q][2];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    x[q][0] = X[lane + 32 * q][2 * warp];
+    x[q][1] = X[lane + 32 * q][2 * warp + 1];
+  }
+#pragma unroll
+  for (int kq = 0; kq < Q; ++kq) {
+    if (kq * 32 < jb) {
+#pragma unroll 8
+      for (int kl = 0; kl < 32; ++kl) {
+        const int k = kq * 32 + kl;
+        const T xk0 = __shfl_sync(0xffffffffu, x[kq][0], kl);
+        const T xk1 = __shfl_sync(0xffffffffu, x[kq][1], kl);
+#pragma unroll
+        for (int q = kq; q < Q; ++q) {
+          const T l = LT[k][lane + 32 * q];  // zero on and above the diagonal and beyond jb
+          if (q > kq || lane > kl) {         // rows strictly below k (predicated: 0 * inf must not make a NaN)
+            x[q][0] = sub_rn(x[q][0], mul_rn(l, xk0));
+            x[q][1] = sub_rn(x[q][1], mul_rn(l, xk1));
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    X[lane + 32 * q][2 * warp] = x[q][0];
+    X[lane + 32 * q][2 * warp + 1] = x[q][1];
+  }
+  __syncthreads();
+  for (int i = ty; i < jb; i += 256 / HEAD_COLS)
+    if (ok) A[(size_t)(j0 + i) * ld + col] = X[i][tx];
+}
+
 template <typename T>
 __global__ void lu_init_piv_kernel(uint64_t* __restrict__ piv, int m, int* __restrict__ sign) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -728,8 +887,8 @@ __global__ void lu_init_piv_kernel(uint64_t* __restrict__ piv, int m, int* __res
 namespace {
 // Per host thread and device: the chain stream (highest priority) and the events that fence it against the bulk stream.
 struct LuSide {
-  cudaStream_t sp = nullptr;
-  cudaEvent_t e_in = nullptr, e_head = nullptr, e_bulk = nullptr;
+  cudaStream_t sp = nullptr, sw = nullptr;
+  cudaEvent_t e_in = nullptr, e_head = nullptr, e_bulk = nullptr, e_panel = nullptr, e_w = nullptr;
 };
 int lu_side(int device, LuSide** out) {
   static thread_local LuSide side[64];
@@ -739,6 +898,9 @@ int lu_side(int device, LuSide** out) {
     int lo = 0, hi = 0;
     LA_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     LA_CUDA_TRY(cudaStreamCreateWithPriority(&s.sp, cudaStreamNonBlocking, hi));
+    LA_CUDA_TRY(cudaStreamCreateWithPriority(&s.sw, cudaStreamNonBlocking, hi));
+    LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e_panel, cudaEventDisableTiming));
+    LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e_w, cudaEventDisableTiming));
     LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e_in, cudaEventDisableTiming));
     LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e_head, cudaEventDisableTiming));
     LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e_bulk, cudaEventDisableTiming));
@@ -767,13 +929,13 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
   // panel width: as wide as shared memory allows for the tallest (first) panel, multiple of 16, <= MAX_NB
   int rpc_first = (M + sms - 1) / sms;
   if (rpc_first < 8) rpc_first = 8;
-  int nb = (int)(PANEL_SMEM_BUDGET / ((size_t)rpc_first * sizeof(T)));
-  nb = nb / 16 * 16;
+  int nb = (int)(PANEL_SMEM_BUDGET / ((size_t)rpc_first * sizeof(T))) - 1;  // rows are padded to an odd stride
+  nb = nb < 0 ? 0 : nb / 16 * 16;
   if (nb > MAX_NB) nb = MAX_NB;
   if (nb < 16)
     return fail(LA_ERR_UNSUPPORTED, "la_lu_factor: %d rows exceed the shared-memory panel capacity of %d SMs", M, sms);
   // single-panel factorisations run the bit-exact (deferred subtraction) panel when twice the panel fits
-  const bool exact = kmin <= nb && (size_t)2 * rpc_first * kmin * sizeof(T) <= PANEL_SMEM_BUDGET;
+  const bool exact = kmin <= nb && (size_t)2 * rpc_first * (kmin | 1) * sizeof(T) <= PANEL_SMEM_BUDGET;
   // multi-panel fp64 on TMA-addressable storage: look-ahead pipeline with U12 = inv(L11) * A12 on the DMMA GEMM
   static const int dbg = getenv("LA_LU_DEBUG") ? atoi(getenv("LA_LU_DEBUG")) : 0;  // 1: one stream, 2: plain loop
   const bool fast = std::is_same<T, double>::value && kmin > nb && (N % 2 == 0) && ((uintptr_t)LU % 16 == 0) &&
@@ -806,10 +968,18 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
   // panel factorisation of columns [j0, j0+jb) on stream s (ipiv lands in the workspace header)
   auto launch_panel = [&](int j0, int jb, cudaStream_t s) -> int {
     const int R = M - j0;
+    // Rows per CTA.  Fewer, fuller CTAs leave more SMs wholly to the bulk GEMMs (a panel CTA takes half the register
+    // file, so a GEMM runs at half occupancy next to it) and the in-panel look-ahead hides their longer update; near
+    // the end the bulk is negligible and many small CTAs give the shortest column time.
+    static const int rpc_min = getenv("LA_LU_RPC_MIN") ? atoi(getenv("LA_LU_RPC_MIN")) : 120;  // tuning knobs
+    static const int rpc_div = getenv("LA_LU_RPC_DIV") ? atoi(getenv("LA_LU_RPC_DIV")) : 64;
     int rpc = (R + sms - 1) / sms;
-    if (rpc < 8) rpc = 8;  // at least one row per warp; fewer, fuller CTAs make the barrier cheaper
+    int want = R / rpc_div;
+    if (want > rpc_min) want = rpc_min;
+    if (want < 8) want = 8;  // at least one row per warp
+    if (rpc < want) rpc = want;
     const int G = (R + rpc - 1) / rpc;
-    const size_t smem = (size_t)rpc * jb * sizeof(T) * (exact ? 2 : 1);
+    const size_t smem = (size_t)rpc * (jb | 1) * sizeof(T) * (exact ? 2 : 1);
     T* a = LU;
     size_t ld = n;
     int mm = M, jj0 = j0, jjb = jb, rr = rpc;
@@ -827,10 +997,12 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
     LA_CUDA_TRY(cudaGetLastError());
     return LA_OK;
   };
-  auto launch_swap = [&](int col0, int col1, int parity, cudaStream_t s) -> int {
-    if (col1 <= col0) return LA_OK;
-    lu_swap_kernel<T><<<(col1 - col0 + SWAP_W - 1) / SWAP_W, 256, SWAP_SMEM, s>>>(LU, n, col0, col1, col1, col1, ws_base,
-                                                                                G_cur, parity);
+  // row interchanges of columns [col0, col1) minus [skip0, skip1)
+  auto launch_swap = [&](int col0, int col1, int skip0, int skip1, int parity, cudaStream_t s) -> int {
+    const int ncols = (col1 - col0) - (skip1 - skip0);
+    if (ncols <= 0) return LA_OK;
+    lu_swap_kernel<T><<<(ncols + SWAP_W - 1) / SWAP_W, 256, SWAP_SMEM, s>>>(LU, n, col0, col1, skip0, skip1, ws_base, G_cur,
+                                                                          parity);
     LA_CUDA_TRY(cudaGetLastError());
     return LA_OK;
   };
@@ -841,7 +1013,7 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
       const int jb = (kmin - j0 < nb) ? (kmin - j0) : nb;
       LA_TRY(launch_panel(j0, jb, st));
       LA_TRY(launch_perm(j0, jb, 0, st));
-      LA_TRY(launch_swap(0, j0, 0, st));
+      LA_TRY(launch_swap(0, j0, j0, j0, 0, st));
       const int c1 = j0 + jb;
       if (c1 < N) {
         lu_swap_trsm_kernel<T><<<(N - c1 + TRSM_W - 1) / TRSM_W, 256, TRSM_SMEM, st>>>(LU, n, j0, jb, c1, N, ws_base,
@@ -856,20 +1028,37 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
   }
 
   // ---- look-ahead pipeline (fp64) -------------------------------------------------------------------------------
-  // chain stream sp (highest priority), per panel i:  perm(i) -> [wait bulk(i-1)] -> row interchanges of the NEXT
-  //   panel's columns -> W = inv(L11) -> U12/trailing update of the next panel's columns -> panel(i+1)
-  // bulk stream st (the caller's), per panel i:       [wait W(i)] -> row interchanges of all other columns ->
+  // chain stream sp (highest priority), per panel i:  perm(i) -> [wait bulk(i-1)] -> head: row interchanges + U12 by
+  //   substitution for the NEXT panel's columns -> their trailing update (DMMA) -> panel(i+1)
+  // side stream sw, per panel i:                      W(i) = inv(L11(i))  (only the bulk needs it)
+  // bulk stream st (the caller's), per panel i:       [wait perm(i), W(i)] -> row interchanges of all other columns ->
   //   U12 = W * A12 and A22 -= L21 * U12 for the columns right of the next panel
-  // The critical path is the chain; the bulk GEMMs fill the SMs underneath it (the cooperative panel CTAs are
-  // latency-bound and co-reside with the DMMA CTAs).  W and the move lists are double-buffered by panel parity.
+  // Early on the bulk GEMMs are the critical path and run back to back (nothing they wait for depends on bulk(i-1));
+  // late the chain is, and it carries nothing the bulk could do.  The cooperative panel CTAs are latency-bound and
+  // co-reside with the DMMA CTAs.  W and the move lists are double-buffered by panel parity.
   if constexpr (std::is_same<T, double>::value) {
     LuSide* side;
     LA_TRY(lu_side(ctx->device, &side));
     cudaStream_t sp = dbg == 1 ? st : side->sp;
+    cudaStream_t sw = dbg == 1 ? st : side->sw;
     double* A = LU;
     const size_t ld = n;
+    const int HEAD_SMEM = (int)(sizeof(T) * ((size_t)MAX_NB * HEAD_LD + (size_t)MAX_NB * (HEAD_COLS + 1) +
+                                             (size_t)MAX_NB * HEAD_COLS));
+    LA_CUDA_TRY(cudaFuncSetAttribute(lu_head_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM));
+    // LA_LU_TRACE=<file>: per-panel timeline from timing events (diagnostic; perturbs the run by the event records)
+    static const char* trace_path = getenv("LA_LU_TRACE");
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t s) {
+      if (!trace_path) return;
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, s);
+      tev.push_back(e);
+    };
     LA_CUDA_TRY(cudaEventRecord(side->e_in, st));
     LA_CUDA_TRY(cudaStreamWaitEvent(sp, side->e_in, 0));
+    mark(sp);  // t0
     LA_TRY(launch_panel(0, nb, sp));
     int it = 0;
     for (int j0 = 0; j0 < kmin; j0 += nb, ++it) {
@@ -881,35 +1070,70 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
       const int c2 = c1 + nb2;
       double* W = Wbuf[parity];
       const double* L21 = A + (size_t)c1 * ld + j0;
-      auto trsm_update = [&](int cb, int ce, cudaStream_t s) -> int {  // columns [cb, ce)
-        if (ce <= cb) return LA_OK;
-        double* U12 = A + (size_t)j0 * ld + cb;
-        LA_TRY(gemm_f64_tensor(W, MAX_NB, U12, ld, U12, ld, (size_t)jb, (size_t)jb, (size_t)(ce - cb), LA_GEMM_ASSIGN,
-                               s));  // in place: one tile row, every CTA reads its whole column block first
-        if (c1 < M)
-          LA_TRY(gemm_f64_tensor(L21, ld, U12, ld, A + (size_t)c1 * ld + cb, ld, (size_t)(M - c1), (size_t)jb,
-                                 (size_t)(ce - cb), LA_GEMM_SUB, s));
-        return LA_OK;
+      auto trailing = [&](int cb, int ce, cudaStream_t s) -> int {  // A22 -= L21 * U12 for columns [cb, ce)
+        if (ce <= cb || c1 >= M) return LA_OK;
+        return gemm_f64_tensor(L21, ld, A + (size_t)j0 * ld + cb, ld, A + (size_t)c1 * ld + cb, ld, (size_t)(M - c1),
+                               (size_t)jb, (size_t)(ce - cb), LA_GEMM_SUB, s);
       };
+      // ---- side: W = inv(L11) as soon as the panel is done ----
+      mark(sp);  // [0] panel(i) done
+      const bool need_w = c2 < N;
+      if (need_w) {
+        LA_CUDA_TRY(cudaEventRecord(side->e_panel, sp));
+        LA_CUDA_TRY(cudaStreamWaitEvent(sw, side->e_panel, 0));
+        lu_invl_kernel<T><<<1, INVL_THREADS, INVL_SMEM, sw>>>(LU, n, j0, jb, W);
+        LA_CUDA_TRY(cudaGetLastError());
+        LA_CUDA_TRY(cudaEventRecord(side->e_w, sw));
+      }
       // ---- chain ----
       LA_TRY(launch_perm(j0, jb, parity, sp));
-      if (c1 < N) {
-        if (it > 0) LA_CUDA_TRY(cudaStreamWaitEvent(sp, side->e_bulk, 0));  // bulk(i-1) updated every column >= c1
-        LA_TRY(launch_swap(c1, c2, parity, sp));
-        lu_invl_kernel<T><<<1, INVL_THREADS, INVL_SMEM, sp>>>(LU, n, j0, jb, W);
-        LA_CUDA_TRY(cudaGetLastError());
-      }
       LA_CUDA_TRY(cudaEventRecord(side->e_head, sp));
+      if (has_next && it > 0) LA_CUDA_TRY(cudaStreamWaitEvent(sp, side->e_bulk, 0));  // bulk(i-1) updated columns >= c1
+      mark(sp);  // [1] perm done and bulk(i-1) done
       if (has_next) {
-        LA_TRY(trsm_update(c1, c2, sp));
+        lu_head_kernel<T><<<(nb2 + HEAD_COLS - 1) / HEAD_COLS, 256, HEAD_SMEM, sp>>>(LU, n, j0, jb, c1, c2, ws_base, G_cur,
+                                                                                    parity);
+        LA_CUDA_TRY(cudaGetLastError());
+        mark(sp);  // [2] next panel's columns interchanged, U12 solved
+        LA_TRY(trailing(c1, c2, sp));
+        mark(sp);  // [3] next panel's columns updated
         LA_TRY(launch_panel(c1, nb2, sp));
+      } else {
+        mark(sp);
+        mark(sp);
       }
       // ---- bulk ----
       LA_CUDA_TRY(cudaStreamWaitEvent(st, side->e_head, 0));
-      LA_TRY(launch_swap(0, j0, parity, st));
-      LA_TRY(launch_swap(c2, N, parity, st));
-      LA_TRY(trsm_update(c2, N, st));
+      if (need_w) LA_CUDA_TRY(cudaStreamWaitEvent(st, side->e_w, 0));
+      mark(st);  // [4] bulk(i) start
+      LA_TRY(launch_swap(0, N, j0, c2, parity, st));  // everything but this panel's and the next panel's columns
+      mark(st);  // [5] bulk swaps done
+      if (need_w) {
+        double* U12 = A + (size_t)j0 * ld + c2;
+        LA_TRY(gemm_f64_tensor(W, MAX_NB, U12, ld, U12, ld, (size_t)jb, (size_t)jb, (size_t)(N - c2), LA_GEMM_ASSIGN,
+                               st));  // in place: one tile row, every CTA reads its whole column block first
+        LA_TRY(trailing(c2, N, st));
+      }
       LA_CUDA_TRY(cudaEventRecord(side->e_bulk, st));
+      mark(st);  // [6] bulk(i) done
+    }
+    if (trace_path) {
+      LA_CUDA_TRY(cudaStreamSynchronize(sp));
+      LA_CUDA_TRY(cudaStreamSynchronize(st));
+      if (FILE* f = fopen(trace_path, "w")) {
+        fprintf(f, "panel,panel_done,perm_and_bulk_prev,head_solved,head_updated,bulk_start,bulk_swapped,bulk_done\n");
+        for (size_t p = 0; p * 7 + 7 < tev.size(); ++p) {
+          fprintf(f, "%zu", p);
+          for (int q = 0; q < 7; ++q) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, tev[0], tev[1 + p * 7 + q]);
+            fprintf(f, ",%.4f", ms);
+          }
+          fprintf(f, "\n");
+        }
+        fclose(f);
+      }
+      for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
     // the caller's stream must also cover the tail of the chain stream
     LA_CUDA_TRY(cudaEventRecord(side->e_head, sp));
