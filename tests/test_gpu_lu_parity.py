@@ -127,16 +127,41 @@ def test_solve_parity(oracle, n, nx):
     assert np.max(np.abs(x - ref_x)) / np.max(np.abs(ref_x)) <= 1e-12 * n * max(1.0, cond / n)
 
 
-def test_solve_given_reference_factors_matches_oracle(oracle):
-    """Feed the ORACLE's packed LU to the CUDA solve: isolates the triangular sweeps (lu.rs:257-275)."""
-    n, nx = 300, 16
+@pytest.mark.parametrize("n,nx", [(64, 3), (300, 16), (511, 16), (510, 16)])
+def test_solve_given_reference_factors_matches_oracle(oracle, n, nx):
+    """Feed the ORACLE's packed LU to the CUDA solve: isolates the triangular sweeps (lu.rs:257-275).  Below 512 rows
+    the launch-per-block path runs: same order, separately rounded ops -> bit-exact."""
     a = oracle.fill((n, n), 1)
     b = oracle.fill((n, nx), 3)
     ref_lu, ref_piv, _ = oracle.lu(a)
     ref_x = oracle.lu_solve(ref_lu, ref_piv, b)
     x = np.empty((n, nx))
     check(lib().la_lu_solve_f64_host(ref_lu.ctypes.data, n, n, ref_piv.ctypes.data, b.ctypes.data, nx, x.ctypes.data))
-    assert np.array_equal(x.view(np.uint64), ref_x.view(np.uint64))  # same order, separately rounded ops: bit-exact
+    assert np.array_equal(x.view(np.uint64), ref_x.view(np.uint64))
+
+
+@pytest.mark.parametrize("n,nx", [(512, 16), (640, 7), (1154, 16), (2048, 1), (2306, 9), (4096, 16)])
+def test_solve_sweep_given_reference_factors(oracle, n, nx):
+    """n >= 512, even, nx <= 16: the persistent sweep kernels (ragged last block included).  Same elimination order
+    with fused multiply-adds and a reciprocal diagonal: the solution must satisfy the SAME triangular systems as the
+    oracle's to rounding -- component-wise backward error of L*U*x = b(piv) within 4x the oracle's own, and the
+    difference to the oracle's x within the 1e-12*n bar scaled by the conditioning."""
+    a = oracle.fill((n, n), 1)
+    b = oracle.fill((n, nx), 3)
+    ref_lu, ref_piv, _ = oracle.lu(a)
+    ref_x = oracle.lu_solve(ref_lu, ref_piv, b)
+    x = np.empty((n, nx))
+    check(lib().la_lu_solve_f64_host(ref_lu.ctypes.data, n, n, ref_piv.ctypes.data, b.ctypes.data, nx, x.ctypes.data))
+    l = np.tril(ref_lu, -1) + np.eye(n)
+    u = np.triu(ref_lu)
+    bp = b[ref_piv.astype(np.int64)]
+
+    def backward_error(sol):
+        return np.max(np.abs(l @ (u @ sol) - bp) / (np.abs(l) @ (np.abs(u) @ np.abs(sol)) + np.abs(bp)))
+
+    assert backward_error(x) <= 4 * max(backward_error(ref_x), np.finfo(np.float64).eps)
+    cond = np.linalg.cond(a)
+    assert np.max(np.abs(x - ref_x)) / np.max(np.abs(ref_x)) <= 1e-12 * n * max(1.0, cond / n)
 
 
 def test_det_parity_and_overflow_order(oracle):
