@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "rust-la_b200", "python"))
 
 METRIC = "f64 GEMM TFLOP/s @n=8192 & LU TFLOP/s @n=16384, % of B200 FP64 peak"
+NOMINAL_TF32_TFLOPS = 1125.0  # half the nominal dense bf16 rate (2250); used only when nothing was measured
 NOMINAL_FP64_TFLOPS = 40.0  # NVIDIA DGX B200 listing, vector == tensor; used only when nothing was measured
 
 
@@ -167,6 +168,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-lu", action="store_true", help="N=1 only: do not time the LU n=16384 leg")
+    ap.add_argument("--skip-f32", action="store_true", help="N=1 only: do not time the f32 65536x1024x16384 leg")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--n", type=int, default=0, help="override the GEMM size (debug)")
     args = ap.parse_args()
@@ -349,6 +351,47 @@ def main():
               "solve_ms": so_t, "solve_gbs": (8.0 * ln * ln * 2) / (so_t * 1e-3) / 1e9,
               "solve_residual": res}
 
+    # ---- f32 GEMM 65536x1024 x 1024x16384 (configs[4]) on the tcgen05 kind::tf32 kernel, 1 GPU only ----
+    f32 = None
+    if n_gpus == 1 and not args.skip_f32:
+        A0 = LU = R = A = B = C = None  # release the f64 buffers
+        torch.cuda.empty_cache()
+        fm, fk, fn = 65536, 1024, 16384
+        f32t = torch.float32
+        FA = torch.empty((fm, fk), dtype=f32t, device=dev)
+        FB = torch.empty((fk, fn), dtype=f32t, device=dev)
+        FC = torch.empty((fm, fn), dtype=f32t, device=dev)
+        chk(L.la_fill_hash_f32_dev(FA.data_ptr(), FA.numel(), 1, 0, sp))
+        chk(L.la_fill_hash_f32_dev(FB.data_ptr(), FB.numel(), 2, 0, sp))
+        for _ in range(3):
+            chk(L.la_gemm_f32_dev(FA.data_ptr(), fk, FB.data_ptr(), fn, FC.data_ptr(), fn, fm, fk, fn, 0, sp))
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        freps = 10
+        f0.record(stream)
+        for _ in range(freps):
+            chk(L.la_gemm_f32_dev(FA.data_ptr(), fk, FB.data_ptr(), fn, FC.data_ptr(), fn, fm, fk, fn, 0, sp))
+        f1.record(stream)
+        torch.cuda.synchronize()
+        f_ms = f0.elapsed_time(f1) / freps
+        rows = torch.arange(0, fm, fm // 64, device=dev)
+        want = FA[rows].double() @ FB.double()
+        rel = float(((FC[rows].double() - want).abs() / want.abs().clamp_min(1e-300)).max())
+        tf32_peak, tf32_src = NOMINAL_TF32_TFLOPS, "nominal dense TF32 (half the nominal bf16 rate)"
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            tf32_peak = float(mp["bf16_tflops"]) / 2.0
+            tf32_src = "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 issues at half the bf16 rate; no TF32 entry in the file)"
+        except Exception:
+            pass
+        f_tf = 2.0 * fm * fk * fn / (f_ms * 1e-3) / 1e12
+        f32 = {"workload": "f32 GEMM 65536x1024 x 1024x16384", "ms": f_ms, "tflops": f_tf,
+               "kernel": "gemm_f32_tf32_kernel (tcgen05.mma kind::tf32, TMEM accumulators, TMA in/out) + B transpose",
+               "max_rel_err_vs_f64_on_64_rows": rel, "tolerance": 1e-4 * fk,
+               "roofline": {"bound": "tensor", "achieved": f_tf, "peak": tf32_peak, "unit": "TFLOP/s",
+                            "frac": f_tf / tf32_peak, "peak_source": tf32_src}}
+        del FA, FB, FC
+
     if rank != 0:
         if n_gpus > 1:
             dist.destroy_process_group()
@@ -403,6 +446,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "lu": lu,
+        "f32": f32,
     }
     print(json.dumps(line))
     if n_gpus > 1:

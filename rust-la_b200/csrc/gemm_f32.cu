@@ -15,7 +15,9 @@
 // toolchain/driver for every LBO/SBO choice (measured, round 1), so B is transposed once per call into a scratch buffer
 // (B^T, K-major) by a bandwidth-bound tile kernel (<= 6 % of the GEMM time at 8192^3, 1 % at the 65536x1024x16384 config).
 // One MMA = M128 N256 K8; four per stage.  Warp roles (192 threads): warp 0 lane 0 = TMA producer, warp 1 = TMEM
-// allocator + MMA issuer (one elected lane), warps 2-5 = epilogue (TMEM lane quarter = warp % 4).
+// allocator + MMA issuer (one elected lane), warps 2-5 = epilogue (TMEM lane quarter = warp % 4).  The kernel is
+// persistent (one CTA per SM) with two accumulators in TMEM, and C leaves through swizzled shared memory and TMA
+// stores (full 32-byte sectors; the first version's per-lane 16-byte stores made L2 read-fill every sector of C).
 #include <stdlib.h>
 
 #include "la_common.cuh"
@@ -29,8 +31,10 @@ constexpr int TA_BYTES = TBM * TBK * 4;        // 16 KiB
 constexpr int TB_BYTES = TBK * TBN * 4;        // 32 KiB
 constexpr int TSTAGE_BYTES = TA_BYTES + TB_BYTES;
 constexpr int TF32_THREADS = 192;
-constexpr int TF32_SMEM = TSTAGES * TSTAGE_BYTES + 256 + 1024;  // stages + barriers/tmem slot + alignment slack
-constexpr int TMEM_COLS = 256;
+constexpr int TOUT_BOX_BYTES = 32 * 32 * 4;              // one 32 x 32 fp32 store box
+constexpr int TOUT_BYTES = 4 * 2 * TOUT_BOX_BYTES;      // 4 epilogue warps, double-buffered
+constexpr int TF32_SMEM = TSTAGES * TSTAGE_BYTES + TOUT_BYTES + 256 + 1024;  // + barriers/tmem slot + alignment slack
+constexpr int TMEM_COLS = 512;                           // two 128 x 256 fp32 accumulators
 constexpr size_t TF32_MIN_K = 32;  // below this TF32's 2^-10 input rounding is not covered by the 1e-4*k parity bar
 
 // 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading/stride byte offsets (all
@@ -80,35 +84,65 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// TMA store / reduce-add of a shared-memory box into a global tensor (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c_inner, int c_outer) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c_inner, int c_outer) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Tile order: bands of GROUP_M tile rows, m fastest inside a band.  The CTAs of one wave then share a handful of B^T
+// tiles and a band of A that both stay in L2 while the band sweeps all tile columns.
+constexpr int GROUP_M = 16;
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tile_m, int& tile_n) {
+  const int per_group = GROUP_M * tiles_n;
+  const int first_m = (t / per_group) * GROUP_M;
+  const int rows_here = min(GROUP_M, tiles_m - first_m);
+  tile_m = first_m + (t % per_group) % rows_here;
+  tile_n = (t % per_group) / rows_here;
+}
+
+// PERSISTENT kernel: one CTA per SM walks the tile list.  The 512 TMEM columns hold TWO 128 x 256 fp32 accumulators, so the
+// epilogue of tile i (TMEM -> registers -> swizzled shared memory -> TMA store / reduce-add) runs under the MMAs of tile
+// i+1; the shared-memory ring keeps streaming across tile boundaries.
 template <int MODE>
 __global__ void __launch_bounds__(TF32_THREADS, 1)
 gemm_f32_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     float* __restrict__ C, size_t ldc, int M, int N, int K, int tiles_m, int tiles_n) {
+                     const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int tiles_m, int tiles_n) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TSTAGES * TSTAGE_BYTES);
+  uint8_t* out_stage = smem + TSTAGES * TSTAGE_BYTES;                     // [4 warps][2][32 rows x 128 B], 1024-aligned
+  uint64_t* full = reinterpret_cast<uint64_t*>(out_stage + TOUT_BYTES);
   uint64_t* empty = full + TSTAGES;
-  uint64_t* accum_full = empty + TSTAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  uint64_t* acc_full = empty + TSTAGES;   // [2]: MMAs of a tile done
+  uint64_t* acc_empty = acc_full + 2;     // [2]: epilogue has drained the accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // rasterise m fastest inside groups of 8 tile rows: the group shares each B tile column while it is hot in L2
-  constexpr int GROUP = 8;
-  const int tile = blockIdx.x;
-  const int per_group = GROUP * tiles_n;
-  const int first_m = (tile / per_group) * GROUP;
-  const int rows_here = min(GROUP, tiles_m - first_m);
-  const int tile_m = first_m + (tile % per_group) % rows_here;
-  const int tile_n = (tile % per_group) / rows_here;
-  const int m0 = tile_m * TBM, n0 = tile_n * TBN;
   const int ktiles = (K + TBK - 1) / TBK;
+  const int ntiles = tiles_m * tiles_n;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TSTAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(accum_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);  // one arrival per epilogue warp
+    }
     mbar_fence_init();
   }
   if (warp == 1) {  // TMEM allocation is warp-wide; the base address lands in shared memory
@@ -126,73 +160,92 @@ gemm_f32_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (lane == 0) {
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
-      for (int kt = 0; kt < ktiles; ++kt) {
-        const int s = kt % TSTAGES;
-        mbar_wait(&empty[s], ((kt / TSTAGES) & 1) ^ 1);
-        uint8_t* sA = smem + s * TSTAGE_BYTES;
-        uint8_t* sB = sA + TA_BYTES;
-        mbar_arrive_expect_tx(&full[s], TSTAGE_BYTES);
-        tma_load_2d(sA, &tmA, &full[s], kt * TBK, m0);  // 32 k (inner, 128 B) x 128 rows
-        tma_load_2d(sB, &tmB, &full[s], kt * TBK, n0);  // B^T: 32 k (inner, 128 B) x 256 n-rows
+      uint32_t g = 0;  // k-tiles issued so far (ring position)
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int tile_m, tile_n;
+        tile_coords(t, tiles_m, tiles_n, tile_m, tile_n);
+        for (int kt = 0; kt < ktiles; ++kt, ++g) {
+          const int s = g % TSTAGES;
+          mbar_wait(&empty[s], ((g / TSTAGES) & 1) ^ 1);
+          uint8_t* sA = smem + s * TSTAGE_BYTES;
+          uint8_t* sB = sA + TA_BYTES;
+          mbar_arrive_expect_tx(&full[s], TSTAGE_BYTES);
+          tma_load_2d(sA, &tmA, &full[s], kt * TBK, tile_m * TBM);  // 32 k (inner, 128 B) x 128 rows
+          tma_load_2d(sB, &tmB, &full[s], kt * TBK, tile_n * TBN);  // B^T: 32 k (inner, 128 B) x 256 n-rows
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: a single thread drives the tensor core =====
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(TBM, TBN, /*A K-major*/ 0, /*B^T K-major*/ 0);
-      for (int kt = 0; kt < ktiles; ++kt) {
-        const int s = kt % TSTAGES;
-        mbar_wait(&full[s], (kt / TSTAGES) & 1);
+      uint32_t g = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int b = it & 1;
+        mbar_wait(&acc_empty[b], ((it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator (free at first use)
         tcgen05_fence_after();
-        const uint32_t sA = smem_u32(smem + s * TSTAGE_BYTES);
-        const uint32_t sB = sA + TA_BYTES;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(b * TBN);
+        for (int kt = 0; kt < ktiles; ++kt, ++g) {
+          const int s = g % TSTAGES;
+          mbar_wait(&full[s], (g / TSTAGES) & 1);
+          tcgen05_fence_after();
+          const uint32_t sA = smem_u32(smem + s * TSTAGE_BYTES);
+          const uint32_t sB = sA + TA_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < TBK / 8; ++kk) {
-          // A, K-major: 8 k = 32 bytes further along the 128-byte swizzled row; 8-row groups are 1024 B apart (SBO)
-          const uint64_t adesc = umma_smem_desc(sA + kk * 32, 16, 1024);
-          const uint64_t bdesc = umma_smem_desc(sB + kk * 32, 16, 1024);  // B^T: same K-major layout as A
-          umma_tf32(tmem_base, adesc, bdesc, idesc, (kt | kk) ? 1u : 0u);
+          for (int kk = 0; kk < TBK / 8; ++kk) {
+            // K-major operands: 8 k = 32 bytes further along the 128-byte swizzled row; 8-row groups are 1024 B apart (SBO)
+            const uint64_t adesc = umma_smem_desc(sA + kk * 32, 16, 1024);
+            const uint64_t bdesc = umma_smem_desc(sB + kk * 32, 16, 1024);
+            umma_tf32(tmem_d, adesc, bdesc, idesc, (kt | kk) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
         }
-        umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
+        umma_commit(&acc_full[b]);  // accumulator complete
       }
-      umma_commit(accum_full);   // accumulator complete
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> global.  Warp w reads TMEM lanes [32*(w%4), +32): lane == tile row =====
+    // ===== epilogue: warp w owns TMEM lanes [32*(w%4), +32) == 32 tile rows =====
     const int quarter = warp & 3;
-    mbar_wait(accum_full, 0);
-    tcgen05_fence_after();
-    const int row = m0 + quarter * 32 + lane;
+    uint8_t* my_stage = out_stage + (warp - 2) * (2 * TOUT_BOX_BYTES);
+    int it = 0;
+    uint32_t nbox = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      int tile_m, tile_n;
+      tile_coords(t, tiles_m, tiles_n, tile_m, tile_n);
+      const int b = it & 1;
+      const int row0 = tile_m * TBM + quarter * 32;
+      mbar_wait(&acc_full[b], (it >> 1) & 1);
+      tcgen05_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < TBN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
-      const int col = n0 + c0;
-      if (row < M && col < N) {
-        float* p = C + (size_t)row * ldc + col;
-        if (col + 32 <= N) {
+      for (int c0 = 0; c0 < TBN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * TBN + c0), r);
+        const int col0 = tile_n * TBN + c0;
+        if (row0 < M && col0 < N) {  // warp-uniform
+          uint8_t* box = my_stage + (nbox & 1) * TOUT_BOX_BYTES;
+          ++nbox;
+          if (lane == 0) bulk_wait_read<1>();  // the store issued from this buffer two boxes ago has read it
+          __syncwarp();
+          // row `lane` of the box, 128 bytes, 16-byte chunks XOR-swizzled by the row (SWIZZLE_128B): conflict-free
 #pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            float4 o = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
-                                   __uint_as_float(r[4 * v + 3]));
-            if (MODE == LA_GEMM_ADD) {
-              const float4 old = __ldcg(reinterpret_cast<const float4*>(p) + v);
-              o.x += old.x;
-              o.y += old.y;
-              o.z += old.z;
-              o.w += old.w;
-            }
-            reinterpret_cast<float4*>(p)[v] = o;
-          }
-        } else {
-          for (int v = 0; v < 32 && col + v < N; ++v) {
-            float o = __uint_as_float(r[v]);
-            if (MODE == LA_GEMM_ADD) o += p[v];
-            p[v] = o;
+          for (int v = 0; v < 8; ++v)
+            *reinterpret_cast<uint4*>(box + lane * 128 + ((v ^ (lane & 7)) << 4)) =
+                make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (MODE == LA_GEMM_ADD) tma_reduce_add_2d(&tmC, box, col0, row0);
+            else tma_store_2d(&tmC, box, col0, row0);  // rows / columns outside C are clipped by the TMA unit
+            bulk_commit();
           }
         }
       }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);
     }
+    if (lane == 0) bulk_wait_all();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -224,11 +277,13 @@ __global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restr
 int g_f32_path = getenv("LA_GEMM_F32_PATH") ? atoi(getenv("LA_GEMM_F32_PATH")) : 0;  // 0 auto, 1 CUDA-core, 2 tcgen05
 
 template <int MODE>
-int launch_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, size_t ldc, int M, int N, int K,
+int launch_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K, int sms,
                 cudaStream_t st) {
   LA_CUDA_TRY(cudaFuncSetAttribute(gemm_f32_tf32_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF32_SMEM));
   const int tiles_m = (M + TBM - 1) / TBM, tiles_n = (N + TBN - 1) / TBN;
-  gemm_f32_tf32_kernel<MODE><<<tiles_m * tiles_n, TF32_THREADS, TF32_SMEM, st>>>(tmA, tmB, C, ldc, M, N, K, tiles_m, tiles_n);
+  const int ntiles = tiles_m * tiles_n;
+  gemm_f32_tf32_kernel<MODE><<<ntiles < sms ? ntiles : sms, TF32_THREADS, TF32_SMEM, st>>>(tmA, tmB, tmC, M, N, K, tiles_m,
+                                                                                         tiles_n);
   LA_CUDA_TRY(cudaGetLastError());
   return LA_OK;
 }
@@ -274,8 +329,10 @@ int gemm_f32_dev(const float* A, size_t lda, const float* B, size_t ldb, float* 
                               CU_TENSOR_MAP_SWIZZLE_128B));
   LA_TRY(encode_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, bt, k, n, ldt * 4, TBK, TBN,
                               CU_TENSOR_MAP_SWIZZLE_128B));
-  if (mode == LA_GEMM_ASSIGN) return launch_tf32<LA_GEMM_ASSIGN>(tmA, tmB, C, ldc, (int)m, (int)n, (int)k, st);
-  return launch_tf32<LA_GEMM_ADD>(tmA, tmB, C, ldc, (int)m, (int)n, (int)k, st);
+  CUtensorMap tmC;  // store boxes: 32 columns (128 B) x 32 rows, same swizzle as the epilogue's shared-memory layout
+  LA_TRY(encode_tensor_map_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, n, m, ldc * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+  if (mode == LA_GEMM_ASSIGN) return launch_tf32<LA_GEMM_ASSIGN>(tmA, tmB, tmC, (int)m, (int)n, (int)k, ctx->sm_count, st);
+  return launch_tf32<LA_GEMM_ADD>(tmA, tmB, tmC, (int)m, (int)n, (int)k, ctx->sm_count, st);
 }
 
 template <>

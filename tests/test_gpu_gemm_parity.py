@@ -47,7 +47,7 @@ def test_gemm_f32_host_api(oracle, shape):
 
 
 @pytest.mark.parametrize("shape", [(128, 32, 256), (512, 1024, 256), (1000, 520, 768), (640, 100, 328), (130, 64, 260),
-                                   (2048, 1024, 2048), (256, 36, 512)])
+                                   (2048, 1024, 2048), (256, 36, 512), (4096, 64, 4096), (3000, 40, 5000)])
 @pytest.mark.parametrize("mode", [0, 2])
 def test_gemm_f32_tcgen05_tf32(oracle, shape, mode):
     """The tcgen05 kind::tf32 kernel (TMEM accumulators, TMA-fed), forced, vs the fp32 oracle: <= 1e-4 * k relative."""
@@ -67,6 +67,31 @@ def test_gemm_f32_tcgen05_tf32(oracle, shape, mode):
     got = dc.to_array((m, n), np.float32)
     assert np.all(np.isfinite(got))
     assert max_rel_err(got, want) <= F32_TOL * k
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_gemm_f32_tcgen05_submatrix_views(oracle, mode):
+    """ld > width on all three operands: the TMA stores of the epilogue must clip at the view's edge (m, n ragged
+    against the 128 x 256 tile and the 32 x 32 store box) and leave the rest of the parent matrix untouched."""
+    ld = 1200
+    m, k, n = 300, 96, 1000
+    big_a = oracle.fill((400, ld), 21, np.float32)
+    big_b = oracle.fill((400, ld), 22, np.float32)
+    big_c = oracle.fill((400, ld), 23, np.float32)
+    a, b = big_a[:m, :k], big_b[:k, :n]
+    ref = oracle.gemm(np.ascontiguousarray(a), np.ascontiguousarray(b))
+    want = big_c.copy()
+    want[:m, :n] = ref if mode == 0 else big_c[:m, :n] + ref
+    da, db, dc = DevBuf.from_array(big_a), DevBuf.from_array(big_b), DevBuf.from_array(big_c)
+    check(lib().la_debug_set_gemm_f32_path(2))
+    try:
+        gemm_dev(da, ld, db, ld, dc, ld, m, k, n, mode, np.float32)
+        sync()
+    finally:
+        lib().la_debug_set_gemm_f32_path(0)
+    got = dc.to_array((400, ld), np.float32)
+    assert np.array_equal(got[m:, :], big_c[m:, :]) and np.array_equal(got[:, n:], big_c[:, n:])
+    assert max_rel_err(got[:m, :n], want[:m, :n]) <= F32_TOL * k
 
 
 def test_gemm_signed_inputs_absolute_error(oracle):
