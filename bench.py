@@ -281,11 +281,16 @@ def main():
         dt = (time.perf_counter() - t0) / reps
         e2e = {"value": flops / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * n * n * 8,
                "d2h_bytes_per_step": n * n * 8, "ms_per_step": dt * 1e3,
-               "api": "la_gemm_f64_host (pinned host A,B,C; row-block pipelined H2D / DMMA kernel / D2H)"}
+               "api": "la_gemm_f64_host (pinned host A,B,C; K-panel then row-block pipelined H2D / DMMA kernel / D2H)"}
         chk(L.la_gemm_f64_dev(A.data_ptr(), k, B.data_ptr(), nn, C.data_ptr(), nn, m_loc, k, nn, 0, sp))
         torch.cuda.synchronize()
-        ok = bool(torch.equal(hC.to(dev), C))
-        e2e["matches_device_resident_result"] = ok
+        # the host path accumulates K in panels (C += A_p B_p): same products, partial sums rounded into C at panel
+        # boundaries -> compare to the single-launch result with the f64 parity tolerance instead of bit-equality
+        dC = hC.to(dev)
+        rel = float(((dC - C).abs() / C.abs().clamp_min(1e-300)).max())
+        e2e["max_rel_diff_vs_device_resident_result"] = rel
+        e2e["matches_device_resident_result"] = bool(rel <= 1e-12)
+        del dC
         del hA, hB, hC
     else:
         # multi-GPU e2e: host shards -> device, B from rank 0's host, result shard back to host

@@ -114,14 +114,64 @@ int gemm_host(const T* A, const T* B, T* C, size_t m, size_t k, size_t n) {
   // rows per block: multiple of 128 (the GEMM tile)
   size_t rows_blk = ((m + blocks - 1) / blocks + 127) / 128 * 128;
   blocks = (m + rows_blk - 1) / rows_blk;
-  LA_CUDA_TRY(cudaMemcpyAsync(dB, B, bb, cudaMemcpyHostToDevice, s_h2d));
-  for (size_t b = 0; b < blocks; ++b) {
-    const size_t r0 = b * rows_blk;
-    const size_t nr = (m - r0 < rows_blk) ? (m - r0) : rows_blk;
-    LA_CUDA_TRY(cudaMemcpyAsync((T*)dA + r0 * k, A + r0 * k, nr * k * sizeof(T), cudaMemcpyHostToDevice, s_h2d));
+  static thread_local cudaEvent_t ev_b2 = nullptr;
+  if (!ev_b2) LA_CUDA_TRY(cudaEventCreateWithFlags(&ev_b2, cudaEventDisableTiming));
+
+  // Deep products: two phases so that neither the upload of B nor the download of C is exposed.
+  //   phase 1 (columns [0, kh) of A / rows [0, kh) of B): K-panels -- panel p of A (strided) and of B go up, C (+)= A_p * B_p
+  //            over ALL rows starts as soon as the first pair has landed and hides the rest of the upload;
+  //   phase 2 (the other half of K): by row blocks, each block's rows of C are final after its GEMM and go down while
+  //            the next block multiplies.
+  // The accumulation order over k differs from a single launch only by where the partial sums are rounded into C.
+  size_t kh = 0;
+  if (k >= 2048) {
+    const size_t kp = 1024;
+    kh = (k * 5 / 8) / kp * kp;  // phase 2 keeps enough of K to cover the download of C
+    for (size_t p = 0; p * kp < kh; ++p) {
+      const size_t k0 = p * kp;
+      LA_CUDA_TRY(cudaMemcpyAsync((T*)dB + k0 * n, B + k0 * n, kp * n * sizeof(T), cudaMemcpyHostToDevice, s_h2d));
+      LA_CUDA_TRY(cudaMemcpy2DAsync((T*)dA + k0, k * sizeof(T), A + k0, k * sizeof(T), kp * sizeof(T), m,
+                                    cudaMemcpyHostToDevice, s_h2d));
+      LA_CUDA_TRY(cudaEventRecord(ev_b2, s_h2d));
+      LA_CUDA_TRY(cudaStreamWaitEvent(st, ev_b2, 0));
+      LA_TRY(gemm_dev<T>((const T*)dA + k0, k, (const T*)dB + k0 * n, n, (T*)dC, n, m, kp, n,
+                         p == 0 ? LA_GEMM_ASSIGN : LA_GEMM_ADD, st));
+    }
+  }
+  LA_CUDA_TRY(cudaMemcpyAsync((T*)dB + kh * n, B + kh * n, (k - kh) * n * sizeof(T), cudaMemcpyHostToDevice, s_h2d));
+  // Row blocks shrink towards the end (1/4, 1/4, 1/4, 1/8, 1/16, 1/16 of the rows): large blocks fill whole waves of
+  // tiles, the small last ones leave little of C to download after the final GEMM.
+  size_t blk_rows[16];
+  if (kh != 0 && m >= 16 * 128) {
+    const size_t q = (m / 4 + 127) / 128 * 128, e = (m / 8 + 127) / 128 * 128, x = (m / 16 + 127) / 128 * 128;
+    const size_t want[6] = {q, q, q, e, x, x};
+    size_t left = m;
+    blocks = 0;
+    for (int i = 0; i < 6 && left > 0; ++i) {
+      const size_t take = (i == 5 || want[i] > left) ? left : want[i];
+      blk_rows[blocks++] = take;
+      left -= take;
+    }
+    if (left > 0) blk_rows[blocks - 1] += left;
+  } else {
+    for (size_t b = 0; b < blocks; ++b) {
+      const size_t r0 = b * rows_blk;
+      blk_rows[b] = (m - r0 < rows_blk) ? (m - r0) : rows_blk;
+    }
+  }
+  size_t r0 = 0;
+  for (size_t b = 0; b < blocks; r0 += blk_rows[b], ++b) {
+    const size_t nr = blk_rows[b];
+    if (kh == 0) {
+      LA_CUDA_TRY(cudaMemcpyAsync((T*)dA + r0 * k, A + r0 * k, nr * k * sizeof(T), cudaMemcpyHostToDevice, s_h2d));
+    } else {
+      LA_CUDA_TRY(cudaMemcpy2DAsync((T*)dA + r0 * k + kh, k * sizeof(T), A + r0 * k + kh, k * sizeof(T),
+                                    (k - kh) * sizeof(T), nr, cudaMemcpyHostToDevice, s_h2d));
+    }
     LA_CUDA_TRY(cudaEventRecord(ev_up[b], s_h2d));
     LA_CUDA_TRY(cudaStreamWaitEvent(st, ev_up[b], 0));
-    LA_TRY(gemm_dev<T>((const T*)dA + r0 * k, k, (const T*)dB, n, (T*)dC + r0 * n, n, nr, k, n, LA_GEMM_ASSIGN, st));
+    LA_TRY(gemm_dev<T>((const T*)dA + r0 * k + kh, k, (const T*)dB + kh * n, n, (T*)dC + r0 * n, n, nr, k - kh, n,
+                       kh == 0 ? LA_GEMM_ASSIGN : LA_GEMM_ADD, st));
     LA_CUDA_TRY(cudaEventRecord(ev_done[b], st));
     LA_CUDA_TRY(cudaStreamWaitEvent(s_d2h, ev_done[b], 0));
     LA_CUDA_TRY(cudaMemcpyAsync(C + r0 * n, (T*)dC + r0 * n, nr * n * sizeof(T), cudaMemcpyDeviceToHost, s_d2h));
