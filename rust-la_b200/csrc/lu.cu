@@ -530,16 +530,42 @@ lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_pe
       }
       const int first = max(0, diag + 1 - row_base);
       const int q0 = (cn + 1) >> 5;  // first column group with work left
-      for (int lr = first + warp - 1; lr < nloc; lr += PANEL_WARPS - 1) {
-        if (lr == skip_a || lr == skip_b) continue;
-        const size_t off = (size_t)lr * ldr;
-        const T li = rows[off + c];
+      // four rows per trip, loads / arithmetic / stores grouped: the compiler cannot reorder the shared-memory stores
+      // of one row behind the loads of the next (possible aliasing), and one row at a time is a ~200-cycle dependent
+      // chain (FP64 latency) -- too slow for CTAs that hold 160+ rows
+      constexpr int UR = 4;
+      for (int lrb = first + warp - 1; lrb < nloc; lrb += UR * (PANEL_WARPS - 1)) {
+        T li[UR];
+        T v[UR][Q];
+        bool live[UR];
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-          const int col = lane + 32 * q;
-          if (q >= q0 && col > cn && col < jb) {
-            if (EXACT) sums[off + col] = add_rn(sums[off + col], mul_rn(li, u[q]));
-            else rows[off + col] = sub_rn(rows[off + col], mul_rn(li, u[q]));
+        for (int i = 0; i < UR; ++i) {
+          const int lr = lrb + i * (PANEL_WARPS - 1);
+          live[i] = lr < nloc && lr != skip_a && lr != skip_b;
+          const size_t off = (size_t)(live[i] ? lr : 0) * ldr;
+          li[i] = rows[off + c];
+#pragma unroll
+          for (int q = 0; q < Q; ++q) {
+            const int col = lane + 32 * q;
+            v[i][q] = (q >= q0 && col > cn && col < jb) ? (EXACT ? sums[off + col] : rows[off + col]) : (T)0;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < UR; ++i)
+#pragma unroll
+          for (int q = 0; q < Q; ++q)
+            v[i][q] = EXACT ? add_rn(v[i][q], mul_rn(li[i], u[q])) : sub_rn(v[i][q], mul_rn(li[i], u[q]));
+#pragma unroll
+        for (int i = 0; i < UR; ++i) {
+          if (!live[i]) continue;
+          const size_t off = (size_t)(lrb + i * (PANEL_WARPS - 1)) * ldr;
+#pragma unroll
+          for (int q = 0; q < Q; ++q) {
+            const int col = lane + 32 * q;
+            if (q >= q0 && col > cn && col < jb) {
+              if (EXACT) sums[off + col] = v[i][q];
+              else rows[off + col] = v[i][q];
+            }
           }
         }
       }
@@ -971,7 +997,7 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
     // Rows per CTA.  Fewer, fuller CTAs leave more SMs wholly to the bulk GEMMs (a panel CTA takes half the register
     // file, so a GEMM runs at half occupancy next to it) and the in-panel look-ahead hides their longer update; near
     // the end the bulk is negligible and many small CTAs give the shortest column time.
-    static const int rpc_min = getenv("LA_LU_RPC_MIN") ? atoi(getenv("LA_LU_RPC_MIN")) : 120;  // tuning knobs
+    static const int rpc_min = getenv("LA_LU_RPC_MIN") ? atoi(getenv("LA_LU_RPC_MIN")) : 200;  // tuning knobs
     static const int rpc_div = getenv("LA_LU_RPC_DIV") ? atoi(getenv("LA_LU_RPC_DIV")) : 64;
     int rpc = (R + sms - 1) / sms;
     int want = R / rpc_div;
