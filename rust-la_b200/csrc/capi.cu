@@ -127,15 +127,17 @@ int gemm_host(const T* A, const T* B, T* C, size_t m, size_t k, size_t n) {
   if (k >= 2048) {
     const size_t kp = 1024;
     kh = (k * 5 / 8) / kp * kp;  // phase 2 keeps enough of K to cover the download of C
-    for (size_t p = 0; p * kp < kh; ++p) {
-      const size_t k0 = p * kp;
-      LA_CUDA_TRY(cudaMemcpyAsync((T*)dB + k0 * n, B + k0 * n, kp * n * sizeof(T), cudaMemcpyHostToDevice, s_h2d));
-      LA_CUDA_TRY(cudaMemcpy2DAsync((T*)dA + k0, k * sizeof(T), A + k0, k * sizeof(T), kp * sizeof(T), m,
+    // the first panel is narrow (256): the first GEMM starts after 1/4 of a full panel's upload
+    for (size_t k0 = 0, p = 0; k0 < kh; ++p) {
+      const size_t w = (p == 0) ? 256 : ((p == 1) ? kp - 256 : kp);
+      LA_CUDA_TRY(cudaMemcpyAsync((T*)dB + k0 * n, B + k0 * n, w * n * sizeof(T), cudaMemcpyHostToDevice, s_h2d));
+      LA_CUDA_TRY(cudaMemcpy2DAsync((T*)dA + k0, k * sizeof(T), A + k0, k * sizeof(T), w * sizeof(T), m,
                                     cudaMemcpyHostToDevice, s_h2d));
       LA_CUDA_TRY(cudaEventRecord(ev_b2, s_h2d));
       LA_CUDA_TRY(cudaStreamWaitEvent(st, ev_b2, 0));
-      LA_TRY(gemm_dev<T>((const T*)dA + k0, k, (const T*)dB + k0 * n, n, (T*)dC, n, m, kp, n,
+      LA_TRY(gemm_dev<T>((const T*)dA + k0, k, (const T*)dB + k0 * n, n, (T*)dC, n, m, w, n,
                          p == 0 ? LA_GEMM_ASSIGN : LA_GEMM_ADD, st));
+      k0 += w;
     }
   }
   LA_CUDA_TRY(cudaMemcpyAsync((T*)dB + kh * n, B + kh * n, (k - kh) * n * sizeof(T), cudaMemcpyHostToDevice, s_h2d));

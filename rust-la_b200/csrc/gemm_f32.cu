@@ -103,13 +103,12 @@ __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Tile order: bands of GROUP_M tile rows, m fastest inside a band.  The CTAs of one wave then share a handful of B^T
+// Tile order: bands of group_m tile rows, m fastest inside a band.  The CTAs of one wave then share a handful of B^T
 // tiles and a band of A that both stay in L2 while the band sweeps all tile columns.
-constexpr int GROUP_M = 16;
-__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tile_m, int& tile_n) {
-  const int per_group = GROUP_M * tiles_n;
-  const int first_m = (t / per_group) * GROUP_M;
-  const int rows_here = min(GROUP_M, tiles_m - first_m);
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int group_m, int& tile_m, int& tile_n) {
+  const int per_group = group_m * tiles_n;
+  const int first_m = (t / per_group) * group_m;
+  const int rows_here = min(group_m, tiles_m - first_m);
   tile_m = first_m + (t % per_group) % rows_here;
   tile_n = (t % per_group) / rows_here;
 }
@@ -120,7 +119,7 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
 template <int MODE>
 __global__ void __launch_bounds__(TF32_THREADS, 1)
 gemm_f32_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int tiles_m, int tiles_n) {
+                     const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int tiles_m, int tiles_n, int group_m) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* out_stage = smem + TSTAGES * TSTAGE_BYTES;                     // [4 warps][2][32 rows x 128 B], 1024-aligned
@@ -163,7 +162,7 @@ gemm_f32_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       uint32_t g = 0;  // k-tiles issued so far (ring position)
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int tile_m, tile_n;
-        tile_coords(t, tiles_m, tiles_n, tile_m, tile_n);
+        tile_coords(t, tiles_m, tiles_n, group_m, tile_m, tile_n);
         for (int kt = 0; kt < ktiles; ++kt, ++g) {
           const int s = g % TSTAGES;
           mbar_wait(&empty[s], ((g / TSTAGES) & 1) ^ 1);
@@ -212,7 +211,7 @@ gemm_f32_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint32_t nbox = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       int tile_m, tile_n;
-      tile_coords(t, tiles_m, tiles_n, tile_m, tile_n);
+      tile_coords(t, tiles_m, tiles_n, group_m, tile_m, tile_n);
       const int b = it & 1;
       const int row0 = tile_m * TBM + quarter * 32;
       mbar_wait(&acc_full[b], (it >> 1) & 1);
@@ -282,8 +281,9 @@ int launch_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   LA_CUDA_TRY(cudaFuncSetAttribute(gemm_f32_tf32_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF32_SMEM));
   const int tiles_m = (M + TBM - 1) / TBM, tiles_n = (N + TBN - 1) / TBN;
   const int ntiles = tiles_m * tiles_n;
+  static const int group_m = getenv("LA_TF32_GROUP_M") ? atoi(getenv("LA_TF32_GROUP_M")) : 16;  // tuning knob
   gemm_f32_tf32_kernel<MODE><<<ntiles < sms ? ntiles : sms, TF32_THREADS, TF32_SMEM, st>>>(tmA, tmB, tmC, M, N, K, tiles_m,
-                                                                                         tiles_n);
+                                                                                         tiles_n, group_m);
   LA_CUDA_TRY(cudaGetLastError());
   return LA_OK;
 }
