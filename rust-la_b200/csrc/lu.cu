@@ -674,9 +674,16 @@ __global__ void __launch_bounds__(256) lu_swap_kernel(T* __restrict__ A, size_t 
 constexpr int IB = 32;
 constexpr int INVL_LD = MAX_NB + 1;
 constexpr int INVL_THREADS = 512;
-template <typename T>
-__global__ void __launch_bounds__(INVL_THREADS) lu_invl_kernel(const T* __restrict__ A, size_t ld, int j0, int jb,
-                                                               T* __restrict__ W /* [MAX_NB][MAX_NB] */) {
+// UPPER = true inverts the upper-triangular, non-unit block U instead (used by the many-right-hand-side solve): with
+// D = diag(U), U = D (I + N), N strictly upper; mirrored (i -> jb-1-i) I + N is a unit lower triangle, so the same code
+// inverts it; inv(U) = inv(I + N) D^-1 is un-mirrored and column-scaled on the way out.
+// Batched: block b of the grid handles the diagonal block at j0 + 128 b (clamped to `total`) and writes W + b * 128 * 128.
+template <typename T, bool UPPER>
+__global__ void __launch_bounds__(INVL_THREADS) lu_invl_kernel(const T* __restrict__ A, size_t ld, int j0, int jb, int total,
+                                                               T* __restrict__ W /* [grid][MAX_NB][MAX_NB] */) {
+  j0 += blockIdx.x * MAX_NB;
+  jb = min(jb, total - j0);
+  W += (size_t)blockIdx.x * MAX_NB * MAX_NB;
   // One padded square in shared memory holds both operands: the lower triangle (with diagonal) is W, the strictly
   // upper triangle is L11 transposed (L[i][k], k < i, lives at SQ[k][i]).  Products in flight use a separate scratch.
   extern __shared__ __align__(16) unsigned char invl_smem[];
@@ -686,7 +693,16 @@ __global__ void __launch_bounds__(INVL_THREADS) lu_invl_kernel(const T* __restri
   for (int idx = tid; idx < MAX_NB * MAX_NB; idx += INVL_THREADS) {
     const int i = idx / MAX_NB, k = idx - i * MAX_NB;
     if (k < i) {
-      SQ[k][i] = (i < jb) ? __ldcg(&A[(size_t)(j0 + i) * ld + j0 + k]) : (T)0;  // L^T into the upper triangle
+      T v = (T)0;
+      if (i < jb) {
+        if (UPPER) {  // mirrored, row-scaled: (I + N)[r][c] = U[r][c] / U[r][r], r = jb-1-i < c = jb-1-k
+          const int r = jb - 1 - i, c = jb - 1 - k;
+          v = __ldcg(&A[(size_t)(j0 + r) * ld + j0 + c]) / __ldcg(&A[(size_t)(j0 + r) * ld + j0 + r]);
+        } else {
+          v = __ldcg(&A[(size_t)(j0 + i) * ld + j0 + k]);
+        }
+      }
+      SQ[k][i] = v;  // L^T into the upper triangle
       SQ[i][k] = (T)0;
     } else if (k == i) {
       SQ[i][i] = (T)0;
@@ -741,7 +757,13 @@ __global__ void __launch_bounds__(INVL_THREADS) lu_invl_kernel(const T* __restri
   }
   for (int idx = tid; idx < MAX_NB * MAX_NB; idx += INVL_THREADS) {
     const int i = idx / MAX_NB, k = idx - i * MAX_NB;
-    W[idx] = (k <= i && i < jb) ? SQ[i][k] : (T)0;
+    if (UPPER) {  // W[r][c] = inv(I + N)[r][c] / U[c][c], c >= r
+      T v = (T)0;
+      if (k >= i && k < jb) v = SQ[jb - 1 - i][jb - 1 - k] / __ldcg(&A[(size_t)(j0 + k) * ld + j0 + k]);
+      W[idx] = v;
+    } else {
+      W[idx] = (k <= i && i < jb) ? SQ[i][k] : (T)0;
+    }
   }
 }
 
@@ -982,7 +1004,7 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
                                    (int)PANEL_SMEM_BUDGET + 2048));
   LA_CUDA_TRY(cudaFuncSetAttribute(lu_swap_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWAP_SMEM));
   LA_CUDA_TRY(cudaFuncSetAttribute(lu_swap_trsm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM));
-  LA_CUDA_TRY(cudaFuncSetAttribute(lu_invl_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, INVL_SMEM));
+  LA_CUDA_TRY(cudaFuncSetAttribute(lu_invl_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, INVL_SMEM));
 
   lu_init_piv_kernel<T><<<(M + 255) / 256, 256, 0, st>>>(piv_dev, M, sign_dev);
   LA_CUDA_TRY(cudaGetLastError());
@@ -1107,7 +1129,7 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
       if (need_w) {
         LA_CUDA_TRY(cudaEventRecord(side->e_panel, sp));
         LA_CUDA_TRY(cudaStreamWaitEvent(sw, side->e_panel, 0));
-        lu_invl_kernel<T><<<1, INVL_THREADS, INVL_SMEM, sw>>>(LU, n, j0, jb, W);
+        lu_invl_kernel<T, false><<<1, INVL_THREADS, INVL_SMEM, sw>>>(LU, n, j0, jb, j0 + jb, W);
         LA_CUDA_TRY(cudaGetLastError());
         LA_CUDA_TRY(cudaEventRecord(side->e_w, sw));
       }
@@ -1167,6 +1189,19 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
   }
   return LA_OK;
 }
+// Inverses of all 128 x 128 diagonal blocks of a packed LU (order n): WL[b] = inv(L_bb) (unit lower), WU[b] = inv(U_bb).
+// One launch each; used by the many-right-hand-side solve (lu_solve.cu), which then needs GEMMs only.
+int lu_diag_block_inverses(const double* LU, size_t n, double* WL, double* WU, cudaStream_t st) {
+  const int INVL_SMEM = (int)(sizeof(double) * ((size_t)MAX_NB * INVL_LD + 3 * IB * IB));
+  LA_CUDA_TRY(cudaFuncSetAttribute(lu_invl_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, INVL_SMEM));
+  LA_CUDA_TRY(cudaFuncSetAttribute(lu_invl_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, INVL_SMEM));
+  const int G = (int)((n + MAX_NB - 1) / MAX_NB);
+  lu_invl_kernel<double, false><<<G, INVL_THREADS, INVL_SMEM, st>>>(LU, n, 0, MAX_NB, (int)n, WL);
+  lu_invl_kernel<double, true><<<G, INVL_THREADS, INVL_SMEM, st>>>(LU, n, 0, MAX_NB, (int)n, WU);
+  LA_CUDA_TRY(cudaGetLastError());
+  return LA_OK;
+}
+
 template int lu_factor_dev<double>(double*, size_t, size_t, uint64_t*, int*, cudaStream_t);
 template int lu_factor_dev<float>(float*, size_t, size_t, uint64_t*, int*, cudaStream_t);
 

@@ -21,6 +21,9 @@
 #include "la_common.cuh"
 
 namespace la {
+int gemm_f64_tensor(const double* A, size_t lda, const double* B, size_t ldb, double* C, size_t ldc, size_t m, size_t k,
+                    size_t n, int mode, cudaStream_t st);  // gemm_f64.cu: TMA/DMMA kernel regardless of size
+int lu_diag_block_inverses(const double* LU, size_t n, double* WL, double* WU, cudaStream_t st);  // lu.cu
 namespace {
 
 constexpr int SB = 64;        // diagonal block
@@ -463,6 +466,41 @@ int lu_solve_dev(const T* LU, size_t n, const uint64_t* piv_dev, const T* B, siz
                     (double)(e[4] - e[3]) * 1e-3);
           }
         }
+      }
+      return LA_OK;
+    }
+  }
+  // many right-hand sides (inverse = n of them), fp64, TMA-addressable: inverted 128 x 128 diagonal blocks turn both
+  // sweeps into DMMA GEMMs -- per block row X_b = W_b * X_b (in place, one tile row) and X_rest -= LU[rest][b] * X_b
+  if constexpr (std::is_same<T, double>::value) {
+    static const int no_gemm = getenv("LA_SOLVE_NO_GEMM") ? atoi(getenv("LA_SOLVE_NO_GEMM")) : 0;  // debug knob
+    if (!no_gemm && nx > 16 && N >= 4 * PB && N % 2 == 0 && nx % 2 == 0 && (uintptr_t)LU % 16 == 0 &&
+        (uintptr_t)X % 16 == 0) {
+      const int G = (N + PB - 1) / PB;
+      void* wbuf = nullptr;
+      LA_TRY(scratch_get(ctx->device, 15, sizeof(double) * 2 * (size_t)G * PB * PB, &wbuf));
+      double* WL = (double*)wbuf;
+      double* WU = WL + (size_t)G * PB * PB;
+      LA_TRY(lu_diag_block_inverses(LU, n, WL, WU, st));
+      {
+        size_t blocks = (n * nx + 255) / 256;
+        size_t cap = (size_t)ctx->sm_count * 8;
+        gather_rows_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(B, X, piv_dev, n, nx);
+        LA_CUDA_TRY(cudaGetLastError());
+      }
+      for (int b = 0; b < G; ++b) {  // forward: L * Y = B(piv,:)
+        const size_t r0 = (size_t)b * PB, nr = (n - r0 < (size_t)PB) ? (n - r0) : (size_t)PB;
+        double* Xb = X + r0 * nx;
+        LA_TRY(gemm_f64_tensor(WL + (size_t)b * PB * PB, PB, Xb, nx, Xb, nx, nr, nr, nx, LA_GEMM_ASSIGN, st));
+        if (r0 + nr < n)
+          LA_TRY(gemm_f64_tensor(LU + (r0 + nr) * n + r0, n, Xb, nx, X + (r0 + nr) * nx, nx, n - r0 - nr, nr, nx,
+                                 LA_GEMM_SUB, st));
+      }
+      for (int b = G - 1; b >= 0; --b) {  // backward: U * X = Y
+        const size_t r0 = (size_t)b * PB, nr = (n - r0 < (size_t)PB) ? (n - r0) : (size_t)PB;
+        double* Xb = X + r0 * nx;
+        LA_TRY(gemm_f64_tensor(WU + (size_t)b * PB * PB, PB, Xb, nx, Xb, nx, nr, nr, nx, LA_GEMM_ASSIGN, st));
+        if (r0 > 0) LA_TRY(gemm_f64_tensor(LU + r0, n, Xb, nx, X, nx, r0, nr, nx, LA_GEMM_SUB, st));
       }
       return LA_OK;
     }

@@ -140,10 +140,12 @@ def test_solve_given_reference_factors_matches_oracle(oracle, n, nx):
     assert np.array_equal(x.view(np.uint64), ref_x.view(np.uint64))
 
 
-@pytest.mark.parametrize("n,nx", [(512, 16), (640, 7), (1154, 16), (2048, 1), (2306, 9), (4096, 16)])
+@pytest.mark.parametrize("n,nx", [(512, 16), (640, 7), (1154, 16), (2048, 1), (2306, 9), (4096, 16),
+                                  (640, 32), (1154, 100), (2048, 2048), (2306, 18)])
 def test_solve_sweep_given_reference_factors(oracle, n, nx):
     """n >= 512, even, nx <= 16: the persistent sweep kernels (ragged last block included).  Same elimination order
-    with fused multiply-adds and a reciprocal diagonal: the solution must satisfy the SAME triangular systems as the
+    with fused multiply-adds and a reciprocal diagonal.  nx > 16 (even): inverted 128 x 128 diagonal blocks + DMMA GEMMs
+    (the path `inverse()` takes).  Either way the solution must satisfy the SAME triangular systems as the
     oracle's to rounding -- component-wise backward error of L*U*x = b(piv) within 4x the oracle's own, and the
     difference to the oracle's x within the 1e-12*n bar scaled by the conditioning."""
     a = oracle.fill((n, n), 1)

@@ -39,3 +39,15 @@ for r in range(reps):
         sync()
     t2 = time.perf_counter()
     print(f"n={n} lu {1e3 * (t1 - t0):.2f} ms ({2 / 3 * n ** 3 / (t1 - t0) / 1e12:.2f} TFLOP/s) solve {1e3 * (t2 - t1):.2f} ms")
+if "--inverse" in sys.argv:
+    # many right-hand sides: X = A^-1 for the last factorisation (nx = n), the path Matrix::inverse takes
+    eye = DevBuf(n * n * es)
+    inv = DevBuf(n * n * es)
+    check((L.la_identity_f32 if f32 else L.la_identity_f64)(eye.h, n))
+    for r in range(2):
+        sync()
+        t0 = time.perf_counter()
+        check(solve(a.ptr(), n, piv.ptr(), eye.ptr(), n, inv.ptr(), None))
+        sync()
+        t1 = time.perf_counter()
+        print(f"n={n} inverse (solve with n right-hand sides) {1e3 * (t1 - t0):.2f} ms ({2.0 * n ** 3 / (t1 - t0) / 1e12:.2f} TFLOP/s)")
