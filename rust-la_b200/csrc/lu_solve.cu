@@ -120,22 +120,20 @@ __global__ void __launch_bounds__(256) solve_update_kernel(const T* __restrict__
 
 // ---------------------------------------------------------------------------------------------------------------
 // Few right-hand sides (nx <= 16), fp64: one persistent cooperative kernel per sweep instead of ~4*n/SB launches.
-//   CTA g owns rows [128 g, 128 g + 128) of X for the whole sweep and keeps them in registers (thread <-> one row x 8
+//   CTA g owns rows [128 g, 128 g + 128) of X for the whole sweep and keeps them in registers (thread <-> 2 rows x 8
 //   columns).  Forward: for k = 0 .. g-1 it waits for block k of the solution (a flag per reader, set by CTA k after a
 //   fence), subtracts LU[g-block][k-block] * X_k -- LU streamed through shared memory by cp.async, two 64-column
-//   halves in flight -- then solves its own 128 x 128 triangle by shuffle substitution (one warp <-> two columns) and
-//   publishes.  Backward is the mirror image with U, dividing by the diagonal first.
-//   Every element still receives its updates in the reference's order (k ascending / descending), but -- like the
-//   multi-panel factorisation -- with fused multiply-adds and a multiplication by the reciprocal of the diagonal: the
-//   sweep is ONE dependent chain of n steps (x_k -> multiply -> subtract [-> divide] -> x_k+1), so every instruction
-//   on it costs n latencies (separately rounded ops + true division: 7.5 ms at n = 16384; this form: see DESIGN.md).
-//   Systems below 512 rows take the launch-per-block path below, which is bit-identical to the reference.
-//   LU is read exactly once per sweep.
+//   halves in flight -- then multiplies by the INVERTED diagonal block (lu_diag_block_inverses, one batched launch per
+//   triangle up front; the same policy as the factorisation's U12 = inv(L11) * A12) and publishes.  Backward is the
+//   mirror image with U.  A substitution inside the block would be one dependent chain of 128 x (FMA + shuffle
+//   [+ divide]) per block -- measured 6.7 us forward / 13 us backward per block against 2 us for the product.
+//   LU is read exactly once per sweep.  Systems below 512 rows take the launch-per-block path below, which keeps the
+//   reference's order with separately rounded operations and is bit-identical to it.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int PB = 128;  // rows per CTA = columns per step
 constexpr int PH = 64;   // columns per shared-memory buffer
 constexpr int SWEEP_THREADS = 256;
-constexpr int SWEEP_SMEM = (2 * PB * PH + PB * 16 + PB * 17) * (int)sizeof(double);
+constexpr int SWEEP_SMEM = (2 * PB * PH + PB * 16) * (int)sizeof(double);
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -145,48 +143,50 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-// Lbuf[half][row][64 columns], 16-byte chunks XOR-swizzled by the row: the update's 128-bit reads (lane <-> row, fixed
-// column pair) are conflict-free
-__device__ __forceinline__ int lbuf_index(int row, int c128) {
-  const int half = c128 >> 6, c = c128 & 63;
-  return (half * PB + row) * PH + ((((c >> 1) ^ (row & 7))) << 1) + (c & 1);
-}
+// Lbuf[half][row][64 columns]: 16-byte chunks XOR-swizzled by the row, so the inner loop's 128-bit reads (lane <-> row,
+// fixed column pair) are conflict-free.
 
 template <bool FORWARD>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1)
 solve_sweep_kernel(const double* __restrict__ LU, size_t n, const uint64_t* __restrict__ piv, const double* __restrict__ B,
                    double* __restrict__ X, int nx, unsigned* __restrict__ flags /* [G readers][G blocks] */,
+                   const double* __restrict__ Winv /* [G][128][128]: inverted diagonal blocks of L (FORWARD) or U */,
                    unsigned long long* __restrict__ dbg /* optional [G][8] phase timestamps (ns) of the last step */) {
   extern __shared__ __align__(16) unsigned char sweep_smem[];
   double* Lbuf = reinterpret_cast<double*>(sweep_smem);      // [2][PB][PH]
   double* Ys = Lbuf + 2 * PB * PH;                           // [PB][16]: block k of the solution
-  double(*Ts)[17] = reinterpret_cast<double(*)[17]>(Ys + PB * 16);  // [PB]: transpose staging for the triangle
   const int G = gridDim.x, g = blockIdx.x;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int r = t & (PB - 1), h = t >> 7;  // row within the block, column half (8 columns)
   const int N = (int)n;
   const int r0 = g * PB;
   const int nr = min(PB, N - r0);
   const uint32_t lbuf_s = (uint32_t)__cvta_generic_to_shared(Lbuf);
 
-  // one 64-column half of LU[r0 .. r0+128)[128 kb + 64 hh ..) into buffer hh (zero-filled outside the matrix)
+  // one 64-column half of LU[r0 .. r0+128)[128 kb + 64 hh ..) into buffer hh (zero-filled outside the matrix);
+  // kb < 0: the CTA's own inverted diagonal block instead (dense 128 x 128, zero-padded)
   auto issue_half = [&](int kb, int hh) {
     const int cbase = kb * PB + hh * PH;
+    const double* wsrc = Winv + (size_t)g * PB * PB + hh * PH;
 #pragma unroll 4
     for (int i = 0; i < (PB * PH / 2) / SWEEP_THREADS; ++i) {
       const int id = t + SWEEP_THREADS * i;
       const int rr = id >> 5, cc = id & 31;
-      const int col = cbase + 2 * cc;
-      const bool ok = r0 + rr < N && col < N;  // n is even: a pair of columns is inside or outside as a whole
-      const double* src = ok ? LU + (size_t)(r0 + rr) * n + col : LU;
-      cp_async16(lbuf_s + (uint32_t)(((hh * PB + rr) * PH + ((cc ^ (rr & 7)) << 1)) * sizeof(double)), src, ok ? 16 : 0);
+      const uint32_t dst = lbuf_s + (uint32_t)(((hh * PB + rr) * PH + ((cc ^ (rr & 7)) << 1)) * sizeof(double));
+      if (kb < 0) {
+        cp_async16(dst, wsrc + (size_t)rr * PB + 2 * cc, 16);
+      } else {
+        const int col = cbase + 2 * cc;
+        const bool ok = r0 + rr < N && col < N;  // n is even: a pair of columns is inside or outside as a whole
+        cp_async16(dst, ok ? LU + (size_t)(r0 + rr) * n + col : LU, ok ? 16 : 0);
+      }
     }
     cp_async_commit();
   };
 
-  // Update phase (warps 0..3): thread <-> 2 rows x 8 columns of the right-hand sides (shared-memory reads, not FP64
-  // issue, bound the update: 2x8 needs 6 128-bit loads per 32 FMAs).  Rows lane + 32 i keep the swizzled reads
-  // conflict-free.
+  // Warps 0..3 compute: thread <-> 2 rows x 8 columns of the right-hand sides (shared-memory reads, not FP64 issue
+  // slots, bound the inner loop: 2x8 needs 6 128-bit loads per 32 FMAs).  Rows lane + 32 i keep the swizzled reads
+  // conflict-free.  Even and odd k accumulate separately: a DFMA result takes ~64 cycles to come back, and one chain
+  // of 128 dependent FMAs per element would be the whole step.
   const int urow = ((warp & 1) << 6) + lane;  // + 32 i
   const int ucol = (warp >> 1) << 3;          // 8 columns from here (warps 0..3 only)
   double acc[2][8];
@@ -199,6 +199,36 @@ solve_sweep_kernel(const double* __restrict__ LU, size_t n, const uint64_t* __re
       if (warp < 4 && rr < nr && col < nx)  // X = B(piv,:), lu.rs:246-254
         acc[i][j] = FORWARD ? B[(size_t)piv[r0 + rr] * nx + col] : X[(size_t)(r0 + rr) * nx + col];
     }
+  // a0/a1 -= (rows urow, urow+32 of buffer hh) * (rows [64 hh, 64 hh + 64) of Ys)
+  auto mac_half = [&](int hh, double (&a0)[2][8], double (&a1)[2][8]) {
+    const double* Lr0 = Lbuf + (hh * PB + urow) * PH;
+    const double* Lr1 = Lr0 + 32 * PH;
+    const int sw = urow & 7;  // == (urow + 32) & 7
+    const double* Yh = Ys + (hh * PH) * 16 + ucol;
+#pragma unroll 4
+    for (int i = 0; i < PH / 2; ++i) {
+      const int kk = 2 * i;
+      const int lo = ((kk >> 1) ^ sw) << 1;
+      const double2 l0 = *reinterpret_cast<const double2*>(Lr0 + lo);
+      const double2 l1 = *reinterpret_cast<const double2*>(Lr1 + lo);
+      double y[8];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(&y[j]) = *reinterpret_cast<const double2*>(Yh + kk * 16 + j);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a0[0][j] = fma(-y[j], l0.x, a0[0][j]);
+        a0[1][j] = fma(-y[j], l1.x, a0[1][j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j += 2)
+        *reinterpret_cast<double2*>(&y[j]) = *reinterpret_cast<const double2*>(Yh + (kk + 1) * 16 + j);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a1[0][j] = fma(-y[j], l0.y, a1[0][j]);
+        a1[1][j] = fma(-y[j], l1.y, a1[1][j]);
+      }
+    }
+  };
 
   auto stamp = [&](int slot) {
     if (dbg && t == 0) {
@@ -209,15 +239,14 @@ solve_sweep_kernel(const double* __restrict__ LU, size_t n, const uint64_t* __re
   };
   const int nsteps = FORWARD ? g : G - 1 - g;  // blocks of the solution this CTA consumes before its own
   auto step_block = [&](int s) { return FORWARD ? s : G - 1 - s; };
-  const int first_half = FORWARD ? 0 : 1;
   {
-    const int kb = nsteps > 0 ? step_block(0) : g;
-    issue_half(kb, first_half);
-    issue_half(kb, first_half ^ 1);
+    const int kb = nsteps > 0 ? step_block(0) : -1;
+    issue_half(kb, 0);
+    issue_half(kb, 1);
   }
   for (int s = 0; s < nsteps; ++s) {
     const int kb = step_block(s);
-    const int next_kb = (s + 1 < nsteps) ? step_block(s + 1) : g;  // the CTA's own diagonal block comes last
+    const int next_kb = (s + 1 < nsteps) ? step_block(s + 1) : -1;  // the CTA's own inverted diagonal block comes last
     if (t == 0) {
       const volatile unsigned* f = flags + (size_t)g * G + kb;
       while (*f == 0u) {
@@ -231,146 +260,55 @@ solve_sweep_kernel(const double* __restrict__ LU, size_t n, const uint64_t* __re
       const int grow = kb * PB + rr;
       Ys[idx] = (grow < N && col < nx) ? __ldcg(&X[(size_t)grow * nx + col]) : 0.0;
     }
+    double odd[2][8];
 #pragma unroll
-    for (int hx = 0; hx < 2; ++hx) {
-      const int hh = first_half ^ hx;
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) odd[i][j] = 0.0;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
       cp_async_wait<1>();
       __syncthreads();  // buffer hh (and, the first time round, Ys) is ready
-      if (warp < 4) {
-        const double* Lr0 = Lbuf + (hh * PB + urow) * PH;
-        const double* Lr1 = Lr0 + 32 * PH;
-        const int sw = urow & 7;  // == (urow + 32) & 7
-        const double* Yh = Ys + (hh * PH) * 16 + ucol;
-#pragma unroll 4
-        for (int i = 0; i < PH / 2; ++i) {
-          const int kk = FORWARD ? 2 * i : PH - 2 - 2 * i;
-          const int lo = ((kk >> 1) ^ sw) << 1;
-          const double2 l0 = *reinterpret_cast<const double2*>(Lr0 + lo);
-          const double2 l1 = *reinterpret_cast<const double2*>(Lr1 + lo);
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {  // the two columns of the pair in elimination order (lu.rs:260 / :272)
-            const int ke = FORWARD ? e : 1 - e;
-            const double la = ke ? l0.y : l0.x, lb = ke ? l1.y : l1.x;
-            const double* yr = Yh + (kk + ke) * 16;
-            double y[8];
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(&y[j]) = *reinterpret_cast<const double2*>(yr + j);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              acc[0][j] = fma(-y[j], la, acc[0][j]);
-              acc[1][j] = fma(-y[j], lb, acc[1][j]);
-            }
-          }
-        }
-      }
+      if (warp < 4) mac_half(hh, acc, odd);
       __syncthreads();  // everyone is done with buffer hh
       issue_half(next_kb, hh);
     }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] += odd[i][j];
   }
   stamp(1);  // updates done
-  cp_async_wait<0>();
-  __syncthreads();  // the diagonal block LU[g-block][g-block] is in the two buffers
-  stamp(2);
 
-  // ---- the CTA's own triangle: warp <-> two columns, lane <-> rows lane, lane+32, ... ----
+  // ---- X_g = W_g * (right-hand sides of this block): the same inner loop on the inverted diagonal block ----
   if (warp < 4) {
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) Ts[urow + 32 * i][ucol + j] = acc[i][j];
+      for (int j = 0; j < 8; ++j) Ys[(urow + 32 * i) * 16 + ucol + j] = acc[i][j];
   }
-  __shared__ double rdiag[PB];
-  if (!FORWARD && t < PB) rdiag[t] = (t < nr) ? 1.0 / Lbuf[lbuf_index(t, t)] : 0.0;
-  __syncthreads();
-  // warp <-> four columns, lane <-> rows lane, lane+32, ...; two elimination steps per 128-bit read of a row's pair
-  // of L/U entries (a column walk of single entries would be a 4-way bank conflict in the swizzled layout)
-  constexpr int Q = PB / 32;
-  constexpr int C = 4;
+  cp_async_wait<0>();
+  __syncthreads();  // W_g is in the two buffers, the block's right-hand sides in Ys
+  stamp(2);
   if (warp < 4) {
-    double x[Q][C];
+    double even[2][8], odd[2][8];
 #pragma unroll
-    for (int q = 0; q < Q; ++q)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int c = 0; c < C; ++c) x[q][c] = Ts[lane + 32 * q][C * warp + c];
-    const int sw = lane & 7;
-    if (FORWARD) {
+      for (int j = 0; j < 8; ++j) even[i][j] = odd[i][j] = 0.0;
+    mac_half(0, even, odd);
+    mac_half(1, even, odd);
 #pragma unroll
-      for (int kq = 0; kq < Q; ++kq) {
-        if (kq * 32 < nr) {
-#pragma unroll 4
-          for (int kl = 0; kl < 32; kl += 2) {
-            const int k = kq * 32 + kl;
-            double2 l2[Q];
+    for (int i = 0; i < 2; ++i) {
+      const int rr = urow + 32 * i;
+      if (rr < nr) {
 #pragma unroll
-            for (int q = kq; q < Q; ++q)
-              l2[q] = *reinterpret_cast<const double2*>(Lbuf + ((k >> 6) * PB + lane + 32 * q) * PH +
-                                                        ((((k & 63) >> 1) ^ sw) << 1));
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              double xk[C];
-#pragma unroll
-              for (int c = 0; c < C; ++c) xk[c] = __shfl_sync(0xffffffffu, x[kq][c], kl + e);
-#pragma unroll
-              for (int q = kq; q < Q; ++q) {
-                const double l = e ? l2[q].y : l2[q].x;
-                if (q > kq || lane > kl + e) {  // rows strictly below k (lu.rs:257-263)
-#pragma unroll
-                  for (int c = 0; c < C; ++c) x[q][c] = fma(-xk[c], l, x[q][c]);
-                }
-              }
-            }
-          }
-        }
-      }
-    } else {
-#pragma unroll
-      for (int kq = Q - 1; kq >= 0; --kq) {
-        if (kq * 32 < nr) {
-#pragma unroll 4
-          for (int kl = 30; kl >= 0; kl -= 2) {
-            const int k = kq * 32 + kl;  // the pair (k + 1, k), in that order
-            double2 u2[Q];
-#pragma unroll
-            for (int q = 0; q <= kq; ++q)
-              u2[q] = *reinterpret_cast<const double2*>(Lbuf + ((k >> 6) * PB + lane + 32 * q) * PH +
-                                                        ((((k & 63) >> 1) ^ sw) << 1));
-#pragma unroll
-            for (int e = 1; e >= 0; --e) {
-              if (k + e < nr) {
-                const double rd = rdiag[k + e];  // 1 / U[k][k] (lu.rs:268), taken off the dependent chain
-                double xk[C];
-#pragma unroll
-                for (int c = 0; c < C; ++c) xk[c] = __shfl_sync(0xffffffffu, x[kq][c], kl + e) * rd;
-                if (lane == kl + e) {
-#pragma unroll
-                  for (int c = 0; c < C; ++c) x[kq][c] = xk[c];
-                }
-#pragma unroll
-                for (int q = 0; q <= kq; ++q) {
-                  const double u = e ? u2[q].y : u2[q].x;
-                  if (q < kq || lane < kl + e) {  // rows strictly above k (lu.rs:270-274)
-#pragma unroll
-                    for (int c = 0; c < C; ++c) x[q][c] = fma(-xk[c], u, x[q][c]);
-                  }
-                }
-              }
-            }
-          }
-        }
+        for (int j = 0; j < 8; ++j)
+          if (ucol + j < nx) X[(size_t)(r0 + rr) * nx + ucol + j] = -(even[i][j] + odd[i][j]);
       }
     }
-#pragma unroll
-    for (int q = 0; q < Q; ++q)
-#pragma unroll
-      for (int c = 0; c < C; ++c) Ts[lane + 32 * q][C * warp + c] = x[q][c];
   }
-  __syncthreads();
-  if (r < nr) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (8 * h + j < nx) X[(size_t)(r0 + r) * nx + 8 * h + j] = Ts[r][8 * h + j];
-  }
-  stamp(3);  // triangle solved, X stored
+  stamp(3);  // block solved, X stored
   __threadfence();
   __syncthreads();
   stamp(4);  // fenced
@@ -445,8 +383,13 @@ int lu_solve_dev(const T* LU, size_t n, const uint64_t* piv_dev, const T* B, siz
         d0 = (unsigned long long*)dp;
         d1 = d0 + 8 * G;
       }
-      void* a0[] = {&lu_p, &nn, &piv_dev, &b_p, &x_p, &nxi, &f0, &d0};
-      void* a1[] = {&lu_p, &nn, &piv_dev, &b_p, &x_p, &nxi, &f1, &d1};
+      void* wbuf = nullptr;
+      LA_TRY(scratch_get(ctx->device, 15, sizeof(double) * 2 * (size_t)G * PB * PB, &wbuf));
+      const double* wl = (const double*)wbuf;
+      const double* wu = wl + (size_t)G * PB * PB;
+      LA_TRY(lu_diag_block_inverses(LU, n, (double*)wbuf, (double*)wbuf + (size_t)G * PB * PB, st));
+      void* a0[] = {&lu_p, &nn, &piv_dev, &b_p, &x_p, &nxi, &f0, &wl, &d0};
+      void* a1[] = {&lu_p, &nn, &piv_dev, &b_p, &x_p, &nxi, &f1, &wu, &d1};
       LA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)solve_sweep_kernel<true>, dim3(G), dim3(SWEEP_THREADS), a0,
                                               SWEEP_SMEM, st));
       LA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)solve_sweep_kernel<false>, dim3(G), dim3(SWEEP_THREADS), a1,
@@ -460,7 +403,7 @@ int lu_solve_dev(const T* LU, size_t n, const uint64_t* piv_dev, const T* B, siz
           const unsigned long long t0 = ph == 0 ? hb[3] : hb[(size_t)(G - 1) * 8 + 3];
           for (int g = 0; g < G; g += (G > 16 ? G / 16 : 1)) {
             const unsigned long long* e = hb + (size_t)g * 8;
-            fprintf(stderr, "solve %s cta %3d: flag %8.2f us | +Y/update %6.2f | +Lwait %5.2f | +triangle %6.2f | +fence %5.2f\n",
+            fprintf(stderr, "solve %s cta %3d: flag %8.2f us | +Y/update %6.2f | +Lwait %5.2f | +block product %6.2f | +fence %5.2f\n",
                     ph == 0 ? "fwd" : "bwd", g, e[0] ? (double)(e[0] - t0) * 1e-3 : 0.0,
                     e[0] ? (double)(e[1] - e[0]) * 1e-3 : 0.0, (double)(e[2] - e[1]) * 1e-3, (double)(e[3] - e[2]) * 1e-3,
                     (double)(e[4] - e[3]) * 1e-3);
