@@ -988,6 +988,10 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
   static const int dbg = getenv("LA_LU_DEBUG") ? atoi(getenv("LA_LU_DEBUG")) : 0;  // 1: one stream, 2: plain loop
   const bool fast = std::is_same<T, double>::value && kmin > nb && (N % 2 == 0) && ((uintptr_t)LU % 16 == 0) &&
                     (kmin % 2 == 0 || kmin == N) && dbg != 2;
+  // multi-panel fp32: the same chain / bulk look-ahead, but exact fp32 arithmetic throughout (the parity bar is an
+  // IDENTICAL pivot sequence to the fp32 reference, which TF32 tensor tiles would not give): U12 by substitution for
+  // all columns, trailing update on the CUDA-core GEMM
+  const bool fast32 = std::is_same<T, float>::value && kmin > nb && dbg != 2;
 
   void* ws_base = nullptr;
   LA_TRY(scratch_get(ctx->device, 8, ws_bytes<T>(sms), &ws_base));
@@ -1055,8 +1059,8 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
     return LA_OK;
   };
 
-  if (!fast) {
-    // ---- plain right-looking loop (single panel / fp32 / odd leading dimension): substitution TRSM kernel ----
+  if (!fast && !fast32) {
+    // ---- plain right-looking loop (single panel / odd leading dimension): substitution TRSM kernel ----
     for (int j0 = 0; j0 < kmin; j0 += nb) {
       const int jb = (kmin - j0 < nb) ? (kmin - j0) : nb;
       LA_TRY(launch_panel(j0, jb, st));
@@ -1184,6 +1188,53 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
       for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
     // the caller's stream must also cover the tail of the chain stream
+    LA_CUDA_TRY(cudaEventRecord(side->e_head, sp));
+    LA_CUDA_TRY(cudaStreamWaitEvent(st, side->e_head, 0));
+  } else {
+    // ---- look-ahead pipeline (fp32): chain = perm -> [wait bulk(i-1)] -> head (next panel's columns) -> their trailing
+    //      update -> panel(i+1); bulk = interchanges left, head kernel (interchanges + U12) and trailing update right ----
+    LuSide* side;
+    LA_TRY(lu_side(ctx->device, &side));
+    cudaStream_t sp = dbg == 1 ? st : side->sp;
+    const size_t ld = n;
+    const int HEAD_SMEM = (int)(sizeof(T) * ((size_t)MAX_NB * HEAD_LD + (size_t)MAX_NB * (HEAD_COLS + 1) +
+                                             (size_t)MAX_NB * HEAD_COLS));
+    LA_CUDA_TRY(cudaFuncSetAttribute(lu_head_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM));
+    LA_CUDA_TRY(cudaEventRecord(side->e_in, st));
+    LA_CUDA_TRY(cudaStreamWaitEvent(sp, side->e_in, 0));
+    LA_TRY(launch_panel(0, nb, sp));
+    int it = 0;
+    for (int j0 = 0; j0 < kmin; j0 += nb, ++it) {
+      const int jb = (kmin - j0 < nb) ? (kmin - j0) : nb;
+      const int c1 = j0 + jb;
+      const int parity = it & 1;
+      const bool has_next = c1 < kmin;
+      const int nb2 = has_next ? ((kmin - c1 < nb) ? (kmin - c1) : nb) : 0;
+      const int c2 = c1 + nb2;
+      auto head_and_update = [&](int cb, int ce, cudaStream_t s) -> int {  // columns [cb, ce)
+        if (ce <= cb) return LA_OK;
+        lu_head_kernel<T><<<(ce - cb + HEAD_COLS - 1) / HEAD_COLS, 256, HEAD_SMEM, s>>>(LU, n, j0, jb, cb, ce, ws_base, G_cur,
+                                                                                    parity);
+        LA_CUDA_TRY(cudaGetLastError());
+        if (c1 < M)
+          LA_TRY(gemm_dev<T>(LU + (size_t)c1 * ld + j0, ld, LU + (size_t)j0 * ld + cb, ld, LU + (size_t)c1 * ld + cb, ld,
+                             (size_t)(M - c1), (size_t)jb, (size_t)(ce - cb), LA_GEMM_SUB, s));
+        return LA_OK;
+      };
+      // ---- chain ----
+      LA_TRY(launch_perm(j0, jb, parity, sp));
+      LA_CUDA_TRY(cudaEventRecord(side->e_head, sp));
+      if (has_next) {
+        if (it > 0) LA_CUDA_TRY(cudaStreamWaitEvent(sp, side->e_bulk, 0));  // bulk(i-1) updated columns >= c1
+        LA_TRY(head_and_update(c1, c2, sp));
+        LA_TRY(launch_panel(c1, nb2, sp));
+      }
+      // ---- bulk ----
+      LA_CUDA_TRY(cudaStreamWaitEvent(st, side->e_head, 0));
+      LA_TRY(launch_swap(0, j0, j0, j0, parity, st));
+      LA_TRY(head_and_update(c2, N, st));
+      LA_CUDA_TRY(cudaEventRecord(side->e_bulk, st));
+    }
     LA_CUDA_TRY(cudaEventRecord(side->e_head, sp));
     LA_CUDA_TRY(cudaStreamWaitEvent(st, side->e_head, 0));
   }
