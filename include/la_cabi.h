@@ -133,6 +133,16 @@ LA_API int la_lu_solve_f32_dev(const float* LU, size_t n, const uint64_t* piv_de
 /* `Matrix::id` (src/matrix/mod.rs:416-426), the RHS of `inverse` (mod.rs:1034-1037) */
 LA_API int la_identity_f64(la_buf* dst, size_t n);
 LA_API int la_identity_f32(la_buf* dst, size_t n);
+/* `Matrix::t` (src/matrix/mod.rs:653-669): dst (cols x rows) = transpose of src (rows x cols), both device-resident, so
+ * that chains like pinverse's `(r.t() * &r).inverse() * &a.t()` (mod.rs:1049-1057) never leave HBM.  No aliasing. */
+LA_API int la_transpose_f64(const la_buf* src, la_buf* dst, size_t rows, size_t cols);
+LA_API int la_transpose_f32(const la_buf* src, la_buf* dst, size_t rows, size_t cols);
+/* `Matrix::permute_rows` (src/matrix/mod.rs:757-759): dst row i = src row idx[i], i < out_rows; idx is HOST memory
+ * (a `&[usize]`), every entry < rows or LA_ERR_INVALID (the reference panics on the out-of-range index). */
+LA_API int la_permute_rows_f64(const la_buf* src, size_t rows, size_t cols, const uint64_t* idx, size_t out_rows,
+                               la_buf* dst);
+LA_API int la_permute_rows_f32(const la_buf* src, size_t rows, size_t cols, const uint64_t* idx, size_t out_rows,
+                               la_buf* dst);
 /* Counter-based synthetic inputs, uniform [0,1) like `Matrix::random` (src/matrix/mod.rs:842-851):
  * element i of dst gets hash(seed, first_idx + i).  Device pointers; asynchronous on `cuda_stream`. */
 LA_API int la_fill_hash_f64_dev(double* dst, size_t count, uint64_t seed, uint64_t first_idx, void* cuda_stream);

@@ -273,6 +273,41 @@ int lu_solve_host(const T* LU, size_t m, size_t n, const uint64_t* piv, const T*
 
 }  // namespace
 
+namespace {
+template <typename T>
+int transpose_buf(const la_buf* src, la_buf* dst, size_t rows, size_t cols) {
+  size_t bytes;
+  LA_REQUIRE(src && dst && rows > 0 && cols > 0, "la_transpose: bad arguments");
+  LA_REQUIRE(!mul_overflows(rows, cols, sizeof(T), &bytes) && src->bytes >= bytes && dst->bytes >= bytes,
+             "la_transpose: buffer too small for %zu x %zu", rows, cols);
+  LA_REQUIRE(src->device == dst->device, "la_transpose: buffers live on different devices");
+  DeviceGuard g;
+  LA_TRY(g.enter(src->device));
+  return transpose_dev<T>((const T*)src->ptr, (T*)dst->ptr, rows, cols, cudaStreamPerThread);
+}
+template <typename T>
+int permute_rows_buf(const la_buf* src, size_t rows, size_t cols, const uint64_t* idx, size_t out_rows, la_buf* dst) {
+  size_t sbytes, dbytes;
+  LA_REQUIRE(src && dst && idx && rows > 0 && cols > 0 && out_rows > 0, "la_permute_rows: bad arguments");
+  LA_REQUIRE(!mul_overflows(rows, cols, sizeof(T), &sbytes) && src->bytes >= sbytes &&
+                 !mul_overflows(out_rows, cols, sizeof(T), &dbytes) && dst->bytes >= dbytes,
+             "la_permute_rows: buffer too small");
+  LA_REQUIRE(src->device == dst->device && src->ptr != dst->ptr, "la_permute_rows: buffers must be distinct, same device");
+  for (size_t i = 0; i < out_rows; ++i)
+    LA_REQUIRE(idx[i] < rows, "la_permute_rows: row index %llu out of range (rows = %zu)", (unsigned long long)idx[i], rows);
+  DeviceGuard g;
+  LA_TRY(g.enter(src->device));
+  void* meta;
+  LA_TRY(scratch_get(src->device, 3, sizeof(uint64_t) * out_rows + 64, &meta));
+  cudaStream_t st = cudaStreamPerThread;
+  LA_CUDA_TRY(cudaMemcpyAsync(meta, idx, sizeof(uint64_t) * out_rows, cudaMemcpyHostToDevice, st));
+  LA_TRY(permute_rows_dev<T>((const T*)src->ptr, (T*)dst->ptr, (const uint64_t*)meta, out_rows, cols, st));
+  LA_CUDA_TRY(cudaStreamSynchronize(st));  // `idx` is the caller's (pageable) memory
+  return LA_OK;
+}
+}  // namespace
+
+
 extern "C" {
 
 int la_version(void) { return 1; }
@@ -472,6 +507,18 @@ int la_identity_f32(la_buf* dst, size_t n) {
   DeviceGuard g;
   LA_TRY(g.enter(dst->device));
   return identity_dev<float>((float*)dst->ptr, n, cudaStreamPerThread);
+}
+int la_transpose_f64(const la_buf* src, la_buf* dst, size_t rows, size_t cols) {
+  return transpose_buf<double>(src, dst, rows, cols);
+}
+int la_transpose_f32(const la_buf* src, la_buf* dst, size_t rows, size_t cols) {
+  return transpose_buf<float>(src, dst, rows, cols);
+}
+int la_permute_rows_f64(const la_buf* src, size_t rows, size_t cols, const uint64_t* idx, size_t out_rows, la_buf* dst) {
+  return permute_rows_buf<double>(src, rows, cols, idx, out_rows, dst);
+}
+int la_permute_rows_f32(const la_buf* src, size_t rows, size_t cols, const uint64_t* idx, size_t out_rows, la_buf* dst) {
+  return permute_rows_buf<float>(src, rows, cols, idx, out_rows, dst);
 }
 int la_fill_hash_f64_dev(double* dst, size_t count, uint64_t seed, uint64_t first_idx, void* stream) {
   return fill_hash_dev<double>(dst, count, seed, first_idx, resolve_stream(stream));

@@ -215,4 +215,62 @@ int identity_dev(T* dst, size_t n, cudaStream_t st) {
 template int identity_dev<double>(double*, size_t, cudaStream_t);
 template int identity_dev<float>(float*, size_t, cudaStream_t);
 
+// dst[c][r] = src[r][c] through 32 x 33 shared-memory tiles: reads and writes are both full 128/256-byte row segments
+// (`Matrix::t`, src/matrix/mod.rs:653-669, walks the source with stride cols).
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ src, T* __restrict__ dst, size_t rows, size_t cols) {
+  __shared__ T tile[32][33];
+  const size_t r0 = (size_t)blockIdx.y * 32, c0 = (size_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const size_t r = r0 + ty + i, c = c0 + tx;
+    if (r < rows && c < cols) tile[ty + i][tx] = src[r * cols + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const size_t c = c0 + ty + i, r = r0 + tx;
+    if (c < cols && r < rows) dst[c * rows + r] = tile[tx][ty + i];
+  }
+}
+template <typename T>
+int transpose_dev(const T* src, T* dst, size_t rows, size_t cols, cudaStream_t st) {
+  LA_REQUIRE(src && dst && rows > 0 && cols > 0, "la_transpose: null pointer or zero dimension");
+  LA_REQUIRE((const void*)src != (const void*)dst, "la_transpose: source and destination must not alias");
+  const size_t gx = (cols + 31) / 32, gy = (rows + 31) / 32;
+  LA_REQUIRE(gy <= 65535 && gx < (1u << 31), "la_transpose: dimension too large");
+  transpose_kernel<T><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, st>>>(src, dst, rows, cols);
+  LA_CUDA_TRY(cudaGetLastError());
+  return LA_OK;
+}
+template int transpose_dev<double>(const double*, double*, size_t, size_t, cudaStream_t);
+template int transpose_dev<float>(const float*, float*, size_t, size_t, cudaStream_t);
+
+// dst row i = src row idx[i] (`Matrix::permute_rows`, src/matrix/mod.rs:757-759 -> sub_matrix(rows, ..)); one warp per
+// destination row segment, coalesced along the row.
+template <typename T>
+__global__ void __launch_bounds__(256) permute_rows_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                           const uint64_t* __restrict__ idx, size_t out_rows, size_t cols) {
+  const size_t total = out_rows * cols;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = e / cols, j = e - i * cols;
+    dst[e] = src[(size_t)idx[i] * cols + j];
+  }
+}
+template <typename T>
+int permute_rows_dev(const T* src, T* dst, const uint64_t* idx_dev, size_t out_rows, size_t cols, cudaStream_t st) {
+  const DeviceCtx* ctx;
+  LA_TRY(current_device_ctx(&ctx));
+  LA_REQUIRE(src && dst && idx_dev && out_rows > 0 && cols > 0, "la_permute_rows: null pointer or zero dimension");
+  size_t blocks = (out_rows * cols + 255) / 256;
+  const size_t cap = (size_t)ctx->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  permute_rows_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(src, dst, idx_dev, out_rows, cols);
+  LA_CUDA_TRY(cudaGetLastError());
+  return LA_OK;
+}
+template int permute_rows_dev<double>(const double*, double*, const uint64_t*, size_t, size_t, cudaStream_t);
+template int permute_rows_dev<float>(const float*, float*, const uint64_t*, size_t, size_t, cudaStream_t);
+
 }  // namespace la

@@ -19,7 +19,7 @@ import numpy as np
 from . import _cabi
 from ._cabi import LaError, lib, check  # noqa: F401
 
-__all__ = ["Matrix", "LUDecomposition", "m", "Panic", "LaError", "APPROX_EPS"]
+__all__ = ["Matrix", "DeviceMatrix", "LUDecomposition", "m", "Panic", "LaError", "APPROX_EPS"]
 
 APPROX_EPS = 1e-6  # src/approxeq.rs:20,36
 
@@ -272,6 +272,88 @@ class LUDecomposition:
         x = np.empty(self._m * nx, dtype=self._dtype)
         xbuf.download(x)
         return Matrix(self._m, x)
+
+
+class DeviceMatrix:
+    """A `Matrix<T>` whose `data` lives in HBM (la_buf): SURVEY.md section 8(f) rank 1 -- chains such as pinverse's
+    `(r.t() * &r).inverse() * &a.t()` (src/matrix/mod.rs:1049-1057) stay on the device between operations.
+
+    Mirrors the subset of the Matrix API that has a device kernel: `t` (mod.rs:653-669), operator `*` (:957-998), `id`
+    (:416-426), `permute_rows` (:757-759), `inverse` (:1034-1037, via LUDecomposition + solve with the identity); same
+    panics, same `None` on singularity."""
+
+    __slots__ = ("no_rows", "no_cols", "dtype", "buf")
+
+    def __init__(self, no_rows, no_cols, dtype, buf):
+        self.no_rows, self.no_cols, self.dtype, self.buf = int(no_rows), int(no_cols), np.dtype(dtype), buf
+
+    @staticmethod
+    def from_matrix(a, device=0):
+        buf = _DeviceBuf(a.data.nbytes, device)
+        buf.upload(a.data)
+        return DeviceMatrix(a.rows(), a.cols(), a.data.dtype, buf)
+
+    @staticmethod
+    def id(n, dtype=np.float64, device=0):
+        dtype = np.dtype(dtype)
+        buf = _DeviceBuf(n * n * dtype.itemsize, device)
+        check(getattr(lib(), f"la_identity_{_suffix(dtype)}")(buf.handle, n))
+        return DeviceMatrix(n, n, dtype, buf)
+
+    def to_matrix(self):
+        h = np.empty(self.no_rows * self.no_cols, dtype=self.dtype)
+        self.buf.download(h)
+        return Matrix(self.no_rows, h)
+
+    def rows(self):
+        return self.no_rows
+
+    def cols(self):
+        return self.no_cols
+
+    def _like(self, rows, cols):
+        return DeviceMatrix(rows, cols, self.dtype, _DeviceBuf(rows * cols * self.dtype.itemsize))
+
+    def t(self):
+        out = self._like(self.no_cols, self.no_rows)
+        check(getattr(lib(), f"la_transpose_{_suffix(self.dtype)}")(self.buf.handle, out.buf.handle, self.no_rows,
+                                                                    self.no_cols))
+        return out
+
+    def permute_rows(self, rows):
+        idx = np.ascontiguousarray(rows, dtype=np.uint64)
+        _assert(idx.size > 0 and int(idx.max()) < self.no_rows, "row index out of bounds")  # sub_matrix panics
+        out = self._like(idx.size, self.no_cols)
+        check(getattr(lib(), f"la_permute_rows_{_suffix(self.dtype)}")(self.buf.handle, self.no_rows, self.no_cols,
+                                                                       _ptr(idx), idx.size, out.buf.handle))
+        return out
+
+    def __mul__(self, other):
+        _assert(isinstance(other, DeviceMatrix), "DeviceMatrix * DeviceMatrix")
+        _assert(self.no_cols == other.no_rows, "self.cols() == m.no_rows")  # mod.rs:961
+        _assert(self.dtype == other.dtype, "same element type")
+        out = self._like(self.no_rows, other.no_cols)
+        check(getattr(lib(), f"la_gemm_{_suffix(self.dtype)}")(self.buf.handle, other.buf.handle, out.buf.handle,
+                                                               self.no_rows, self.no_cols, other.no_cols))
+        return out
+
+    def inverse(self):
+        """mod.rs:1034-1037: `LUDecomposition::new(self).solve(&Matrix::id(...))`; None when singular."""
+        _assert(self.no_rows == self.no_cols, "self.no_rows == self.cols()")
+        n, suf = self.no_rows, _suffix(self.dtype)
+        lu = self._like(n, n)
+        check(lib().la_buf_copy(lu.buf.handle, self.buf.handle, n * n * self.dtype.itemsize))  # the factorisation's copy
+        piv = np.empty(n, dtype=np.uint64)
+        sign = ctypes.c_int(1)
+        check(getattr(lib(), f"la_lu_factor_{suf}")(lu.buf.handle, n, n, _ptr(piv), ctypes.byref(sign)))
+        ok = ctypes.c_int(0)
+        check(getattr(lib(), f"la_lu_is_nonsingular_{suf}")(lu.buf.handle, n, ctypes.byref(ok)))
+        if not ok.value:
+            return None
+        eye = DeviceMatrix.id(n, self.dtype)
+        out = self._like(n, n)
+        check(getattr(lib(), f"la_lu_solve_{suf}")(lu.buf.handle, n, n, _ptr(piv), eye.buf.handle, n, out.buf.handle))
+        return out
 
 
 def m(spec, dtype=None):

@@ -65,6 +65,10 @@ SIGNATURES = {
     "la_lu_solve_f32_dev": ([_p, _sz, _p, _p, _sz, _p, _p], _i),
     "la_identity_f64": ([_p, _sz], _i),
     "la_identity_f32": ([_p, _sz], _i),
+    "la_transpose_f64": ([_p, _p, _sz, _sz], _i),
+    "la_transpose_f32": ([_p, _p, _sz, _sz], _i),
+    "la_permute_rows_f64": ([_p, _sz, _sz, _p, _sz, _p], _i),
+    "la_permute_rows_f32": ([_p, _sz, _sz, _p, _sz, _p], _i),
     "la_fill_hash_f64_dev": ([_p, _sz, _u64, _u64, _p], _i),
     "la_fill_hash_f32_dev": ([_p, _sz, _u64, _u64, _p], _i),
     "la_debug_set_gemm_path": ([_i], _i),

@@ -76,6 +76,12 @@ extern "C" {
 
     pub fn la_identity_f64(dst: *mut la_buf, n: usize) -> c_int;
     pub fn la_identity_f32(dst: *mut la_buf, n: usize) -> c_int;
+    pub fn la_transpose_f64(src: *const la_buf, dst: *mut la_buf, rows: usize, cols: usize) -> c_int;
+    pub fn la_transpose_f32(src: *const la_buf, dst: *mut la_buf, rows: usize, cols: usize) -> c_int;
+    pub fn la_permute_rows_f64(src: *const la_buf, rows: usize, cols: usize, idx: *const u64, out_rows: usize,
+                               dst: *mut la_buf) -> c_int;
+    pub fn la_permute_rows_f32(src: *const la_buf, rows: usize, cols: usize, idx: *const u64, out_rows: usize,
+                               dst: *mut la_buf) -> c_int;
     pub fn la_fill_hash_f64_dev(dst: *mut f64, count: usize, seed: u64, first_idx: u64, cuda_stream: *mut c_void) -> c_int;
     pub fn la_fill_hash_f32_dev(dst: *mut f32, count: usize, seed: u64, first_idx: u64, cuda_stream: *mut c_void) -> c_int;
     pub fn la_debug_set_gemm_path(path: c_int) -> c_int;
