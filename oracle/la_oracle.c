@@ -350,3 +350,72 @@ ORACLE_API double oracle_lu_backward_error_f32(const float* a, const float* lu, 
   }
   return sqrt(num / den);
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Cholesky: CholeskyDecomposition::new  src/decomp/cholesky.rs:56-110,
+ * solve :116-144.  Returns 1 for Some(..), 0 for None (not square is the caller's check, :57-59; not symmetric :91-93,
+ * exact `!=` so a NaN pair is "not symmetric"; not positive definite :99-102, `d <= 0`, so a NaN d is NOT rejected).
+ *   canon : the reference's row-by-row loop nest, including the point at which it gives up.
+ *   fast  : column by column -- every element's sum keeps its i-ascending order and separate roundings, rows of a
+ *           column are independent (OpenMP); the symmetry test is hoisted (it reads only the input).  Same Some/None
+ *           and, for Some, bit-identical L (tests/test_oracle_cholesky.py).
+ * --------------------------------------------------------------------------------------------------------------- */
+#define DEFINE_CHOL(T, SUF, SQRT)                                                                           \
+  ORACLE_API int oracle_chol_canon_##SUF(const T* a, size_t n, T* l) {                                      \
+    for (size_t j = 0; j < n; ++j) {                                                                        \
+      T d = (T)0;                                                                                           \
+      for (size_t k = 0; k < j; ++k) {                                                                      \
+        T s = (T)0;                                                                                         \
+        for (size_t i = 0; i < k; ++i) s = s + l[k * n + i] * l[j * n + i]; /* cholesky.rs:80-82 */          \
+        s = (a[j * n + k] - s) / l[k * n + k];                              /* :85 */                        \
+        l[j * n + k] = s;                                                                                   \
+        d = d + s * s;                                                      /* :89 */                        \
+        if (a[k * n + j] != a[j * n + k]) return 0;                         /* :92-94 */                     \
+      }                                                                                                     \
+      d = a[j * n + j] - d;                                                 /* :99 */                        \
+      if (d <= (T)0) return 0;                                              /* :100-103 */                   \
+      l[j * n + j] = SQRT(d);                                                                               \
+      for (size_t k = j + 1; k < n; ++k) l[j * n + k] = (T)0;               /* :107-109 */                   \
+    }                                                                                                       \
+    return 1;                                                                                               \
+  }                                                                                                         \
+  ORACLE_API int oracle_chol_fast_##SUF(const T* a, size_t n, T* l) {                                       \
+    int sym = 1;                                                                                            \
+    _Pragma("omp parallel for schedule(dynamic, 16) reduction(&& : sym)")                                   \
+    for (size_t j = 0; j < n; ++j)                                                                          \
+      for (size_t k = 0; k < j; ++k)                                                                        \
+        if (a[k * n + j] != a[j * n + k]) sym = 0;                                                          \
+    /* The reference meets `d <= 0` of row j before it looks at the symmetry of rows > j, but both end in None. */ \
+    for (size_t k = 0; k < n; ++k) {                                                                        \
+      T d = (T)0;                                                                                           \
+      for (size_t i = 0; i < k; ++i) d = d + l[k * n + i] * l[k * n + i];                                   \
+      d = a[k * n + k] - d;                                                                                 \
+      if (d <= (T)0) return 0;                                                                              \
+      l[k * n + k] = SQRT(d);                                                                               \
+      for (size_t c = k + 1; c < n; ++c) l[k * n + c] = (T)0;                                               \
+      const T lkk = l[k * n + k];                                                                           \
+      _Pragma("omp parallel for schedule(static)")                                                          \
+      for (size_t j = k + 1; j < n; ++j) {                                                                  \
+        T s = (T)0;                                                                                         \
+        for (size_t i = 0; i < k; ++i) s = s + l[k * n + i] * l[j * n + i];                                 \
+        l[j * n + k] = (a[j * n + k] - s) / lkk;                                                            \
+      }                                                                                                     \
+    }                                                                                                       \
+    return sym;                                                                                             \
+  }                                                                                                         \
+  /* solve :116-144: forward with L (divide by the diagonal), backward with L' */                           \
+  ORACLE_API void oracle_chol_solve_##SUF(const T* l, size_t n, const T* b, size_t nx, T* x) {              \
+    memcpy(x, b, n * nx * sizeof(T));                                                                       \
+    for (size_t k = 0; k < n; ++k)                                                                          \
+      for (size_t j = 0; j < nx; ++j) {                                                                     \
+        for (size_t i = 0; i < k; ++i) x[k * nx + j] = x[k * nx + j] - x[i * nx + j] * l[k * n + i];        \
+        x[k * nx + j] = x[k * nx + j] / l[k * n + k];                                                       \
+      }                                                                                                     \
+    for (size_t k = n; k-- > 0;)                                                                            \
+      for (size_t j = 0; j < nx; ++j) {                                                                     \
+        for (size_t i = k + 1; i < n; ++i) x[k * nx + j] = x[k * nx + j] - x[i * nx + j] * l[i * n + k];    \
+        x[k * nx + j] = x[k * nx + j] / l[k * n + k];                                                       \
+      }                                                                                                     \
+  }
+DEFINE_CHOL(double, f64, sqrt)
+DEFINE_CHOL(float, f32, sqrtf)

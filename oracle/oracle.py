@@ -59,6 +59,10 @@ def _declare(L):
         getattr(L, f"oracle_lu_get_l_{suf}").argtypes = [_p, _sz, _sz, _p]
         getattr(L, f"oracle_lu_get_u_{suf}").argtypes = [_p, _sz, _sz, _p]
         getattr(L, f"oracle_identity_{suf}").argtypes = [_p, _sz]
+        for form in ("canon", "fast"):
+            f = getattr(L, f"oracle_chol_{form}_{suf}")
+            f.argtypes, f.restype = [_p, _sz, _p], _int
+        getattr(L, f"oracle_chol_solve_{suf}").argtypes = [_p, _sz, _p, _sz, _p]
         f = getattr(L, f"oracle_lu_backward_error_{suf}")
         f.argtypes, f.restype = [_p, _p, _sz, _sz, _p], ctypes.c_double
     L.oracle_gemm_canon_i64.argtypes = [_p, _p, _p, _sz, _sz, _sz]
@@ -179,3 +183,24 @@ def lu_backward_error(a, packed, piv):
     m, n = a.shape
     return getattr(lib(), f"oracle_lu_backward_error_{_suf(a.dtype)}")(
         _ptr(a), _ptr(packed), m, n, _ptr(np.ascontiguousarray(piv, dtype=np.uint64)))
+
+
+def chol(a, form="fast"):
+    """CholeskyDecomposition::new (src/decomp/cholesky.rs:56-110): L (lower, zeros above) or None."""
+    a = np.ascontiguousarray(a)
+    if a.shape[0] != a.shape[1]:
+        return None  # cholesky.rs:57-59
+    n = a.shape[0]
+    l = np.zeros((n, n), dtype=a.dtype)
+    ok = getattr(lib(), f"oracle_chol_{'canon' if form == 'canon' else 'fast'}_{_suf(a.dtype)}")(_ptr(a), n, _ptr(l))
+    return l if ok else None
+
+
+def chol_solve(l, b):
+    """CholeskyDecomposition::solve (cholesky.rs:116-144)."""
+    l = np.ascontiguousarray(l)
+    b = np.ascontiguousarray(b)
+    assert l.shape[0] == b.shape[0]
+    x = np.empty_like(b)
+    getattr(lib(), f"oracle_chol_solve_{_suf(l.dtype)}")(_ptr(l), l.shape[0], _ptr(b), b.shape[1], _ptr(x))
+    return x
