@@ -356,6 +356,45 @@ def main():
               "solve_ms": so_t, "solve_gbs": (8.0 * ln * ln * 2) / (so_t * 1e-3) / 1e9,
               "solve_residual": res}
 
+    # ---- Cholesky n=16384 + solve with 16 RHS (widening step), 1 GPU only ----
+    chol = None
+    if n_gpus == 1 and not args.skip_lu:
+        cn, cnx = 16384, 16
+        A0 = LU = R = A = B = C = None  # release the earlier legs' buffers
+        torch.cuda.empty_cache()
+        G0 = torch.empty((cn, cn), dtype=f64, device=dev)
+        chk(L.la_fill_hash_f64_dev(G0.data_ptr(), G0.numel(), 1, 0, sp))
+        S0 = G0 @ G0.T  # input generation only (torch): A = G G' + n I, symmetrised exactly
+        S0 = (S0 + S0.T) * 0.5
+        S0.diagonal().add_(float(cn))
+        del G0
+        CL = torch.empty_like(S0)
+        CBm = torch.empty((cn, cnx), dtype=f64, device=dev)
+        CX = torch.empty((cn, cnx), dtype=f64, device=dev)
+        cflags = torch.zeros((2,), dtype=torch.int32, device=dev)
+        chk(L.la_fill_hash_f64_dev(CBm.data_ptr(), CBm.numel(), 3, 0, sp))
+        c_ms, cs_ms = [], []
+        for it in range(1 + 2):
+            CL.copy_(S0)
+            c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            c0.record(stream)
+            chk(L.la_chol_factor_f64_dev(CL.data_ptr(), cn, cflags.data_ptr(), sp))
+            c1.record(stream)
+            chk(L.la_chol_solve_f64_dev(CL.data_ptr(), cn, CBm.data_ptr(), cnx, CX.data_ptr(), sp))
+            c2.record(stream)
+            torch.cuda.synchronize()
+            if it > 0:
+                c_ms.append(c0.elapsed_time(c1))
+                cs_ms.append(c1.elapsed_time(c2))
+        c_t = sum(c_ms) / len(c_ms)
+        fl = cflags.cpu().tolist()
+        chol = {"workload": "f64 Cholesky n=16384 (A = G G' + n I) + solve nx=16", "ok": int(fl[0] == 0 and fl[1] == 0),
+                "chol_ms": c_t, "chol_tflops": cn ** 3 / 3.0 / (c_t * 1e-3) / 1e12, "flops_formula": "1/3 n^3",
+                "solve_ms": sum(cs_ms) / len(cs_ms),
+                "backward_error": float((CL @ CL.T - S0).norm() / S0.norm()),
+                "solve_residual": float((S0 @ CX - CBm).norm() / (S0.norm() * CX.norm()))}
+        del S0, CL, CBm, CX
+
     # ---- f32 GEMM 65536x1024 x 1024x16384 (configs[4]) on the tcgen05 kind::tf32 kernel, 1 GPU only ----
     f32 = None
     if not args.skip_f32:
@@ -434,6 +473,8 @@ def main():
             roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
         except Exception:
             pass
+    if chol:
+        chol["frac_of_fp64_peak"] = chol["chol_tflops"] / peak_tf
     if lu:
         lu["frac_of_fp64_peak"] = lu["lu_tflops"] / peak_tf
         lu["frac_of_nominal_40"] = lu["lu_tflops"] / NOMINAL_FP64_TFLOPS
@@ -467,6 +508,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "lu": lu,
+        "cholesky": chol,
         "f32": f32,
     }
     print(json.dumps(line))

@@ -129,6 +129,27 @@ LA_API int la_lu_solve_f64_dev(const double* LU, size_t n, const uint64_t* piv_d
 LA_API int la_lu_solve_f32_dev(const float* LU, size_t n, const uint64_t* piv_dev, const float* B, size_t nx,
                                float* X, void* cuda_stream);
 
+/* ---- Cholesky (widening step) ------------------------------------------------ */
+/* `CholeskyDecomposition::new` (src/decomp/cholesky.rs:56-110), in place on a device buffer holding the n x n matrix:
+ * on return *ok_out = 1 and the buffer holds L (lower triangle, zeros above), or *ok_out = 0 -- the reference's `None`:
+ * not symmetric (exact `!=` on every pair, :91-93) or not positive definite (`a[j][j] - sum <= 0`, :99-102); the buffer
+ * content is then unspecified.  "Not square" (:57-59) is the caller's check, as are all shape panics. */
+LA_API int la_chol_factor_f64(la_buf* A_inout, size_t n, int* ok_out);
+LA_API int la_chol_factor_f32(la_buf* A_inout, size_t n, int* ok_out);
+LA_API int la_chol_factor_f64_host(const double* A, double* L_out, size_t n, int* ok_out);
+LA_API int la_chol_factor_f32_host(const float* A, float* L_out, size_t n, int* ok_out);
+/* Device-pointer forms, asynchronous on `cuda_stream` (NULL = the calling thread's stream).  flags_dev points to two
+ * device ints that are cleared and then set: [0] != 0 = not symmetric, [1] != 0 = not positive definite. */
+LA_API int la_chol_factor_f64_dev(double* A_inout, size_t n, int* flags_dev, void* cuda_stream);
+LA_API int la_chol_factor_f32_dev(float* A_inout, size_t n, int* flags_dev, void* cuda_stream);
+LA_API int la_chol_solve_f64_dev(const double* L, size_t n, const double* B, size_t nx, double* X, void* cuda_stream);
+LA_API int la_chol_solve_f32_dev(const float* L, size_t n, const float* B, size_t nx, float* X, void* cuda_stream);
+/* `CholeskyDecomposition::solve` (cholesky.rs:116-144): X (n x nx) = A^-1 B from L; B and X distinct buffers. */
+LA_API int la_chol_solve_f64(const la_buf* L, size_t n, const la_buf* B, size_t nx, la_buf* X);
+LA_API int la_chol_solve_f32(const la_buf* L, size_t n, const la_buf* B, size_t nx, la_buf* X);
+LA_API int la_chol_solve_f64_host(const double* L, size_t n, const double* B, size_t nx, double* X);
+LA_API int la_chol_solve_f32_host(const float* L, size_t n, const float* B, size_t nx, float* X);
+
 /* ---- aux ------------------------------------------------------------------------------------------ */
 /* `Matrix::id` (src/matrix/mod.rs:416-426), the RHS of `inverse` (mod.rs:1034-1037) */
 LA_API int la_identity_f64(la_buf* dst, size_t n);

@@ -308,6 +308,80 @@ int permute_rows_buf(const la_buf* src, size_t rows, size_t cols, const uint64_t
 }  // namespace
 
 
+namespace {
+template <typename T>
+int chol_factor_buf(la_buf* A, size_t n, int* ok_out) {
+  size_t bytes;
+  LA_REQUIRE(A && ok_out && n > 0, "la_chol_factor: bad arguments");
+  LA_REQUIRE(!mul_overflows(n, n, sizeof(T), &bytes) && A->bytes >= bytes, "la_chol_factor: buffer too small");
+  DeviceGuard g;
+  LA_TRY(g.enter(A->device));
+  void* meta;
+  LA_TRY(scratch_get(A->device, 3, 64, &meta));
+  cudaStream_t st = cudaStreamPerThread;
+  LA_TRY(chol_factor_dev<T>((T*)A->ptr, n, (int*)meta, st));
+  int flags[2] = {0, 0};
+  LA_CUDA_TRY(cudaMemcpyAsync(flags, meta, sizeof(flags), cudaMemcpyDeviceToHost, st));
+  LA_CUDA_TRY(cudaStreamSynchronize(st));
+  *ok_out = (flags[0] == 0 && flags[1] == 0) ? 1 : 0;
+  return LA_OK;
+}
+template <typename T>
+int chol_factor_host(const T* A, T* L_out, size_t n, int* ok_out) {
+  size_t bytes;
+  LA_REQUIRE(A && L_out && ok_out && n > 0, "la_chol_factor_host: bad arguments");
+  LA_REQUIRE(!mul_overflows(n, n, sizeof(T), &bytes), "la_chol_factor_host: size overflow");
+  const DeviceCtx* ctx;
+  LA_TRY(current_device_ctx(&ctx));
+  void *dA, *meta;
+  LA_TRY(scratch_get(ctx->device, 0, bytes, &dA));
+  LA_TRY(scratch_get(ctx->device, 3, 64, &meta));
+  cudaStream_t st = cudaStreamPerThread;
+  LA_CUDA_TRY(cudaMemcpyAsync(dA, A, bytes, cudaMemcpyHostToDevice, st));
+  LA_TRY(chol_factor_dev<T>((T*)dA, n, (int*)meta, st));
+  int flags[2] = {0, 0};
+  LA_CUDA_TRY(cudaMemcpyAsync(flags, meta, sizeof(flags), cudaMemcpyDeviceToHost, st));
+  LA_CUDA_TRY(cudaMemcpyAsync(L_out, dA, bytes, cudaMemcpyDeviceToHost, st));
+  LA_CUDA_TRY(cudaStreamSynchronize(st));
+  *ok_out = (flags[0] == 0 && flags[1] == 0) ? 1 : 0;
+  return LA_OK;
+}
+template <typename T>
+int chol_solve_buf(const la_buf* L, size_t n, const la_buf* B, size_t nx, la_buf* X) {
+  size_t bl, bx;
+  LA_REQUIRE(L && B && X && n > 0 && nx > 0, "la_chol_solve: bad arguments");
+  LA_REQUIRE(!mul_overflows(n, n, sizeof(T), &bl) && L->bytes >= bl && !mul_overflows(n, nx, sizeof(T), &bx) &&
+                 B->bytes >= bx && X->bytes >= bx,
+             "la_chol_solve: buffer too small");
+  LA_REQUIRE(L->device == B->device && L->device == X->device, "la_chol_solve: buffers live on different devices");
+  DeviceGuard g;
+  LA_TRY(g.enter(L->device));
+  cudaStream_t st = cudaStreamPerThread;
+  LA_TRY(chol_solve_dev<T>((const T*)L->ptr, n, (const T*)B->ptr, nx, (T*)X->ptr, st));
+  LA_CUDA_TRY(cudaStreamSynchronize(st));
+  return LA_OK;
+}
+template <typename T>
+int chol_solve_host(const T* L, size_t n, const T* B, size_t nx, T* X) {
+  size_t bl, bx;
+  LA_REQUIRE(L && B && X && n > 0 && nx > 0, "la_chol_solve_host: bad arguments");
+  LA_REQUIRE(!mul_overflows(n, n, sizeof(T), &bl) && !mul_overflows(n, nx, sizeof(T), &bx), "la_chol_solve_host: overflow");
+  const DeviceCtx* ctx;
+  LA_TRY(current_device_ctx(&ctx));
+  void *dL, *dB, *dX;
+  LA_TRY(scratch_get(ctx->device, 0, bl, &dL));
+  LA_TRY(scratch_get(ctx->device, 1, bx, &dB));
+  LA_TRY(scratch_get(ctx->device, 2, bx, &dX));
+  cudaStream_t st = cudaStreamPerThread;
+  LA_CUDA_TRY(cudaMemcpyAsync(dL, L, bl, cudaMemcpyHostToDevice, st));
+  LA_CUDA_TRY(cudaMemcpyAsync(dB, B, bx, cudaMemcpyHostToDevice, st));
+  LA_TRY(chol_solve_dev<T>((const T*)dL, n, (const T*)dB, nx, (T*)dX, st));
+  LA_CUDA_TRY(cudaMemcpyAsync(X, dX, bx, cudaMemcpyDeviceToHost, st));
+  LA_CUDA_TRY(cudaStreamSynchronize(st));
+  return LA_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int la_version(void) { return 1; }
@@ -519,6 +593,38 @@ int la_permute_rows_f64(const la_buf* src, size_t rows, size_t cols, const uint6
 }
 int la_permute_rows_f32(const la_buf* src, size_t rows, size_t cols, const uint64_t* idx, size_t out_rows, la_buf* dst) {
   return permute_rows_buf<float>(src, rows, cols, idx, out_rows, dst);
+}
+int la_chol_factor_f64(la_buf* A, size_t n, int* ok_out) { return chol_factor_buf<double>(A, n, ok_out); }
+int la_chol_factor_f32(la_buf* A, size_t n, int* ok_out) { return chol_factor_buf<float>(A, n, ok_out); }
+int la_chol_factor_f64_host(const double* A, double* L_out, size_t n, int* ok_out) {
+  return chol_factor_host<double>(A, L_out, n, ok_out);
+}
+int la_chol_factor_f32_host(const float* A, float* L_out, size_t n, int* ok_out) {
+  return chol_factor_host<float>(A, L_out, n, ok_out);
+}
+int la_chol_factor_f64_dev(double* A, size_t n, int* flags_dev, void* stream) {
+  return chol_factor_dev<double>(A, n, flags_dev, resolve_stream(stream));
+}
+int la_chol_factor_f32_dev(float* A, size_t n, int* flags_dev, void* stream) {
+  return chol_factor_dev<float>(A, n, flags_dev, resolve_stream(stream));
+}
+int la_chol_solve_f64_dev(const double* L, size_t n, const double* B, size_t nx, double* X, void* stream) {
+  return chol_solve_dev<double>(L, n, B, nx, X, resolve_stream(stream));
+}
+int la_chol_solve_f32_dev(const float* L, size_t n, const float* B, size_t nx, float* X, void* stream) {
+  return chol_solve_dev<float>(L, n, B, nx, X, resolve_stream(stream));
+}
+int la_chol_solve_f64(const la_buf* L, size_t n, const la_buf* B, size_t nx, la_buf* X) {
+  return chol_solve_buf<double>(L, n, B, nx, X);
+}
+int la_chol_solve_f32(const la_buf* L, size_t n, const la_buf* B, size_t nx, la_buf* X) {
+  return chol_solve_buf<float>(L, n, B, nx, X);
+}
+int la_chol_solve_f64_host(const double* L, size_t n, const double* B, size_t nx, double* X) {
+  return chol_solve_host<double>(L, n, B, nx, X);
+}
+int la_chol_solve_f32_host(const float* L, size_t n, const float* B, size_t nx, float* X) {
+  return chol_solve_host<float>(L, n, B, nx, X);
 }
 int la_fill_hash_f64_dev(double* dst, size_t count, uint64_t seed, uint64_t first_idx, void* stream) {
   return fill_hash_dev<double>(dst, count, seed, first_idx, resolve_stream(stream));

@@ -78,6 +78,10 @@ int lu_det_dev(const T* LU, size_t n, int pospivsign, T* out_host, cudaStream_t 
 template <typename T>
 int identity_dev(T* dst, size_t n, cudaStream_t st);
 template <typename T>
+int chol_factor_dev(T* A, size_t n, int* flags_dev, cudaStream_t st);  // cholesky.cu
+template <typename T>
+int chol_solve_dev(const T* L, size_t n, const T* B, size_t nx, T* X, cudaStream_t st);
+template <typename T>
 int transpose_dev(const T* src, T* dst, size_t rows, size_t cols, cudaStream_t st);
 template <typename T>
 int permute_rows_dev(const T* src, T* dst, const uint64_t* idx_dev, size_t out_rows, size_t cols, cudaStream_t st);

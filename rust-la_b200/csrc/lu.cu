@@ -678,9 +678,13 @@ constexpr int INVL_THREADS = 512;
 // D = diag(U), U = D (I + N), N strictly upper; mirrored (i -> jb-1-i) I + N is a unit lower triangle, so the same code
 // inverts it; inv(U) = inv(I + N) D^-1 is un-mirrored and column-scaled on the way out.
 // Batched: block b of the grid handles the diagonal block at j0 + 128 b (clamped to `total`) and writes W + b * 128 * 128.
-template <typename T, bool UPPER>
+// MODE 2 inverts a lower-triangular NON-unit block (Cholesky's L11): L = D (I + N) with N = D^-1 * strict(L), so
+// inv(L) = inv(I + N) D^-1 -- the same unit-lower inversion on the row-scaled block, columns rescaled on the way out.
+// trans_out writes the transpose of the result (the B operand of `X = A21 * inv(L11)'`).
+template <typename T, int MODE>
 __global__ void __launch_bounds__(INVL_THREADS) lu_invl_kernel(const T* __restrict__ A, size_t ld, int j0, int jb, int total,
-                                                               T* __restrict__ W /* [grid][MAX_NB][MAX_NB] */) {
+                                                               T* __restrict__ W /* [grid][MAX_NB][MAX_NB] */, int trans_out) {
+  constexpr bool UPPER = MODE == 1;
   j0 += blockIdx.x * MAX_NB;
   jb = min(jb, total - j0);
   W += (size_t)blockIdx.x * MAX_NB * MAX_NB;
@@ -700,6 +704,7 @@ __global__ void __launch_bounds__(INVL_THREADS) lu_invl_kernel(const T* __restri
           v = __ldcg(&A[(size_t)(j0 + r) * ld + j0 + c]) / __ldcg(&A[(size_t)(j0 + r) * ld + j0 + r]);
         } else {
           v = __ldcg(&A[(size_t)(j0 + i) * ld + j0 + k]);
+          if (MODE == 2) v = v / __ldcg(&A[(size_t)(j0 + i) * ld + j0 + i]);
         }
       }
       SQ[k][i] = v;  // L^T into the upper triangle
@@ -757,13 +762,13 @@ __global__ void __launch_bounds__(INVL_THREADS) lu_invl_kernel(const T* __restri
   }
   for (int idx = tid; idx < MAX_NB * MAX_NB; idx += INVL_THREADS) {
     const int i = idx / MAX_NB, k = idx - i * MAX_NB;
+    T v = (T)0;
     if (UPPER) {  // W[r][c] = inv(I + N)[r][c] / U[c][c], c >= r
-      T v = (T)0;
       if (k >= i && k < jb) v = SQ[jb - 1 - i][jb - 1 - k] / __ldcg(&A[(size_t)(j0 + k) * ld + j0 + k]);
-      W[idx] = v;
-    } else {
-      W[idx] = (k <= i && i < jb) ? SQ[i][k] : (T)0;
+    } else if (k <= i && i < jb) {
+      v = (MODE == 2) ? ((k == i ? (T)1 : SQ[i][k]) / __ldcg(&A[(size_t)(j0 + k) * ld + j0 + k])) : SQ[i][k];
     }
+    W[trans_out ? k * MAX_NB + i : idx] = v;
   }
 }
 
@@ -1008,7 +1013,7 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
                                    (int)PANEL_SMEM_BUDGET + 2048));
   LA_CUDA_TRY(cudaFuncSetAttribute(lu_swap_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWAP_SMEM));
   LA_CUDA_TRY(cudaFuncSetAttribute(lu_swap_trsm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM));
-  LA_CUDA_TRY(cudaFuncSetAttribute(lu_invl_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, INVL_SMEM));
+  LA_CUDA_TRY(cudaFuncSetAttribute(lu_invl_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, INVL_SMEM));
 
   lu_init_piv_kernel<T><<<(M + 255) / 256, 256, 0, st>>>(piv_dev, M, sign_dev);
   LA_CUDA_TRY(cudaGetLastError());
@@ -1133,7 +1138,7 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
       if (need_w) {
         LA_CUDA_TRY(cudaEventRecord(side->e_panel, sp));
         LA_CUDA_TRY(cudaStreamWaitEvent(sw, side->e_panel, 0));
-        lu_invl_kernel<T, false><<<1, INVL_THREADS, INVL_SMEM, sw>>>(LU, n, j0, jb, j0 + jb, W);
+        lu_invl_kernel<T, 0><<<1, INVL_THREADS, INVL_SMEM, sw>>>(LU, n, j0, jb, j0 + jb, W, 0);
         LA_CUDA_TRY(cudaGetLastError());
         LA_CUDA_TRY(cudaEventRecord(side->e_w, sw));
       }
@@ -1240,16 +1245,32 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
   }
   return LA_OK;
 }
-// Inverses of all 128 x 128 diagonal blocks of a packed LU (order n): WL[b] = inv(L_bb) (unit lower), WU[b] = inv(U_bb).
-// One launch each; used by the many-right-hand-side solve (lu_solve.cu), which then needs GEMMs only.
-int lu_diag_block_inverses(const double* LU, size_t n, double* WL, double* WU, cudaStream_t st) {
-  const int INVL_SMEM = (int)(sizeof(double) * ((size_t)MAX_NB * INVL_LD + 3 * IB * IB));
-  LA_CUDA_TRY(cudaFuncSetAttribute(lu_invl_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, INVL_SMEM));
-  LA_CUDA_TRY(cudaFuncSetAttribute(lu_invl_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, INVL_SMEM));
-  const int G = (int)((n + MAX_NB - 1) / MAX_NB);
-  lu_invl_kernel<double, false><<<G, INVL_THREADS, INVL_SMEM, st>>>(LU, n, 0, MAX_NB, (int)n, WL);
-  lu_invl_kernel<double, true><<<G, INVL_THREADS, INVL_SMEM, st>>>(LU, n, 0, MAX_NB, (int)n, WU);
+// Batched inverses of the 128 x 128 diagonal blocks [first_block, first_block + nblocks) of an order-n triangular factor:
+// mode 0 = unit lower (L of a packed LU), 1 = upper non-unit (U of a packed LU, or L' of a Cholesky factor),
+// 2 = lower non-unit (Cholesky's L).  One launch; W[b] is zero-padded; trans_out stores the transposes.
+template <typename T>
+int tri_block_inverses(const T* M, size_t n, int mode, int first_block, int nblocks, T* W, int trans_out, cudaStream_t st) {
+  const int INVL_SMEM = (int)(sizeof(T) * ((size_t)MAX_NB * INVL_LD + 3 * IB * IB));
+  LA_REQUIRE(mode >= 0 && mode <= 2 && nblocks > 0, "tri_block_inverses: bad arguments");
+  const void* fn = mode == 0 ? (const void*)lu_invl_kernel<T, 0>
+                             : (mode == 1 ? (const void*)lu_invl_kernel<T, 1> : (const void*)lu_invl_kernel<T, 2>);
+  LA_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, INVL_SMEM));
+  const int j0 = first_block * MAX_NB;
+  if (mode == 0) lu_invl_kernel<T, 0><<<nblocks, INVL_THREADS, INVL_SMEM, st>>>(M, n, j0, MAX_NB, (int)n, W, trans_out);
+  if (mode == 1) lu_invl_kernel<T, 1><<<nblocks, INVL_THREADS, INVL_SMEM, st>>>(M, n, j0, MAX_NB, (int)n, W, trans_out);
+  if (mode == 2) lu_invl_kernel<T, 2><<<nblocks, INVL_THREADS, INVL_SMEM, st>>>(M, n, j0, MAX_NB, (int)n, W, trans_out);
   LA_CUDA_TRY(cudaGetLastError());
+  return LA_OK;
+}
+template int tri_block_inverses<double>(const double*, size_t, int, int, int, double*, int, cudaStream_t);
+template int tri_block_inverses<float>(const float*, size_t, int, int, int, float*, int, cudaStream_t);
+
+// WL[b] = inv(L_bb) (unit lower), WU[b] = inv(U_bb) for all diagonal blocks of a packed LU: the many-right-hand-side
+// solve and the sweep kernels (lu_solve.cu) then need products only.
+int lu_diag_block_inverses(const double* LU, size_t n, double* WL, double* WU, cudaStream_t st) {
+  const int G = (int)((n + MAX_NB - 1) / MAX_NB);
+  LA_TRY(tri_block_inverses<double>(LU, n, 0, 0, G, WL, 0, st));
+  LA_TRY(tri_block_inverses<double>(LU, n, 1, 0, G, WU, 0, st));
   return LA_OK;
 }
 

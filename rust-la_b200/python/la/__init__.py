@@ -5,6 +5,7 @@ Mirrors (reference, relative to /root/reference):
                                                    id :416-426, operator * :957-998, det/solve/inverse/is_singular :1025-1047
   Matrix::mmul         src/matrix/mmatrix.rs:82-98
   LUDecomposition<T>   src/decomp/lu.rs:95-278     new, is_singular, is_non_singular, get_l, get_u, get_p, get_piv, det, solve
+  CholeskyDecomposition<T>  src/decomp/cholesky.rs:52-144   new (None unless square, symmetric, positive definite), get_l, solve
   m!                   src/macros.rs:39-42         -> m("1, 2; 3, 4") / m([[1, 2], [3, 4]])
   ApproxEq             src/approxeq.rs:34-47       absolute 1e-6
 
@@ -19,7 +20,7 @@ import numpy as np
 from . import _cabi
 from ._cabi import LaError, lib, check  # noqa: F401
 
-__all__ = ["Matrix", "DeviceMatrix", "LUDecomposition", "m", "Panic", "LaError", "APPROX_EPS"]
+__all__ = ["Matrix", "DeviceMatrix", "LUDecomposition", "CholeskyDecomposition", "m", "Panic", "LaError", "APPROX_EPS"]
 
 APPROX_EPS = 1e-6  # src/approxeq.rs:20,36
 
@@ -272,6 +273,46 @@ class LUDecomposition:
         x = np.empty(self._m * nx, dtype=self._dtype)
         xbuf.download(x)
         return Matrix(self._m, x)
+
+
+class CholeskyDecomposition:
+    """CholeskyDecomposition<T>, src/decomp/cholesky.rs:52-54: `{ l: Matrix<T> }` with A = L L'.  L stays in HBM."""
+
+    def __init__(self, n, dtype, buf):
+        self._n, self._dtype, self._buf = n, np.dtype(dtype), buf
+        self._l_host = None
+
+    @staticmethod
+    def new(a, device=0):
+        """cholesky.rs:56-110: None unless `a` is square, symmetric (exact) and positive definite."""
+        if a.rows() != a.cols():
+            return None  # :57-59
+        n, suf = a.rows(), _suffix(a.data.dtype)
+        buf = _DeviceBuf(a.data.nbytes, device)
+        buf.upload(a.data)
+        ok = ctypes.c_int(0)
+        check(getattr(lib(), f"la_chol_factor_{suf}")(buf.handle, n, ctypes.byref(ok)))
+        return CholeskyDecomposition(n, a.data.dtype, buf) if ok.value else None
+
+    def get_l(self):
+        if self._l_host is None:
+            h = np.empty(self._n * self._n, dtype=self._dtype)
+            self._buf.download(h)
+            self._l_host = Matrix(self._n, h)
+        return self._l_host
+
+    def solve(self, b):
+        """cholesky.rs:116-144."""
+        _assert(b.rows() == self._n, "l.rows() == b.rows()")  # :118
+        _assert(b.data.dtype == self._dtype, "same element type")
+        nx = b.cols()
+        bbuf = _DeviceBuf(b.data.nbytes)
+        xbuf = _DeviceBuf(b.data.nbytes)
+        bbuf.upload(b.data)
+        check(getattr(lib(), f"la_chol_solve_{_suffix(self._dtype)}")(self._buf.handle, self._n, bbuf.handle, nx, xbuf.handle))
+        x = np.empty(self._n * nx, dtype=self._dtype)
+        xbuf.download(x)
+        return Matrix(self._n, x)
 
 
 class DeviceMatrix:

@@ -63,6 +63,18 @@ SIGNATURES = {
     "la_lu_solve_f32_host": ([_p, _sz, _sz, _p, _p, _sz, _p], _i),
     "la_lu_solve_f64_dev": ([_p, _sz, _p, _p, _sz, _p, _p], _i),
     "la_lu_solve_f32_dev": ([_p, _sz, _p, _p, _sz, _p, _p], _i),
+    "la_chol_factor_f64": ([_p, _sz, _pi], _i),
+    "la_chol_factor_f32": ([_p, _sz, _pi], _i),
+    "la_chol_factor_f64_host": ([_p, _p, _sz, _pi], _i),
+    "la_chol_factor_f32_host": ([_p, _p, _sz, _pi], _i),
+    "la_chol_factor_f64_dev": ([_p, _sz, _p, _p], _i),
+    "la_chol_factor_f32_dev": ([_p, _sz, _p, _p], _i),
+    "la_chol_solve_f64_dev": ([_p, _sz, _p, _sz, _p, _p], _i),
+    "la_chol_solve_f32_dev": ([_p, _sz, _p, _sz, _p, _p], _i),
+    "la_chol_solve_f64": ([_p, _sz, _p, _sz, _p], _i),
+    "la_chol_solve_f32": ([_p, _sz, _p, _sz, _p], _i),
+    "la_chol_solve_f64_host": ([_p, _sz, _p, _sz, _p], _i),
+    "la_chol_solve_f32_host": ([_p, _sz, _p, _sz, _p], _i),
     "la_identity_f64": ([_p, _sz], _i),
     "la_identity_f32": ([_p, _sz], _i),
     "la_transpose_f64": ([_p, _p, _sz, _sz], _i),

@@ -8,7 +8,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let cuda = env::var("CUDA_HOME").unwrap_or_else(|_| "/usr/local/cuda".to_string());
     let nvcc = format!("{}/bin/nvcc", cuda);
-    let srcs = ["la_runtime", "gemm_f64", "gemm_f32", "gemm_simt", "lu", "lu_solve", "capi"];
+    let srcs = ["la_runtime", "gemm_f64", "gemm_f32", "gemm_simt", "lu", "lu_solve", "cholesky", "capi"];
     let mut objs = Vec::new();
     for s in srcs.iter() {
         let src = format!("../csrc/{}.cu", s);

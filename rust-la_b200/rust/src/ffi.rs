@@ -74,6 +74,18 @@ extern "C" {
     pub fn la_lu_solve_f32_dev(lu: *const f32, n: usize, piv_dev: *const u64, b: *const f32, nx: usize, x: *mut f32,
                                cuda_stream: *mut c_void) -> c_int;
 
+    pub fn la_chol_factor_f64(a_inout: *mut la_buf, n: usize, ok_out: *mut c_int) -> c_int;
+    pub fn la_chol_factor_f32(a_inout: *mut la_buf, n: usize, ok_out: *mut c_int) -> c_int;
+    pub fn la_chol_factor_f64_host(a: *const f64, l_out: *mut f64, n: usize, ok_out: *mut c_int) -> c_int;
+    pub fn la_chol_factor_f32_host(a: *const f32, l_out: *mut f32, n: usize, ok_out: *mut c_int) -> c_int;
+    pub fn la_chol_factor_f64_dev(a_inout: *mut f64, n: usize, flags_dev: *mut c_int, stream: *mut c_void) -> c_int;
+    pub fn la_chol_factor_f32_dev(a_inout: *mut f32, n: usize, flags_dev: *mut c_int, stream: *mut c_void) -> c_int;
+    pub fn la_chol_solve_f64_dev(l: *const f64, n: usize, b: *const f64, nx: usize, x: *mut f64, stream: *mut c_void) -> c_int;
+    pub fn la_chol_solve_f32_dev(l: *const f32, n: usize, b: *const f32, nx: usize, x: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn la_chol_solve_f64(l: *const la_buf, n: usize, b: *const la_buf, nx: usize, x: *mut la_buf) -> c_int;
+    pub fn la_chol_solve_f32(l: *const la_buf, n: usize, b: *const la_buf, nx: usize, x: *mut la_buf) -> c_int;
+    pub fn la_chol_solve_f64_host(l: *const f64, n: usize, b: *const f64, nx: usize, x: *mut f64) -> c_int;
+    pub fn la_chol_solve_f32_host(l: *const f32, n: usize, b: *const f32, nx: usize, x: *mut f32) -> c_int;
     pub fn la_identity_f64(dst: *mut la_buf, n: usize) -> c_int;
     pub fn la_identity_f32(dst: *mut la_buf, n: usize) -> c_int;
     pub fn la_transpose_f64(src: *const la_buf, dst: *mut la_buf, rows: usize, cols: usize) -> c_int;

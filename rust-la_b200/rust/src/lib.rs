@@ -9,10 +9,12 @@ extern crate num;
 #[macro_use]
 mod macros;
 mod approxeq;
+mod cholesky;
 mod ffi;
 mod lu;
 mod matrix;
 
 pub use approxeq::ApproxEq;
+pub use cholesky::{CholScalar, CholeskyDecomposition};
 pub use lu::LUDecomposition;
 pub use matrix::{DeviceScalar, Matrix};

@@ -66,7 +66,7 @@ impl<T: Copy> Matrix<T> {
 
 impl<T: DeviceScalar> Matrix<T> {
     /// Output allocation of Mul: the reference's `alloc_dirty_vec` (src/internalutil.rs:7-13).
-    fn dirty_vec(len: usize) -> Vec<T> {
+    pub(crate) fn dirty_vec(len: usize) -> Vec<T> {
         let mut v = Vec::with_capacity(len);
         unsafe { v.set_len(len) };
         v
