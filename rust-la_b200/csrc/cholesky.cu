@@ -16,7 +16,8 @@
 //   4. A22 -= L21 * L21' : the transposed panel is materialised once (tile transpose), then one GEMM per 2048-column
 //                          strip restricted to the rows at or below the strip (the upper triangle is never read);
 //                          the strips are independent and alternate over three streams.
-// The solve builds L' once and runs both sweeps as GEMMs with inverted diagonal blocks (fp64, n >= 512, even sizes);
+// The solve builds L' once, inverts the diagonal blocks of L and L', and runs both sweeps with the LU solve's persistent
+// kernels (nx <= 16) or as GEMMs (fp64, n >= 512, even sizes);
 // everything else takes a reference-order kernel that is bit-identical to the reference given the same L.
 #include <stdlib.h>
 
@@ -30,6 +31,8 @@ int gemm_f64_tensor(const double* A, size_t lda, const double* B, size_t ldb, do
 template <typename T>
 int tri_block_inverses(const T* M, size_t n, int mode, int first_block, int nblocks, T* W, int trans_out,
                        cudaStream_t st);  // lu.cu
+int tri_sweeps_dev(const double* Lmat, const double* Umat, size_t n, const uint64_t* piv_dev, const double* B, size_t nx,
+                   double* X, const double* wl, const double* wu, cudaStream_t st);  // lu_solve.cu
 
 namespace {
 constexpr int CB = 128;  // block size
@@ -305,6 +308,8 @@ int chol_solve_dev(const T* L, size_t n, const T* B, size_t nx, T* X, cudaStream
       LA_TRY(transpose_dev<double>(L, LT, n, n, st));
       LA_TRY(tri_block_inverses<double>(L, n, 2, 0, G, WL, 0, st));
       LA_TRY(tri_block_inverses<double>(LT, n, 1, 0, G, WU, 0, st));
+      if (nx <= 16 && G <= ctx->sm_count && ctx->coop)  // few right-hand sides: the LU solve's persistent sweep kernels
+        return tri_sweeps_dev(L, LT, n, nullptr, B, nx, X, WL, WU, st);
       for (int b = 0; b < G; ++b) {  // L Y = B
         const size_t r0 = (size_t)b * CB, nr = (n - r0 < (size_t)CB) ? (n - r0) : (size_t)CB;
         double* Xb = X + r0 * nx;

@@ -197,7 +197,8 @@ solve_sweep_kernel(const double* __restrict__ LU, size_t n, const uint64_t* __re
       const int rr = urow + 32 * i, col = ucol + j;
       acc[i][j] = 0.0;
       if (warp < 4 && rr < nr && col < nx)  // X = B(piv,:), lu.rs:246-254
-        acc[i][j] = FORWARD ? B[(size_t)piv[r0 + rr] * nx + col] : X[(size_t)(r0 + rr) * nx + col];
+        acc[i][j] = FORWARD ? B[(size_t)(piv ? piv[r0 + rr] : (uint64_t)(r0 + rr)) * nx + col]
+                            : X[(size_t)(r0 + rr) * nx + col];
     }
   // a0/a1 -= (rows urow, urow+32 of buffer hh) * (rows [64 hh, 64 hh + 64) of Ys)
   auto mac_half = [&](int hh, double (&a0)[2][8], double (&a1)[2][8]) {
@@ -345,6 +346,65 @@ __global__ void det_kernel(const T* __restrict__ diag, size_t n, int pospivsign,
 
 }  // namespace
 
+// Two persistent sweeps (see solve_sweep_kernel): X = Umat^-1 (Lmat^-1 B(piv,:)) where only the blocks of Lmat strictly
+// below and of Umat strictly above the block diagonal are read, the diagonal blocks arriving inverted in WL / WU
+// ([G][128][128]).  Lmat == Umat == packed LU for the LU solve; L and L' for Cholesky.  piv_dev may be null (identity).
+// Caller guarantees: nx <= 16, n even, 16-byte aligned matrices, ceil(n / 128) <= SM count, cooperative launch support.
+int tri_sweeps_dev(const double* Lmat, const double* Umat, size_t n, const uint64_t* piv_dev, const double* B, size_t nx,
+                   double* X, const double* wl, const double* wu, cudaStream_t st) {
+  const DeviceCtx* ctx;
+  LA_TRY(current_device_ctx(&ctx));
+  const int G = (int)((n + PB - 1) / PB);
+  void* fl = nullptr;
+  const size_t fbytes = sizeof(unsigned) * (size_t)G * G;
+  LA_TRY(scratch_get(ctx->device, 13, 2 * fbytes, &fl));
+  LA_CUDA_TRY(cudaMemsetAsync(fl, 0, 2 * fbytes, st));
+  LA_CUDA_TRY(cudaFuncSetAttribute(solve_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM));
+  LA_CUDA_TRY(cudaFuncSetAttribute(solve_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM));
+  const double* lu_p = Lmat;
+  const double* uu_p = Umat;
+  const double* b_p = B;
+  double* x_p = X;
+  size_t nn = n;
+  int nxi = (int)nx;
+  unsigned* f0 = (unsigned*)fl;
+  unsigned* f1 = f0 + (size_t)G * G;
+  // LA_SOLVE_TRACE=1: phase timestamps of every CTA's last step, printed after a sync (diagnostic)
+  static const int trace = getenv("LA_SOLVE_TRACE") ? atoi(getenv("LA_SOLVE_TRACE")) : 0;
+  unsigned long long* d0 = nullptr;
+  unsigned long long* d1 = nullptr;
+  if (trace) {
+    void* dp = nullptr;
+    LA_TRY(scratch_get(ctx->device, 14, 2 * sizeof(unsigned long long) * 8 * G, &dp));
+    LA_CUDA_TRY(cudaMemsetAsync(dp, 0, 2 * sizeof(unsigned long long) * 8 * G, st));
+    d0 = (unsigned long long*)dp;
+    d1 = d0 + 8 * G;
+  }
+  void* a0[] = {&lu_p, &nn, &piv_dev, &b_p, &x_p, &nxi, &f0, &wl, &d0};
+  void* a1[] = {&uu_p, &nn, &piv_dev, &b_p, &x_p, &nxi, &f1, &wu, &d1};
+  LA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)solve_sweep_kernel<true>, dim3(G), dim3(SWEEP_THREADS), a0,
+                                          SWEEP_SMEM, st));
+  LA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)solve_sweep_kernel<false>, dim3(G), dim3(SWEEP_THREADS), a1,
+                                          SWEEP_SMEM, st));
+  if (trace) {
+    std::vector<unsigned long long> hbuf(16 * (size_t)G);
+    LA_CUDA_TRY(cudaStreamSynchronize(st));
+    LA_CUDA_TRY(cudaMemcpy(hbuf.data(), d0, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int ph = 0; ph < 2; ++ph) {
+      const unsigned long long* hb = hbuf.data() + (size_t)ph * 8 * G;
+      const unsigned long long t0 = ph == 0 ? hb[3] : hb[(size_t)(G - 1) * 8 + 3];
+      for (int g = 0; g < G; g += (G > 16 ? G / 16 : 1)) {
+        const unsigned long long* e = hb + (size_t)g * 8;
+        fprintf(stderr, "solve %s cta %3d: flag %8.2f us | +Y/update %6.2f | +Lwait %5.2f | +block product %6.2f | +fence %5.2f\n",
+                ph == 0 ? "fwd" : "bwd", g, e[0] ? (double)(e[0] - t0) * 1e-3 : 0.0,
+                e[0] ? (double)(e[1] - e[0]) * 1e-3 : 0.0, (double)(e[2] - e[1]) * 1e-3, (double)(e[3] - e[2]) * 1e-3,
+                (double)(e[4] - e[3]) * 1e-3);
+      }
+    }
+  }
+  return LA_OK;
+}
+
 template <typename T>
 int lu_solve_dev(const T* LU, size_t n, const uint64_t* piv_dev, const T* B, size_t nx, T* X, cudaStream_t st) {
   const DeviceCtx* ctx;
@@ -359,57 +419,12 @@ int lu_solve_dev(const T* LU, size_t n, const uint64_t* piv_dev, const T* B, siz
     const int G = (N + PB - 1) / PB;
     static const int no_sweep = getenv("LA_SOLVE_NO_SWEEP") ? atoi(getenv("LA_SOLVE_NO_SWEEP")) : 0;  // debug knob
     if (!no_sweep && nx <= 16 && N >= 4 * PB && N % 2 == 0 && (uintptr_t)LU % 16 == 0 && G <= ctx->sm_count && ctx->coop) {
-      void* fl = nullptr;
-      const size_t fbytes = sizeof(unsigned) * (size_t)G * G;
-      LA_TRY(scratch_get(ctx->device, 13, 2 * fbytes, &fl));
-      LA_CUDA_TRY(cudaMemsetAsync(fl, 0, 2 * fbytes, st));
-      LA_CUDA_TRY(cudaFuncSetAttribute(solve_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM));
-      LA_CUDA_TRY(cudaFuncSetAttribute(solve_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM));
-      const double* lu_p = LU;
-      const double* b_p = B;
-      double* x_p = X;
-      size_t nn = n;
-      int nxi = (int)nx;
-      unsigned* f0 = (unsigned*)fl;
-      unsigned* f1 = f0 + (size_t)G * G;
-      // LA_SOLVE_TRACE=1: phase timestamps of every CTA's last step, printed after a sync (diagnostic)
-      static const int trace = getenv("LA_SOLVE_TRACE") ? atoi(getenv("LA_SOLVE_TRACE")) : 0;
-      unsigned long long* d0 = nullptr;
-      unsigned long long* d1 = nullptr;
-      if (trace) {
-        void* dp = nullptr;
-        LA_TRY(scratch_get(ctx->device, 14, 2 * sizeof(unsigned long long) * 8 * G, &dp));
-        LA_CUDA_TRY(cudaMemsetAsync(dp, 0, 2 * sizeof(unsigned long long) * 8 * G, st));
-        d0 = (unsigned long long*)dp;
-        d1 = d0 + 8 * G;
-      }
       void* wbuf = nullptr;
       LA_TRY(scratch_get(ctx->device, 15, sizeof(double) * 2 * (size_t)G * PB * PB, &wbuf));
-      const double* wl = (const double*)wbuf;
-      const double* wu = wl + (size_t)G * PB * PB;
-      LA_TRY(lu_diag_block_inverses(LU, n, (double*)wbuf, (double*)wbuf + (size_t)G * PB * PB, st));
-      void* a0[] = {&lu_p, &nn, &piv_dev, &b_p, &x_p, &nxi, &f0, &wl, &d0};
-      void* a1[] = {&lu_p, &nn, &piv_dev, &b_p, &x_p, &nxi, &f1, &wu, &d1};
-      LA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)solve_sweep_kernel<true>, dim3(G), dim3(SWEEP_THREADS), a0,
-                                              SWEEP_SMEM, st));
-      LA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)solve_sweep_kernel<false>, dim3(G), dim3(SWEEP_THREADS), a1,
-                                              SWEEP_SMEM, st));
-      if (trace) {
-        std::vector<unsigned long long> hbuf(16 * (size_t)G);
-        LA_CUDA_TRY(cudaStreamSynchronize(st));
-        LA_CUDA_TRY(cudaMemcpy(hbuf.data(), d0, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        for (int ph = 0; ph < 2; ++ph) {
-          const unsigned long long* hb = hbuf.data() + (size_t)ph * 8 * G;
-          const unsigned long long t0 = ph == 0 ? hb[3] : hb[(size_t)(G - 1) * 8 + 3];
-          for (int g = 0; g < G; g += (G > 16 ? G / 16 : 1)) {
-            const unsigned long long* e = hb + (size_t)g * 8;
-            fprintf(stderr, "solve %s cta %3d: flag %8.2f us | +Y/update %6.2f | +Lwait %5.2f | +block product %6.2f | +fence %5.2f\n",
-                    ph == 0 ? "fwd" : "bwd", g, e[0] ? (double)(e[0] - t0) * 1e-3 : 0.0,
-                    e[0] ? (double)(e[1] - e[0]) * 1e-3 : 0.0, (double)(e[2] - e[1]) * 1e-3, (double)(e[3] - e[2]) * 1e-3,
-                    (double)(e[4] - e[3]) * 1e-3);
-          }
-        }
-      }
+      double* wl = (double*)wbuf;
+      double* wu = wl + (size_t)G * PB * PB;
+      LA_TRY(lu_diag_block_inverses(LU, n, wl, wu, st));
+      LA_TRY(tri_sweeps_dev(LU, LU, n, piv_dev, B, nx, X, wl, wu, st));
       return LA_OK;
     }
   }
