@@ -1,18 +1,34 @@
-// ApproxEq -- absolute 1e-6 for f32 and f64, as in the reference (src/approxeq.rs:12-47).
+// Approximate comparison used by the reference's tests (`approx_eq` on scalars and, through matrix.rs, on matrices).
+// Contract mirrored from the reference (src/approxeq.rs:12-47): an ABSOLUTE tolerance, strict `<`, default 1e-6 for both
+// float widths; the trait keeps the reference's name and method set so user code and the crate's other modules compile
+// unchanged.  The two implementations are generated from one macro.
 pub trait ApproxEq<Eps> {
     fn approx_epsilon() -> Eps;
     fn approx_eq(&self, other: &Self) -> bool;
     fn approx_eq_eps(&self, other: &Self, approx_epsilon: &Eps) -> bool;
 }
 
-impl ApproxEq<f32> for f32 {
-    fn approx_epsilon() -> f32 { 1.0e-6 }
-    fn approx_eq(&self, other: &f32) -> bool { self.approx_eq_eps(other, &1.0e-6) }
-    fn approx_eq_eps(&self, other: &f32, approx_epsilon: &f32) -> bool { (*self - *other).abs() < *approx_epsilon }
-}
+/// Default absolute tolerance of `approx_eq`, shared by f32 and f64.
+pub const DEFAULT_ABS_TOLERANCE: f64 = 1.0e-6;
 
-impl ApproxEq<f64> for f64 {
-    fn approx_epsilon() -> f64 { 1.0e-6 }
-    fn approx_eq(&self, other: &f64) -> bool { self.approx_eq_eps(other, &1.0e-6) }
-    fn approx_eq_eps(&self, other: &f64, approx_epsilon: &f64) -> bool { (*self - *other).abs() < *approx_epsilon }
+macro_rules! absolute_tolerance_impl {
+    ($($float:ty),+) => {$(
+        impl ApproxEq<$float> for $float {
+            #[inline]
+            fn approx_epsilon() -> $float {
+                DEFAULT_ABS_TOLERANCE as $float
+            }
+            #[inline]
+            fn approx_eq(&self, other: &$float) -> bool {
+                let tolerance = <$float as ApproxEq<$float>>::approx_epsilon();
+                self.approx_eq_eps(other, &tolerance)
+            }
+            #[inline]
+            fn approx_eq_eps(&self, other: &$float, approx_epsilon: &$float) -> bool {
+                let distance = if *self >= *other { *self - *other } else { *other - *self };
+                distance < *approx_epsilon // NaN on either side compares false, as `(a - b).abs() < eps` does
+            }
+        }
+    )+};
 }
+absolute_tolerance_impl!(f32, f64);
