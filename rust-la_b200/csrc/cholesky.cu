@@ -75,8 +75,9 @@ chol_diag_kernel(T* __restrict__ A, size_t ld, int j0, int jb, int* __restrict__
   extern __shared__ __align__(16) unsigned char chol_smem[];
   T* Lp = reinterpret_cast<T*>(chol_smem);  // packed lower triangle: a[j][k] on entry, L[j][k] on exit
   T* Sp = Lp + CB * (CB + 1) / 2;           // packed deferred sums
-  __shared__ T col[CB];                     // column i of L (dense), L[i][i] at col[i]
+  __shared__ T col[CB];                     // column i of L (dense)
   __shared__ T dsum[CB];
+  __shared__ T ldiag[CB];
   const int tid = threadIdx.x;
   for (int e = tid; e < jb * (jb + 1) / 2; e += CHOL_THREADS) Sp[e] = (T)0;
   for (int e = tid; e < jb * jb; e += CHOL_THREADS) {
@@ -86,17 +87,15 @@ chol_diag_kernel(T* __restrict__ A, size_t ld, int j0, int jb, int* __restrict__
   if (tid < CB) dsum[tid] = (T)0;
   __syncthreads();
   for (int i = 0; i < jb; ++i) {
-    // diagonal: L[i][i] = sqrt(a[i][i] - d), None when a[i][i] - d <= 0 (cholesky.rs:99-104)
-    if (tid == 0) {
-      const T d = sub_rn(Lp[tri(i, i)], dsum[i]);
-      if (d <= (T)0) flags[1] = 1;
-      const T lii = sqrt(d);
-      Lp[tri(i, i)] = lii;
-      col[i] = lii;
-    }
-    __syncthreads();
+    // diagonal: L[i][i] = sqrt(a[i][i] - d), None when a[i][i] - d <= 0 (cholesky.rs:99-104) -- evaluated redundantly by
+    // every thread of the column phase (same inputs, same result) instead of by one thread between two barriers;
     // column i: L[j][i] = (a[j][i] - s[j][i]) / L[i][i] (cholesky.rs:85), d[j] += L[j][i]^2 (:89)
-    const T lii = col[i];
+    const T dii = sub_rn(Lp[tri(i, i)], dsum[i]);
+    const T lii = sqrt(dii);
+    if (tid == 0) {
+      if (dii <= (T)0) flags[1] = 1;
+      ldiag[i] = lii;  // kept apart from the packed triangle: a[i][i] there is still being read by the other threads
+    }
     for (int j = i + 1 + tid; j < jb; j += CHOL_THREADS) {
       const T v = sub_rn(Lp[tri(j, i)], Sp[tri(j, i)]) / lii;
       Lp[tri(j, i)] = v;
@@ -104,20 +103,39 @@ chol_diag_kernel(T* __restrict__ A, size_t ld, int j0, int jb, int* __restrict__
       dsum[j] = add_rn(dsum[j], mul_rn(v, v));
     }
     __syncthreads();
-    // deferred sums of the columns still to come: i < k < j
-    const int rem = jb - i - 1;  // rows/columns i+1 .. jb-1
-    for (int e = tid; e < rem * rem; e += CHOL_THREADS) {
-      const int jj = e / rem, kk = e - jj * rem;
-      if (kk < jj) {
-        const int j = i + 1 + jj, k = i + 1 + kk;
-        Sp[tri(j, k)] = add_rn(Sp[tri(j, k)], mul_rn(col[k], col[j]));
+    // deferred sums of the columns still to come: i < k < j.  Threads form a 16 x 16 grid over (k, j); four rows j per
+    // trip with loads, arithmetic and stores grouped, so the ~64-cycle FP64 latencies of independent elements overlap
+    // (one element at a time, with an integer division for its index, made this kernel 376 us per block).
+    {
+      const int tx = tid & 15, ty = tid >> 4;
+      for (int jb0 = i + 2 + ty; jb0 < jb; jb0 += 64) {  // j = jb0, jb0 + 16, jb0 + 32, jb0 + 48
+        T cj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cj[u] = (jb0 + 16 * u < jb) ? col[jb0 + 16 * u] : (T)0;
+        const int kmax = min(jb0 + 48, jb - 1);  // k < j for the largest j of the trip
+        for (int k = i + 1 + tx; k < kmax; k += 16) {
+          const T ck = col[k];
+          T sv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = jb0 + 16 * u;
+            sv[u] = (j < jb && k < j) ? Sp[tri(j, k)] : (T)0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) sv[u] = add_rn(sv[u], mul_rn(ck, cj[u]));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = jb0 + 16 * u;
+            if (j < jb && k < j) Sp[tri(j, k)] = sv[u];
+          }
+        }
       }
     }
     __syncthreads();
   }
   for (int e = tid; e < jb * jb; e += CHOL_THREADS) {
     const int j = e / jb, k = e - j * jb;
-    A[(size_t)(j0 + j) * ld + j0 + k] = (k <= j) ? Lp[tri(j, k)] : (T)0;  // zeros above the diagonal (:107-109)
+    A[(size_t)(j0 + j) * ld + j0 + k] = (k < j) ? Lp[tri(j, k)] : (k == j ? ldiag[j] : (T)0);  // zeros above (:107-109)
   }
 }
 
