@@ -47,6 +47,8 @@ template <> struct Abi<double> {
   static int nonsingular(const la_buf* lu, size_t n, int* out) { return la_lu_is_nonsingular_f64(lu, n, out); }
   static int det(const la_buf* lu, size_t n, int pos, double* out) { return la_lu_det_f64(lu, n, pos, out); }
   static int solve(const la_buf* lu, size_t m, size_t n, const uint64_t* piv, const la_buf* b, size_t nx, la_buf* x) { return la_lu_solve_f64(lu, m, n, piv, b, nx, x); }
+  static int chol_factor(la_buf* a, size_t n, int* ok) { return la_chol_factor_f64(a, n, ok); }
+  static int chol_solve(const la_buf* l, size_t n, const la_buf* b, size_t nx, la_buf* x) { return la_chol_solve_f64(l, n, b, nx, x); }
 };
 template <> struct Abi<float> {
   static int gemm_host(const float* a, const float* b, float* c, size_t m, size_t k, size_t n) { return la_gemm_f32_host(a, b, c, m, k, n); }
@@ -54,6 +56,8 @@ template <> struct Abi<float> {
   static int nonsingular(const la_buf* lu, size_t n, int* out) { return la_lu_is_nonsingular_f32(lu, n, out); }
   static int det(const la_buf* lu, size_t n, int pos, float* out) { return la_lu_det_f32(lu, n, pos, out); }
   static int solve(const la_buf* lu, size_t m, size_t n, const uint64_t* piv, const la_buf* b, size_t nx, la_buf* x) { return la_lu_solve_f32(lu, m, n, piv, b, nx, x); }
+  static int chol_factor(la_buf* a, size_t n, int* ok) { return la_chol_factor_f32(a, n, ok); }
+  static int chol_solve(const la_buf* l, size_t n, const la_buf* b, size_t nx, la_buf* x) { return la_chol_solve_f32(l, n, b, nx, x); }
 };
 template <> struct Abi<int64_t> {
   static int gemm_host(const int64_t* a, const int64_t* b, int64_t* c, size_t m, size_t k, size_t n) { return la_gemm_i64_host(a, b, c, m, k, n); }
@@ -231,6 +235,43 @@ class LUDecomposition {
   detail::DevBuf lu_;
   std::vector<uint64_t> piv_;
   bool pospivsign_ = true;
+};
+
+// CholeskyDecomposition<T>, cholesky.rs:52-144.  `make` is the reference's `new`: empty unless the matrix is square,
+// exactly symmetric and positive definite.  L stays resident in HBM.
+template <typename T>
+class CholeskyDecomposition {
+ public:
+  static std::optional<CholeskyDecomposition<T>> make(const Matrix<T>& a) {
+    if (a.rows() != a.cols()) return std::nullopt;  // cholesky.rs:57-59
+    CholeskyDecomposition<T> c(a.rows());
+    check(la_buf_upload(c.l_.h, 0, a.get_data().data(), c.n_ * c.n_ * sizeof(T)));
+    int ok = 0;
+    check(Abi<T>::chol_factor(c.l_.h, c.n_, &ok));
+    if (!ok) return std::nullopt;  // not symmetric (:91-93) or not positive definite (:99-102)
+    return std::optional<CholeskyDecomposition<T>>(std::move(c));
+  }
+  Matrix<T> get_l() const {
+    std::vector<T> d(n_ * n_);
+    check(la_buf_download(l_.h, 0, d.data(), d.size() * sizeof(T)));
+    return Matrix<T>(n_, n_, std::move(d));
+  }
+  Matrix<T> solve(const Matrix<T>& b) const {  // cholesky.rs:116-144
+    LA_ASSERT(b.rows() == n_);
+    size_t nx = b.cols(), bytes = n_ * nx * sizeof(T);
+    detail::DevBuf db(bytes), dx(bytes);
+    check(la_buf_upload(db.h, 0, b.get_data().data(), bytes));
+    check(Abi<T>::chol_solve(l_.h, n_, db.h, nx, dx.h));
+    std::vector<T> x(n_ * nx);
+    check(la_buf_download(dx.h, 0, x.data(), bytes));
+    return Matrix<T>(n_, nx, std::move(x));
+  }
+  CholeskyDecomposition(CholeskyDecomposition&&) noexcept = default;
+
+ private:
+  explicit CholeskyDecomposition(size_t n) : n_(n), l_(n * n * sizeof(T)) {}
+  size_t n_;
+  detail::DevBuf l_;
 };
 
 }  // namespace la

@@ -1,5 +1,6 @@
 // test_la.cpp -- the reference's unit tests for the hot path, written against la.hpp (C++ mirror of the crate API).
-// Sources: src/matrix/mod.rs:1479-1571, src/matrix/mmatrix.rs:234-259, src/decomp/lu.rs:281-375.
+// Sources: src/matrix/mod.rs:1479-1571, src/matrix/mmatrix.rs:234-259, src/decomp/lu.rs:281-375,
+// src/decomp/cholesky.rs:146-183.
 // Without a GPU every compute call throws la::LaError (no CPU fallback); `--require-gpu` turns that into a failure,
 // otherwise the binary only checks the host-side contract (panics before FFI) and reports SKIP for the rest.
 #include <cmath>
@@ -114,6 +115,21 @@ int main(int argc, char** argv) {
     auto a = la::m<float>({{4, 8}, {3, 4}});
     CHECK(a.det() == -8.0f);
     CHECK((a * Matrix<float>::id(2, 2)) == a);
+  });
+  run("cholesky (cholesky.rs:146-183)", [] {
+    typedef la::CholeskyDecomposition<double> Chol;
+    auto a = la::m<double>({{4, 12, -16}, {12, 37, -43}, {-16, -43, 98}});
+    auto c = Chol::make(a);
+    CHECK(c.has_value());
+    auto l = c->get_l();
+    CHECK(l.get_data() == std::vector<double>({2, 0, 0, 6, 1, 0, -8, 5, 3}));
+    CHECK(l * l.t() == a);
+    CHECK(!Chol::make(la::m<double>({{4, 12, -16}, {12, 37, 43}, {-16, 43, 98}})).has_value());  // not positive definite
+    CHECK(!Chol::make(la::m<double>({{4, 12, -16}, {12, 37, 43}})).has_value());                  // not square
+    auto s = Chol::make(la::m<double>({{2, 1, 0}, {1, 1, 0}, {0, 0, 1}}));
+    CHECK(s.has_value());
+    CHECK(s->solve(la::m<double>({{1}, {2}, {3}})).approx_eq(la::m<double>({{-1}, {3}, {3}})));
+    should_panic([&] { s->solve(la::m<double>({{1}, {2}, {3}, {4}})); });
   });
   printf("%d passed, %d skipped, %d failed\n", passed, skipped, failures);
   return failures ? 1 : 0;
