@@ -108,7 +108,7 @@ __device__ __forceinline__ unsigned long long rec_pack(unsigned key32, unsigned 
 template <typename T>
 struct PanelWs {
   int ipiv[MAX_NB];  // absolute pivot row chosen for column j0 + c
-  MoveList moves[2];
+  MoveList moves[4];  // [0], [1]: whole panels by parity; [2], [3]: the two 64-wide halves of a split panel
   // double-buffered (step parity) exchange area, laid out after the struct:
   //   Rec inbox[2][G reader][G writer]; LL<T>::word cand_row[2][G][XROW]; LL<T>::word top_row[2][XROW];
   // Every CTA pushes its record into each reader's PRIVATE inbox and polls only its own: an all-to-all in which no
@@ -187,7 +187,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
 // so the column time is max(exchange latency, update time) instead of their sum.
 template <typename T, bool EXACT>
 __global__ void __launch_bounds__(PANEL_THREADS, 1)
-lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_per_cta, void* ws_base, unsigned epoch) {
+lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_per_cta, void* ws_base, unsigned epoch,
+                int ipiv_off) {
   typedef typename LL<T>::word llw;
   constexpr int Q = MAX_NB / 32;
   extern __shared__ __align__(16) unsigned char panel_smem[];
@@ -446,7 +447,7 @@ lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_pe
     __syncthreads();       // (A) step c's pivot row is in shared memory; the bulk update of step c-1 is complete
     const int p = s_p[par];
     const T pv = s_u[par][c];
-    if (blockIdx.x == 0 && threadIdx.x == 0) ws.hdr->ipiv[c] = p;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ws.hdr->ipiv[ipiv_off + c] = p;
 
     // ---- interchange (whole panel row; the rest of the row is swapped by lu_swap/lu_head kernels), by the warp that
     //      owns the row in the urgent phase below ----
@@ -585,7 +586,8 @@ lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_pe
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(2 * MAX_NB)
-lu_perm_kernel(void* ws_base, int G, int parity, int j0, int jb, uint64_t* __restrict__ piv, int* __restrict__ sign) {
+lu_perm_kernel(void* ws_base, int G, int parity, int j0, int jb, uint64_t* __restrict__ piv, int* __restrict__ sign,
+               int ipiv_off, int update_piv) {
   // One thread per position that can change: the jb top rows and the (distinct) pivot rows below them.  The content
   // that ends up at position q is the original row reached by tracing q BACKWARDS through the jb transpositions.
   __shared__ int ipiv_s[MAX_NB];
@@ -594,7 +596,7 @@ lu_perm_kernel(void* ws_base, int G, int parity, int j0, int jb, uint64_t* __res
   const WsView<T> ws = ws_view<T>(ws_base, G);
   MoveList* ml = &ws.hdr->moves[parity];
   const int tid = threadIdx.x;
-  if (tid < jb) ipiv_s[tid] = ws.hdr->ipiv[tid];
+  if (tid < jb) ipiv_s[tid] = ws.hdr->ipiv[ipiv_off + tid];
   if (tid == 0) {
     nm = 0;
     flips = 0;
@@ -623,13 +625,13 @@ lu_perm_kernel(void* ws_base, int G, int parity, int j0, int jb, uint64_t* __res
     slot = atomicAdd(&nm, 1);
     ml->dst[slot] = q;
     ml->src[slot] = r;
-    pold = piv[r];  // `piv` is permuted exactly like a matrix column (lu.rs:147-149)
+    if (update_piv) pold = piv[r];  // `piv` is permuted exactly like a matrix column (lu.rs:147-149)
   }
   __syncthreads();
-  if (slot >= 0) piv[q] = pold;
+  if (slot >= 0 && update_piv) piv[q] = pold;
   if (tid == 0) {
     ml->n_moves = nm;
-    if (flips & 1) *sign = !*sign;
+    if (update_piv && (flips & 1)) *sign = !*sign;
   }
 }
 
@@ -1023,7 +1025,7 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
 
   int G_cur = 1;
   // panel factorisation of columns [j0, j0+jb) on stream s (ipiv lands in the workspace header)
-  auto launch_panel = [&](int j0, int jb, cudaStream_t s) -> int {
+  auto launch_panel = [&](int j0, int jb, cudaStream_t s, int ipiv_off = 0) -> int {
     const int R = M - j0;
     // Rows per CTA.  Fewer, fuller CTAs leave more SMs wholly to the bulk GEMMs (a panel CTA takes half the register
     // file, so a GEMM runs at half occupancy next to it) and the in-panel look-ahead hides their longer update; near
@@ -1032,7 +1034,13 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
     static const int rpc_div = getenv("LA_LU_RPC_DIV") ? atoi(getenv("LA_LU_RPC_DIV")) : 64;
     int rpc = (R + sms - 1) / sms;
     int want = R / rpc_div;
-    if (want > rpc_min) want = rpc_min;
+    int rpc_cap = rpc_min;
+    if (jb <= MAX_NB / 2 && !exact) {  // a 64-wide half panel holds twice the rows in the same shared memory
+      const int fit = (int)(PANEL_SMEM_BUDGET / ((size_t)(jb | 1) * sizeof(T))) / 8 * 8;
+      rpc_cap = 2 * rpc_min < fit ? 2 * rpc_min : fit;
+      want = 2 * want;
+    }
+    if (want > rpc_cap) want = rpc_cap;
     if (want < 8) want = 8;  // at least one row per warp
     if (rpc < want) rpc = want;
     const int G = (R + rpc - 1) / rpc;
@@ -1042,15 +1050,16 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
     int mm = M, jj0 = j0, jjb = jb, rr = rpc;
     void* wsb = ws_base;
     unsigned ep = ++epoch;  // distinguishes this panel's flagged words from every earlier panel's
-    void* args[] = {&a, &ld, &mm, &jj0, &jjb, &rr, &wsb, &ep};
+    int ioff = ipiv_off;
+    void* args[] = {&a, &ld, &mm, &jj0, &jjb, &rr, &wsb, &ep, &ioff};
     const void* fn = exact ? (const void*)lu_panel_kernel<T, true> : (const void*)lu_panel_kernel<T, false>;
     LA_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PANEL_THREADS), args, smem, s));
     G_cur = G;
     return LA_OK;
   };
   // net permutation + piv / sign bookkeeping of the panel just factored
-  auto launch_perm = [&](int j0, int jb, int parity, cudaStream_t s) -> int {
-    lu_perm_kernel<T><<<1, 2 * MAX_NB, 0, s>>>(ws_base, G_cur, parity, j0, jb, piv_dev, sign_dev);
+  auto launch_perm = [&](int j0, int jb, int parity, cudaStream_t s, int ipiv_off = 0, int update_piv = 1) -> int {
+    lu_perm_kernel<T><<<1, 2 * MAX_NB, 0, s>>>(ws_base, G_cur, parity, j0, jb, piv_dev, sign_dev, ipiv_off, update_piv);
     LA_CUDA_TRY(cudaGetLastError());
     return LA_OK;
   };
@@ -1154,7 +1163,26 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
         mark(sp);  // [2] next panel's columns interchanged, U12 solved
         LA_TRY(trailing(c1, c2, sp));
         mark(sp);  // [3] next panel's columns updated
-        LA_TRY(launch_panel(c1, nb2, sp));
+        // While the trailing matrix is tall the bulk GEMM is the critical path and the panel costs it SMs (its CTAs are
+        // exclusive on their SMs because of their shared memory): factor the panel as two 64-wide halves -- half the
+        // shared memory per row, half the SMs -- with the half-panel head/update in between.  The net effect on the 128
+        // columns is that of one panel; the 128 pivots land in ipiv[0..128) for the usual perm/head/bulk of the next step.
+        static const int split_rows = getenv("LA_LU_SPLIT_ROWS") ? atoi(getenv("LA_LU_SPLIT_ROWS")) : 6144;  // 0 = never
+        if (split_rows > 0 && nb2 == MAX_NB && M - c1 >= split_rows) {
+          const int h = MAX_NB / 2, cm = c1 + h;
+          LA_TRY(launch_panel(c1, h, sp, 0));
+          LA_TRY(launch_perm(c1, h, 2, sp, 0, 0));
+          lu_head_kernel<T><<<(h + HEAD_COLS - 1) / HEAD_COLS, 256, HEAD_SMEM, sp>>>(LU, n, c1, h, cm, c2, ws_base, G_cur, 2);
+          LA_CUDA_TRY(cudaGetLastError());
+          if (cm < M)
+            LA_TRY(gemm_f64_tensor(A + (size_t)cm * ld + c1, ld, A + (size_t)c1 * ld + cm, ld, A + (size_t)cm * ld + cm, ld,
+                                   (size_t)(M - cm), (size_t)h, (size_t)h, LA_GEMM_SUB, sp));
+          LA_TRY(launch_panel(cm, h, sp, h));
+          LA_TRY(launch_perm(cm, h, 3, sp, h, 0));
+          LA_TRY(launch_swap(c1, cm, cm, cm, 3, sp));  // the second half's interchanges on the first half's columns
+        } else {
+          LA_TRY(launch_panel(c1, nb2, sp));
+        }
       } else {
         mark(sp);
         mark(sp);
