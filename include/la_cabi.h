@@ -53,6 +53,15 @@ enum {
   LA_GEMM_ADD = 2     /* C += P   (K-panel pipelined multi-GPU Mul)                       */
 };
 
+/* Arithmetic of the fp32 tensor-core Mul (la_set_gemm_f32_mode).  The reference's fp32 Mul is exact fp32 arithmetic
+ * (src/matrix/mod.rs:965-973 with T = f32), so the DEFAULT is the split-compensated form. */
+enum {
+  LA_F32_3XTF32 = 0, /* default: every operand split into TF32 big + small parts, three tcgen05 passes, fp32 accumulate:
+                        relative error ~1e-6 of |A||B| (fp32-grade), about a third of the TF32 rate               */
+  LA_F32_TF32 = 1    /* opt-in: inputs rounded to TF32 (10 mantissa bits, ~1e-3 of |A||B|), full tensor rate; used
+                        only for k >= 32 where BASELINE's 1e-4*k bar covers it                                     */
+};
+
 typedef struct la_buf la_buf; /* opaque device buffer handle */
 
 /* ---- library / device ---------------------------------------------------------------------------- */
@@ -92,6 +101,46 @@ LA_API int la_gemm_f64_dev(const double* A, size_t lda, const double* B, size_t 
                            size_t m, size_t k, size_t n, int mode, void* cuda_stream);
 LA_API int la_gemm_f32_dev(const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc,
                            size_t m, size_t k, size_t n, int mode, void* cuda_stream);
+
+/* ---- multi-GPU Mul: the same product, src/matrix/mod.rs:957-980, at N GPUs of one node.  GPU g owns
+ *      a row block of A and C; rank q owns a COLUMN block of B (it uploads / produces only that) inside its full-size
+ *      replica, and every rank pulls the other blocks over NVLink with the library's own kernel (peer-mapped loads,
+ *      device-side ready/ack flags) while it already multiplies by the blocks it has.  No reduction: K is not split. ---- */
+/* one process, `ngpus` distinct devices, host operands; synchronous.  Small products run on devices[0] alone. */
+LA_API int la_gemm_f64_mg(int ngpus, const int* devices, const double* A, const double* B, double* C, size_t m, size_t k,
+                          size_t n);
+LA_API int la_gemm_f32_mg(int ngpus, const int* devices, const float* A, const float* B, float* C, size_t m, size_t k,
+                          size_t n);
+/* One process per GPU (torchrun / MPI style).  Each rank creates a context (it allocates the rank's replica of B,
+ * k x n, row-major), publishes LA_MG_HANDLE_BYTES of handle, and connects with all ranks' handles in rank order (the
+ * launcher moves the bytes: MPI_Allgather, torch.distributed.all_gather, a file ...).  la_mg_shard is the partition
+ * every rank must agree on -- pure arithmetic, callable without a device: rows [row0,row1) of A and C, columns
+ * [col0,col1) of B. */
+#define LA_MG_HANDLE_BYTES 256
+typedef struct la_mg la_mg;
+LA_API int la_mg_shard(int nranks, int rank, size_t m, size_t n, size_t elem_bytes, size_t* row0, size_t* row1,
+                       size_t* col0, size_t* col1);
+LA_API int la_mg_create(int rank, int nranks, int device, size_t elem_bytes, size_t k, size_t n, la_mg** out);
+LA_API int la_mg_handle(const la_mg* ctx, void* handle_out /* LA_MG_HANDLE_BYTES */);
+LA_API int la_mg_connect(la_mg* ctx, const void* handles /* nranks * LA_MG_HANDLE_BYTES, rank order */);
+LA_API int la_mg_destroy(la_mg* ctx);
+/* where this rank's column block lives: *block_dev = &replica[0][col0], leading dimension *ldb (= n) elements */
+LA_API int la_mg_b_block(const la_mg* ctx, void** block_dev, size_t* ldb, size_t* col0, size_t* col1);
+/* C_shard[m_local x n] = A_shard[m_local x k] * B, all device-resident; the rank's own column block must already be in
+ * its replica (written earlier on `cuda_stream`).  Collective: every rank calls it once per product.  Asynchronous. */
+LA_API int la_gemm_f64_mg_rank(la_mg* ctx, const double* A_shard, size_t lda, double* C_shard, size_t ldc, size_t m_local,
+                               void* cuda_stream);
+LA_API int la_gemm_f32_mg_rank(la_mg* ctx, const float* A_shard, size_t lda, float* C_shard, size_t ldc, size_t m_local,
+                               void* cuda_stream);
+/* host shards: A rows (tight), the rank's column block of B (k rows, leading dimension ldb elements), C rows out (tight).
+ * Uploads, pulls, multiplies and downloads in one pipeline; synchronous. */
+LA_API int la_gemm_f64_mg_rank_host(la_mg* ctx, const double* A_shard, const double* B_block, size_t ldb, double* C_shard,
+                                    size_t m_local);
+LA_API int la_gemm_f32_mg_rank_host(la_mg* ctx, const float* A_shard, const float* B_block, size_t ldb, float* C_shard,
+                                    size_t m_local);
+/* Before a rank rewrites its column block IN PLACE for the next product: makes `cuda_stream` wait until every peer has
+ * finished pulling the block of the previous product. */
+LA_API int la_mg_quiesce(la_mg* ctx, void* cuda_stream);
 
 /* ---- LU: replaces `LUDecomposition::new` (src/decomp/lu.rs:104-168).  Factorises IN PLACE the m x n
  *      row-major matrix in `LU` (the caller clones A first, lu.rs:105).  Outputs: packed L\U, the permutation
@@ -168,6 +217,12 @@ LA_API int la_permute_rows_f32(const la_buf* src, size_t rows, size_t cols, cons
  * element i of dst gets hash(seed, first_idx + i).  Device pointers; asynchronous on `cuda_stream`. */
 LA_API int la_fill_hash_f64_dev(double* dst, size_t count, uint64_t seed, uint64_t first_idx, void* cuda_stream);
 LA_API int la_fill_hash_f32_dev(float* dst, size_t count, uint64_t seed, uint64_t first_idx, void* cuda_stream);
+
+/* Process-wide accuracy mode of the fp32 tensor-core product (LA_F32_*; initial value from the environment variable
+ * LA_GEMM_F32_MODE = "3xtf32" | "tf32").  Products that are small (m*n*k <= 128^3), unaligned or LA_GEMM_SUB always run
+ * the exact reference-order CUDA-core kernel, whatever the mode. */
+LA_API int la_set_gemm_f32_mode(int mode);
+LA_API int la_get_gemm_f32_mode(int* out);
 
 /* Test hooks (not part of the drop-in surface).  fp64: 0 = automatic kernel choice, 1 = force the generic CUDA-core GEMM,
  * 2 = force the TMA/DMMA GEMM (fails with LA_ERR_INVALID when the operands are not TMA-addressable), 3 / 4 = force its

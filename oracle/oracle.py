@@ -92,6 +92,18 @@ def fill(shape, seed, dtype=np.float64, first_idx=0):
     return out
 
 
+def fill_block(row0, rows, col0, cols, ld, seed, dtype=np.float64):
+    """Rows [row0, row0+rows) x columns [col0, col0+cols) of the synthetic matrix with row length `ld` (element (i, j) is
+    hash(seed, i * ld + j)): lets a checker rebuild a window of a 32768 x 32768 operand without the 8 GiB whole."""
+    out = np.empty((rows, cols), dtype=dtype)
+    f = getattr(lib(), f"oracle_fill_{_suf(dtype)}")
+    isz = out.itemsize
+    base = out.ctypes.data
+    for i in range(rows):
+        f(_p(base + i * cols * isz), cols, seed, (row0 + i) * ld + col0)
+    return out
+
+
 def gemm(a, b, form="fast"):
     """C = A*B in the reference's per-element order (src/matrix/mod.rs:957-980)."""
     a = np.ascontiguousarray(a)

@@ -15,7 +15,15 @@ struct la_buf {
 namespace la {
 void debug_set_gemm_path(int p);
 void debug_set_gemm_f32_path(int p);
+int set_gemm_f32_mode(int mode);
+int get_gemm_f32_mode();
 }
+
+// *_dev entry points: the caller's stream on the CURRENT device (see CallScope)
+#define DEV_SCOPE(stream_arg)                  \
+  int _scope_dev = -1;                         \
+  if (cudaGetDevice(&_scope_dev) != cudaSuccess) { cudaGetLastError(); _scope_dev = -1; } \
+  la::CallScope _scope(_scope_dev, la::resolve_stream(stream_arg))
 
 namespace {
 
@@ -61,6 +69,7 @@ int gemm_bufs(const la_buf* A, const la_buf* B, la_buf* C, size_t m, size_t k, s
   LA_REQUIRE(C->ptr != A->ptr && C->ptr != B->ptr, "la_gemm: output aliases an input");
   DeviceGuard g;
   LA_TRY(g.enter(A->device));
+  CallScope scope(A->device, cudaStreamPerThread);
   return gemm_dev<T>((const T*)A->ptr, k, (const T*)B->ptr, n, (T*)C->ptr, n, m, k, n, LA_GEMM_ASSIGN,
                      cudaStreamPerThread);
 }
@@ -78,6 +87,7 @@ int gemm_host(const T* A, const T* B, T* C, size_t m, size_t k, size_t n) {
              "la_gemm_host: size overflow");
   const DeviceCtx* ctx;
   LA_TRY(current_device_ctx(&ctx));
+  CallScope scope(ctx->device, cudaStreamPerThread);
   void *dA, *dB, *dC;
   LA_TRY(scratch_get(ctx->device, 0, ba, &dA));
   LA_TRY(scratch_get(ctx->device, 1, bb, &dB));
@@ -196,6 +206,7 @@ int lu_factor_buf(la_buf* LU, size_t m, size_t n, uint64_t* piv_out, int* pospiv
   uint64_t* piv_dev = (uint64_t*)meta;
   int* sign_dev = (int*)(piv_dev + m);
   cudaStream_t st = cudaStreamPerThread;
+  CallScope scope(LU->device, st);
   LA_TRY(lu_factor_dev<T>((T*)LU->ptr, m, n, piv_dev, sign_dev, st));
   LA_CUDA_TRY(cudaMemcpyAsync(piv_out, piv_dev, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, st));
   LA_CUDA_TRY(cudaMemcpyAsync(pospivsign_out, sign_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -217,6 +228,7 @@ int lu_factor_host(const T* A, T* LU_out, size_t m, size_t n, uint64_t* piv_out,
   uint64_t* piv_dev = (uint64_t*)meta;
   int* sign_dev = (int*)(piv_dev + m);
   cudaStream_t st = cudaStreamPerThread;
+  CallScope scope(ctx->device, st);
   LA_CUDA_TRY(cudaMemcpyAsync(dLU, A, bytes, cudaMemcpyHostToDevice, st));  // == ludata = a.get_data().clone()
   LA_TRY(lu_factor_dev<T>((T*)dLU, m, n, piv_dev, sign_dev, st));
   LA_CUDA_TRY(cudaMemcpyAsync(LU_out, dLU, bytes, cudaMemcpyDeviceToHost, st));
@@ -240,6 +252,7 @@ int lu_solve_buf(const la_buf* LU, size_t m, size_t n, const uint64_t* piv, cons
   void* meta;
   LA_TRY(scratch_get(LU->device, 3, sizeof(uint64_t) * n + 64, &meta));
   cudaStream_t st = cudaStreamPerThread;
+  CallScope scope(LU->device, st);
   LA_CUDA_TRY(cudaMemcpyAsync(meta, piv, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, st));
   LA_TRY(lu_solve_dev<T>((const T*)LU->ptr, n, (const uint64_t*)meta, (const T*)B->ptr, nx, (T*)X->ptr, st));
   LA_CUDA_TRY(cudaStreamSynchronize(st));
@@ -262,6 +275,7 @@ int lu_solve_host(const T* LU, size_t m, size_t n, const uint64_t* piv, const T*
   LA_TRY(scratch_get(ctx->device, 2, bx, &dX));
   LA_TRY(scratch_get(ctx->device, 3, sizeof(uint64_t) * n + 64, &meta));
   cudaStream_t st = cudaStreamPerThread;
+  CallScope scope(ctx->device, st);
   LA_CUDA_TRY(cudaMemcpyAsync(dLU, LU, bl, cudaMemcpyHostToDevice, st));
   LA_CUDA_TRY(cudaMemcpyAsync(dB, B, bx, cudaMemcpyHostToDevice, st));
   LA_CUDA_TRY(cudaMemcpyAsync(meta, piv, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, st));
@@ -300,6 +314,7 @@ int permute_rows_buf(const la_buf* src, size_t rows, size_t cols, const uint64_t
   void* meta;
   LA_TRY(scratch_get(src->device, 3, sizeof(uint64_t) * out_rows + 64, &meta));
   cudaStream_t st = cudaStreamPerThread;
+  CallScope scope(src->device, st);
   LA_CUDA_TRY(cudaMemcpyAsync(meta, idx, sizeof(uint64_t) * out_rows, cudaMemcpyHostToDevice, st));
   LA_TRY(permute_rows_dev<T>((const T*)src->ptr, (T*)dst->ptr, (const uint64_t*)meta, out_rows, cols, st));
   LA_CUDA_TRY(cudaStreamSynchronize(st));  // `idx` is the caller's (pageable) memory
@@ -319,6 +334,7 @@ int chol_factor_buf(la_buf* A, size_t n, int* ok_out) {
   void* meta;
   LA_TRY(scratch_get(A->device, 3, 64, &meta));
   cudaStream_t st = cudaStreamPerThread;
+  CallScope scope(A->device, st);
   LA_TRY(chol_factor_dev<T>((T*)A->ptr, n, (int*)meta, st));
   int flags[2] = {0, 0};
   LA_CUDA_TRY(cudaMemcpyAsync(flags, meta, sizeof(flags), cudaMemcpyDeviceToHost, st));
@@ -337,6 +353,7 @@ int chol_factor_host(const T* A, T* L_out, size_t n, int* ok_out) {
   LA_TRY(scratch_get(ctx->device, 0, bytes, &dA));
   LA_TRY(scratch_get(ctx->device, 3, 64, &meta));
   cudaStream_t st = cudaStreamPerThread;
+  CallScope scope(ctx->device, st);
   LA_CUDA_TRY(cudaMemcpyAsync(dA, A, bytes, cudaMemcpyHostToDevice, st));
   LA_TRY(chol_factor_dev<T>((T*)dA, n, (int*)meta, st));
   int flags[2] = {0, 0};
@@ -357,6 +374,7 @@ int chol_solve_buf(const la_buf* L, size_t n, const la_buf* B, size_t nx, la_buf
   DeviceGuard g;
   LA_TRY(g.enter(L->device));
   cudaStream_t st = cudaStreamPerThread;
+  CallScope scope(L->device, st);
   LA_TRY(chol_solve_dev<T>((const T*)L->ptr, n, (const T*)B->ptr, nx, (T*)X->ptr, st));
   LA_CUDA_TRY(cudaStreamSynchronize(st));
   return LA_OK;
@@ -373,6 +391,7 @@ int chol_solve_host(const T* L, size_t n, const T* B, size_t nx, T* X) {
   LA_TRY(scratch_get(ctx->device, 1, bx, &dB));
   LA_TRY(scratch_get(ctx->device, 2, bx, &dX));
   cudaStream_t st = cudaStreamPerThread;
+  CallScope scope(ctx->device, st);
   LA_CUDA_TRY(cudaMemcpyAsync(dL, L, bl, cudaMemcpyHostToDevice, st));
   LA_CUDA_TRY(cudaMemcpyAsync(dB, B, bx, cudaMemcpyHostToDevice, st));
   LA_TRY(chol_solve_dev<T>((const T*)dL, n, (const T*)dB, nx, (T*)dX, st));
@@ -498,10 +517,12 @@ int la_gemm_i64_host(const int64_t* A, const int64_t* B, int64_t* C, size_t m, s
 }
 int la_gemm_f64_dev(const double* A, size_t lda, const double* B, size_t ldb, double* C, size_t ldc, size_t m, size_t k,
                     size_t n, int mode, void* stream) {
+  DEV_SCOPE(stream);
   return gemm_f64_dev(A, lda, B, ldb, C, ldc, m, k, n, mode, resolve_stream(stream));
 }
 int la_gemm_f32_dev(const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, size_t m, size_t k,
                     size_t n, int mode, void* stream) {
+  DEV_SCOPE(stream);
   return gemm_f32_dev(A, lda, B, ldb, C, ldc, m, k, n, mode, resolve_stream(stream));
 }
 
@@ -518,9 +539,11 @@ int la_lu_factor_f32_host(const float* A, float* LU_out, size_t m, size_t n, uin
   return lu_factor_host<float>(A, LU_out, m, n, piv_out, sign_out);
 }
 int la_lu_factor_f64_dev(double* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, void* stream) {
+  DEV_SCOPE(stream);
   return lu_factor_dev<double>(LU, m, n, piv_dev, sign_dev, resolve_stream(stream));
 }
 int la_lu_factor_f32_dev(float* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, void* stream) {
+  DEV_SCOPE(stream);
   return lu_factor_dev<float>(LU, m, n, piv_dev, sign_dev, resolve_stream(stream));
 }
 
@@ -563,10 +586,12 @@ int la_lu_solve_f32_host(const float* LU, size_t m, size_t n, const uint64_t* pi
 }
 int la_lu_solve_f64_dev(const double* LU, size_t n, const uint64_t* piv_dev, const double* B, size_t nx, double* X,
                         void* stream) {
+  DEV_SCOPE(stream);
   return lu_solve_dev<double>(LU, n, piv_dev, B, nx, X, resolve_stream(stream));
 }
 int la_lu_solve_f32_dev(const float* LU, size_t n, const uint64_t* piv_dev, const float* B, size_t nx, float* X,
                         void* stream) {
+  DEV_SCOPE(stream);
   return lu_solve_dev<float>(LU, n, piv_dev, B, nx, X, resolve_stream(stream));
 }
 
@@ -603,15 +628,19 @@ int la_chol_factor_f32_host(const float* A, float* L_out, size_t n, int* ok_out)
   return chol_factor_host<float>(A, L_out, n, ok_out);
 }
 int la_chol_factor_f64_dev(double* A, size_t n, int* flags_dev, void* stream) {
+  DEV_SCOPE(stream);
   return chol_factor_dev<double>(A, n, flags_dev, resolve_stream(stream));
 }
 int la_chol_factor_f32_dev(float* A, size_t n, int* flags_dev, void* stream) {
+  DEV_SCOPE(stream);
   return chol_factor_dev<float>(A, n, flags_dev, resolve_stream(stream));
 }
 int la_chol_solve_f64_dev(const double* L, size_t n, const double* B, size_t nx, double* X, void* stream) {
+  DEV_SCOPE(stream);
   return chol_solve_dev<double>(L, n, B, nx, X, resolve_stream(stream));
 }
 int la_chol_solve_f32_dev(const float* L, size_t n, const float* B, size_t nx, float* X, void* stream) {
+  DEV_SCOPE(stream);
   return chol_solve_dev<float>(L, n, B, nx, X, resolve_stream(stream));
 }
 int la_chol_solve_f64(const la_buf* L, size_t n, const la_buf* B, size_t nx, la_buf* X) {
@@ -631,6 +660,13 @@ int la_fill_hash_f64_dev(double* dst, size_t count, uint64_t seed, uint64_t firs
 }
 int la_fill_hash_f32_dev(float* dst, size_t count, uint64_t seed, uint64_t first_idx, void* stream) {
   return fill_hash_dev<float>(dst, count, seed, first_idx, resolve_stream(stream));
+}
+
+int la_set_gemm_f32_mode(int mode) { return la::set_gemm_f32_mode(mode); }
+int la_get_gemm_f32_mode(int* out) {
+  LA_REQUIRE(out, "la_get_gemm_f32_mode: null output");
+  *out = la::get_gemm_f32_mode();
+  return LA_OK;
 }
 
 /* test hook: 0 = automatic kernel choice, 1 = force the CUDA-core kernel, 2 = force the TMA/DMMA kernel */

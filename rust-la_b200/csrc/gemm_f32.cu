@@ -19,6 +19,7 @@
 // persistent (one CTA per SM) with two accumulators in TMEM, and C leaves through swizzled shared memory and TMA
 // stores (full 32-byte sectors; the first version's per-lane 16-byte stores made L2 read-fill every sector of C).
 #include <stdlib.h>
+#include <string.h>
 
 #include "la_common.cuh"
 
@@ -119,7 +120,9 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
 template <int MODE>
 __global__ void __launch_bounds__(TF32_THREADS, 1)
 gemm_f32_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int tiles_m, int tiles_n, int group_m) {
+                     const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                     const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int tiles_m, int tiles_n, int group_m,
+                     int kpasses) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* out_stage = smem + TSTAGES * TSTAGE_BYTES;                     // [4 warps][2][32 rows x 128 B], 1024-aligned
@@ -130,7 +133,11 @@ gemm_f32_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ktiles = (K + TBK - 1) / TBK;
+  const int ktiles1 = (K + TBK - 1) / TBK;
+  // kpasses == 3 (split-compensated "3xTF32"): the K loop runs three times over operand pairs
+  //   (A_small, B_big), (A_big, B_small), (A_big, B_big)   with tmA = A_big, tmA1 = A_small, tmB = B_big^T, tmB1 = B_small^T
+  // into the same fp32 accumulator -- the small terms first, so they are summed at full relative precision.
+  const int ktiles = ktiles1 * kpasses;
   const int ntiles = tiles_m * tiles_n;
 
   if (threadIdx.x == 0) {
@@ -159,6 +166,10 @@ gemm_f32_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (lane == 0) {
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
+      if (kpasses > 1) {
+        tma_prefetch_desc(&tmA1);
+        tma_prefetch_desc(&tmB1);
+      }
       uint32_t g = 0;  // k-tiles issued so far (ring position)
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int tile_m, tile_n;
@@ -169,8 +180,10 @@ gemm_f32_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           uint8_t* sA = smem + s * TSTAGE_BYTES;
           uint8_t* sB = sA + TA_BYTES;
           mbar_arrive_expect_tx(&full[s], TSTAGE_BYTES);
-          tma_load_2d(sA, &tmA, &full[s], kt * TBK, tile_m * TBM);  // 32 k (inner, 128 B) x 128 rows
-          tma_load_2d(sB, &tmB, &full[s], kt * TBK, tile_n * TBN);  // B^T: 32 k (inner, 128 B) x 256 n-rows
+          const int pass = (kpasses > 1) ? kt / ktiles1 : 2;  // 0: small x big, 1: big x small, 2: big x big
+          const int kc = (kt - (kpasses > 1 ? pass * ktiles1 : 0)) * TBK;
+          tma_load_2d(sA, pass == 0 ? &tmA1 : &tmA, &full[s], kc, tile_m * TBM);  // 32 k (inner, 128 B) x 128 rows
+          tma_load_2d(sB, pass == 1 ? &tmB1 : &tmB, &full[s], kc, tile_n * TBN);  // B^T: 32 k (inner, 128 B) x 256 n-rows
         }
       }
     }
@@ -254,9 +267,25 @@ gemm_f32_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+// Split of an fp32 value for the compensated ("3xTF32") product: big = x rounded to TF32 (10 explicit mantissa bits, so
+// the tensor core's own input conversion is the identity on it), small = x - big (exact in fp32; the tensor core keeps
+// its leading 11 bits).  x*y ~= big_x*big_y + big_x*small_y + small_x*big_y with relative error ~2^-21 per product.
+__device__ __forceinline__ void split_tf32(float x, float& big, float& small) {
+  const uint32_t u = __float_as_uint(x);
+  if ((u & 0x7f800000u) == 0x7f800000u) {  // inf / nan travel in the big part
+    big = x;
+    small = 0.0f;
+    return;
+  }
+  big = __uint_as_float((u + 0x1000u) & 0xffffe000u);  // round to nearest (ties away) at bit 13
+  small = x - big;
+}
+
 // B^T[n][k] = B[k][n] through 32 x 33 shared-memory tiles: both the read and the write are coalesced 128-byte rows.
+// SPLIT also writes the small parts (second destination).
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restrict__ B, size_t ldb, float* __restrict__ BT,
-                                                            size_t ldt, int K, int N) {
+                                                            float* __restrict__ BT_small, size_t ldt, int K, int N) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -269,21 +298,63 @@ __global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restr
 #pragma unroll
   for (int r = 0; r < 32; r += 8) {
     const int nn = n0 + ty + r, kk = k0 + tx;
-    if (nn < N && kk < K) BT[(size_t)nn * ldt + kk] = tile[tx][ty + r];
+    if (nn < N && kk < K) {
+      const float x = tile[tx][ty + r];
+      if (SPLIT) {
+        float b, s;
+        split_tf32(x, b, s);
+        BT[(size_t)nn * ldt + kk] = b;
+        BT_small[(size_t)nn * ldt + kk] = s;
+      } else {
+        BT[(size_t)nn * ldt + kk] = x;
+      }
+    }
+  }
+}
+
+// A -> (A_big, A_small), same row-major shape, leading dimension ldo
+__global__ void __launch_bounds__(256) split_f32_kernel(const float* __restrict__ A, size_t lda, float* __restrict__ big,
+                                                        float* __restrict__ small, size_t ldo, size_t M, size_t K) {
+  const size_t k4 = (K + 3) / 4;  // groups of four columns
+  const size_t total = M * k4;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = e / k4, c = (e - r * k4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c + 4 <= K) {
+      v = *reinterpret_cast<const float4*>(A + r * lda + c);  // lda % 4 == 0 and A 16-byte aligned (tensor-path precondition)
+    } else {
+      v.x = A[r * lda + c];
+      if (c + 1 < K) v.y = A[r * lda + c + 1];
+      if (c + 2 < K) v.z = A[r * lda + c + 2];
+    }
+    float4 b, s;
+    split_tf32(v.x, b.x, s.x);
+    split_tf32(v.y, b.y, s.y);
+    split_tf32(v.z, b.z, s.z);
+    split_tf32(v.w, b.w, s.w);
+    *reinterpret_cast<float4*>(big + r * ldo + c) = b;  // ldo is a multiple of 4: the padded tail is ours to write
+    *reinterpret_cast<float4*>(small + r * ldo + c) = s;
   }
 }
 
 int g_f32_path = getenv("LA_GEMM_F32_PATH") ? atoi(getenv("LA_GEMM_F32_PATH")) : 0;  // 0 auto, 1 CUDA-core, 2 tcgen05
+// Accuracy mode of the tensor path: LA_F32_3XTF32 (default, fp32-grade) or LA_F32_TF32 (opt-in, 10-bit inputs)
+int initial_f32_mode() {
+  const char* e = getenv("LA_GEMM_F32_MODE");
+  if (e && (!strcmp(e, "tf32") || !strcmp(e, "1"))) return LA_F32_TF32;
+  return LA_F32_3XTF32;
+}
+int g_f32_mode = initial_f32_mode();
 
 template <int MODE>
-int launch_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K, int sms,
-                cudaStream_t st) {
+int launch_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA1, const CUtensorMap& tmB1,
+                const CUtensorMap& tmC, int M, int N, int K, int kpasses, int sms, cudaStream_t st) {
   LA_CUDA_TRY(cudaFuncSetAttribute(gemm_f32_tf32_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF32_SMEM));
   const int tiles_m = (M + TBM - 1) / TBM, tiles_n = (N + TBN - 1) / TBN;
   const int ntiles = tiles_m * tiles_n;
   static const int group_m = getenv("LA_TF32_GROUP_M") ? atoi(getenv("LA_TF32_GROUP_M")) : 16;  // tuning knob
-  gemm_f32_tf32_kernel<MODE><<<ntiles < sms ? ntiles : sms, TF32_THREADS, TF32_SMEM, st>>>(tmA, tmB, tmC, M, N, K, tiles_m,
-                                                                                         tiles_n, group_m);
+  gemm_f32_tf32_kernel<MODE><<<ntiles < sms ? ntiles : sms, TF32_THREADS, TF32_SMEM, st>>>(
+      tmA, tmB, tmA1, tmB1, tmC, M, N, K, tiles_m, tiles_n, group_m, kpasses);
   LA_CUDA_TRY(cudaGetLastError());
   return LA_OK;
 }
@@ -291,6 +362,12 @@ int launch_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
 }  // namespace
 
 void debug_set_gemm_f32_path(int p) { g_f32_path = p; }
+int set_gemm_f32_mode(int mode) {
+  LA_REQUIRE(mode == LA_F32_3XTF32 || mode == LA_F32_TF32, "la_set_gemm_f32_mode: bad mode %d", mode);
+  g_f32_mode = mode;
+  return LA_OK;
+}
+int get_gemm_f32_mode() { return g_f32_mode; }
 
 int gemm_f32_dev(const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, size_t m, size_t k,
                  size_t n, int mode, cudaStream_t st) {
@@ -305,7 +382,10 @@ int gemm_f32_dev(const float* A, size_t lda, const float* B, size_t ldb, float* 
   const bool aligned = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0) &&
                        lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0;
   const bool small = (double)m * (double)n * (double)k <= 128.0 * 128.0 * 128.0;  // bit-exact reference-order kernel
-  bool use_tc = aligned && !small && k >= TF32_MIN_K && mode != LA_GEMM_SUB;
+  const int acc_mode = g_f32_mode;
+  // plain TF32 rounds the inputs to 10 mantissa bits: only when the caller opted in, and only where the 1e-4*k parity bar
+  // covers it (k >= 32).  The split-compensated mode is fp32-grade and has no such floor.
+  bool use_tc = aligned && !small && mode != LA_GEMM_SUB && (acc_mode == LA_F32_3XTF32 || k >= TF32_MIN_K);
   if (g_f32_path == 1) use_tc = false;
   if (g_f32_path == 2) {
     if (!aligned || mode == LA_GEMM_SUB)
@@ -314,25 +394,53 @@ int gemm_f32_dev(const float* A, size_t lda, const float* B, size_t ldb, float* 
   }
   if (!use_tc) return gemm_simt<float>(A, lda, B, ldb, C, ldc, m, k, n, mode, st);
 
-  // B^T into scratch (K-major operand for the tensor core), leading dimension padded to 16 bytes
+  // B^T into scratch (K-major operand for the tensor core), leading dimension padded to 16 bytes.  In the compensated
+  // mode the same pass also writes the small parts, and A is split into (big, small) by a streaming kernel.
+  const bool comp = acc_mode == LA_F32_3XTF32;
   const size_t ldt = (k + 3) & ~(size_t)3;
   void* bt = nullptr;
-  LA_TRY(scratch_get(ctx->device, 12, n * ldt * sizeof(float), &bt));
+  LA_TRY(scratch_get(ctx->device, 12, (comp ? 2 : 1) * n * ldt * sizeof(float), &bt));
+  float* bt_big = (float*)bt;
+  float* bt_small = comp ? bt_big + n * ldt : nullptr;
   {
     dim3 grid((unsigned)((n + 31) / 32), (unsigned)((k + 31) / 32));
     LA_REQUIRE(grid.y <= 65535, "la_gemm_f32: inner dimension too large for the transpose grid");
-    transpose_f32_kernel<<<grid, 256, 0, st>>>(B, ldb, (float*)bt, ldt, (int)k, (int)n);
+    if (comp) transpose_f32_kernel<true><<<grid, 256, 0, st>>>(B, ldb, bt_big, bt_small, ldt, (int)k, (int)n);
+    else transpose_f32_kernel<false><<<grid, 256, 0, st>>>(B, ldb, bt_big, nullptr, ldt, (int)k, (int)n);
     LA_CUDA_TRY(cudaGetLastError());
   }
-  CUtensorMap tmA, tmB;
-  LA_TRY(encode_tensor_map_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, k, m, lda * 4, TBK, TBM,
+  const float* a_big = A;
+  const float* a_small = A;
+  size_t ld_a = lda;
+  if (comp) {
+    void* as = nullptr;
+    LA_TRY(scratch_get(ctx->device, 20, 2 * m * ldt * sizeof(float), &as));
+    float* ab = (float*)as;
+    float* asml = ab + m * ldt;
+    size_t blocks = (m * (ldt / 4) + 255) / 256;
+    const size_t cap = (size_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    split_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, lda, ab, asml, ldt, m, k);
+    LA_CUDA_TRY(cudaGetLastError());
+    a_big = ab;
+    a_small = asml;
+    ld_a = ldt;
+  }
+  CUtensorMap tmA, tmB, tmA1, tmB1;
+  LA_TRY(encode_tensor_map_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a_big, k, m, ld_a * 4, TBK, TBM,
                               CU_TENSOR_MAP_SWIZZLE_128B));
-  LA_TRY(encode_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, bt, k, n, ldt * 4, TBK, TBN,
+  LA_TRY(encode_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, bt_big, k, n, ldt * 4, TBK, TBN,
+                              CU_TENSOR_MAP_SWIZZLE_128B));
+  LA_TRY(encode_tensor_map_2d(&tmA1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a_small, k, m, ld_a * 4, TBK, TBM,
+                              CU_TENSOR_MAP_SWIZZLE_128B));
+  LA_TRY(encode_tensor_map_2d(&tmB1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, comp ? bt_small : bt_big, k, n, ldt * 4, TBK, TBN,
                               CU_TENSOR_MAP_SWIZZLE_128B));
   CUtensorMap tmC;  // store boxes: 32 columns (128 B) x 32 rows, same swizzle as the epilogue's shared-memory layout
   LA_TRY(encode_tensor_map_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, n, m, ldc * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
-  if (mode == LA_GEMM_ASSIGN) return launch_tf32<LA_GEMM_ASSIGN>(tmA, tmB, tmC, (int)m, (int)n, (int)k, ctx->sm_count, st);
-  return launch_tf32<LA_GEMM_ADD>(tmA, tmB, tmC, (int)m, (int)n, (int)k, ctx->sm_count, st);
+  const int kpasses = comp ? 3 : 1;
+  if (mode == LA_GEMM_ASSIGN)
+    return launch_tf32<LA_GEMM_ASSIGN>(tmA, tmB, tmA1, tmB1, tmC, (int)m, (int)n, (int)k, kpasses, ctx->sm_count, st);
+  return launch_tf32<LA_GEMM_ADD>(tmA, tmB, tmA1, tmB1, tmC, (int)m, (int)n, (int)k, kpasses, ctx->sm_count, st);
 }
 
 template <>

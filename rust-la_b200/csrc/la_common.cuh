@@ -50,6 +50,17 @@ cudaStream_t resolve_stream(void* s);               // NULL -> cudaStreamPerThre
 // Grow-only per-(thread,device) scratch used by the *_host entry points and the LU driver.
 int scratch_get(int device, int slot, size_t bytes, void** out);
 
+// The scratch pool, the LU / Cholesky side streams and their events are per (host thread, device), not per stream.  Two
+// library calls from one thread on DIFFERENT streams would therefore share them while both are in flight.  Every entry
+// point that queues work on a caller-visible stream opens a CallScope: when the stream differs from the one the thread's
+// previous call used on this device, the new stream first waits for that call's tail (one event per thread and device).
+struct CallScope {
+  int device;
+  cudaStream_t st;
+  CallScope(int device, cudaStream_t st);
+  ~CallScope();
+};
+
 // cuTensorMapEncodeTiled fetched through the runtime (no link-time libcuda dependency).
 int encode_tensor_map_2d(CUtensorMap* map, CUtensorMapDataType dtype, size_t elem_bytes, const void* base,
                          uint64_t inner, uint64_t outer, uint64_t row_stride_bytes, uint32_t box_inner,

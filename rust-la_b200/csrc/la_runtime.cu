@@ -120,6 +120,37 @@ int scratch_get(int device, int slot, size_t bytes, void** out) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// serialisation of successive calls of one host thread that use different streams (see CallScope in la_common.cuh)
+// ---------------------------------------------------------------------------------------------------
+struct CallTail {
+  cudaEvent_t ev = nullptr;
+  cudaStream_t last = nullptr;
+  bool valid = false;
+};
+static thread_local CallTail tl_tail[64];
+
+CallScope::CallScope(int device_, cudaStream_t st_) : device(device_), st(st_) {
+  if (device < 0 || device >= 64) return;
+  CallTail& t = tl_tail[device];
+  if (t.valid && t.last != st) cudaStreamWaitEvent(st, t.ev, 0);  // the previous call's tail, queued on another stream
+}
+CallScope::~CallScope() {
+  if (device < 0 || device >= 64) return;
+  CallTail& t = tl_tail[device];
+  if (!t.ev && cudaEventCreateWithFlags(&t.ev, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    t.ev = nullptr;
+    return;
+  }
+  if (cudaEventRecord(t.ev, st) == cudaSuccess) {
+    t.last = st;
+    t.valid = true;
+  } else {
+    cudaGetLastError();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // TMA descriptor encoding through the runtime's driver entry point lookup
 // ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

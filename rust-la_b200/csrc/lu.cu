@@ -1041,6 +1041,10 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
       want = 2 * want;
     }
     if (want > rpc_cap) want = rpc_cap;
+    // never more rows than the shared-memory budget holds (the bit-exact panel keeps a second array of deferred sums:
+    // a tall single-panel matrix such as 8000 x 128 would otherwise ask for 125 rows x 129 x 16 B = 258 KB)
+    const int fit_rows = (int)(PANEL_SMEM_BUDGET / ((size_t)(jb | 1) * sizeof(T) * (exact ? 2 : 1)));
+    if (want > fit_rows) want = fit_rows;
     if (want < 8) want = 8;  // at least one row per warp
     if (rpc < want) rpc = want;
     const int G = (R + rpc - 1) / rpc;

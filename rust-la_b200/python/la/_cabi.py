@@ -8,6 +8,7 @@ LIB_PATH = os.environ.get("LA_B200_LIB") or os.path.normpath(os.path.join(_PKG, 
 
 LA_OK, LA_ERR_INVALID, LA_ERR_CUDA, LA_ERR_NOMEM, LA_ERR_NO_DEVICE, LA_ERR_UNSUPPORTED = range(6)
 LA_GEMM_ASSIGN, LA_GEMM_SUB, LA_GEMM_ADD = 0, 1, 2
+LA_F32_3XTF32, LA_F32_TF32 = 0, 1
 
 
 class LaError(RuntimeError):
@@ -22,6 +23,8 @@ _i = ctypes.c_int
 _u64 = ctypes.c_uint64
 _pp = ctypes.POINTER(ctypes.c_void_p)
 _pi = ctypes.POINTER(ctypes.c_int)
+_psz = ctypes.POINTER(ctypes.c_size_t)
+LA_MG_HANDLE_BYTES = 256
 
 # name -> (argtypes, restype); the C header is the single source of truth, tests/test_cabi_symbols.py cross-checks it
 SIGNATURES = {
@@ -47,6 +50,19 @@ SIGNATURES = {
     "la_gemm_i64_host": ([_p, _p, _p, _sz, _sz, _sz], _i),
     "la_gemm_f64_dev": ([_p, _sz, _p, _sz, _p, _sz, _sz, _sz, _sz, _i, _p], _i),
     "la_gemm_f32_dev": ([_p, _sz, _p, _sz, _p, _sz, _sz, _sz, _sz, _i, _p], _i),
+    "la_gemm_f64_mg": ([_i, _pi, _p, _p, _p, _sz, _sz, _sz], _i),
+    "la_gemm_f32_mg": ([_i, _pi, _p, _p, _p, _sz, _sz, _sz], _i),
+    "la_mg_shard": ([_i, _i, _sz, _sz, _sz, _psz, _psz, _psz, _psz], _i),
+    "la_mg_create": ([_i, _i, _i, _sz, _sz, _sz, _pp], _i),
+    "la_mg_handle": ([_p, _p], _i),
+    "la_mg_connect": ([_p, _p], _i),
+    "la_mg_destroy": ([_p], _i),
+    "la_mg_b_block": ([_p, _pp, _psz, _psz, _psz], _i),
+    "la_gemm_f64_mg_rank": ([_p, _p, _sz, _p, _sz, _sz, _p], _i),
+    "la_gemm_f32_mg_rank": ([_p, _p, _sz, _p, _sz, _sz, _p], _i),
+    "la_gemm_f64_mg_rank_host": ([_p, _p, _p, _sz, _p, _sz], _i),
+    "la_gemm_f32_mg_rank_host": ([_p, _p, _p, _sz, _p, _sz], _i),
+    "la_mg_quiesce": ([_p, _p], _i),
     "la_lu_factor_f64": ([_p, _sz, _sz, _p, _pi], _i),
     "la_lu_factor_f32": ([_p, _sz, _sz, _p, _pi], _i),
     "la_lu_factor_f64_host": ([_p, _p, _sz, _sz, _p, _pi], _i),
@@ -83,6 +99,8 @@ SIGNATURES = {
     "la_permute_rows_f32": ([_p, _sz, _sz, _p, _sz, _p], _i),
     "la_fill_hash_f64_dev": ([_p, _sz, _u64, _u64, _p], _i),
     "la_fill_hash_f32_dev": ([_p, _sz, _u64, _u64, _p], _i),
+    "la_set_gemm_f32_mode": ([_i], _i),
+    "la_get_gemm_f32_mode": ([_pi], _i),
     "la_debug_set_gemm_path": ([_i], _i),
     "la_debug_set_gemm_f32_path": ([_i], _i),
 }

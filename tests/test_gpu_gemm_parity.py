@@ -49,8 +49,11 @@ def test_gemm_f32_host_api(oracle, shape):
 @pytest.mark.parametrize("shape", [(128, 32, 256), (512, 1024, 256), (1000, 520, 768), (640, 100, 328), (130, 64, 260),
                                    (2048, 1024, 2048), (256, 36, 512), (4096, 64, 4096), (3000, 40, 5000)])
 @pytest.mark.parametrize("mode", [0, 2])
-def test_gemm_f32_tcgen05_tf32(oracle, shape, mode):
-    """The tcgen05 kind::tf32 kernel (TMEM accumulators, TMA-fed), forced, vs the fp32 oracle: <= 1e-4 * k relative."""
+@pytest.mark.parametrize("acc", ["3xtf32", "tf32"])
+def test_gemm_f32_tcgen05_tf32(oracle, shape, mode, acc):
+    """The tcgen05 kind::tf32 kernel (TMEM accumulators, TMA-fed), forced, vs the fp32 oracle: <= 1e-4 * k relative in the
+    opt-in TF32 mode; the default split-compensated mode (three passes over big/small operand parts) is fp32-grade:
+    <= 4e-6 + 1.2e-7 * k relative on these positive inputs."""
     m, k, n = shape
     a = oracle.fill((m, k), 1, np.float32)
     b = oracle.fill((k, n), 2, np.float32)
@@ -59,14 +62,16 @@ def test_gemm_f32_tcgen05_tf32(oracle, shape, mode):
     want = ref if mode == 0 else (c0.astype(np.float64) + ref.astype(np.float64))
     da, db, dc = DevBuf.from_array(a), DevBuf.from_array(b), DevBuf.from_array(c0)
     check(lib().la_debug_set_gemm_f32_path(2))
+    check(lib().la_set_gemm_f32_mode(_cabi.LA_F32_TF32 if acc == "tf32" else _cabi.LA_F32_3XTF32))
     try:
         gemm_dev(da, k, db, n, dc, n, m, k, n, mode, np.float32)
         sync()
     finally:
         lib().la_debug_set_gemm_f32_path(0)
+        lib().la_set_gemm_f32_mode(_cabi.LA_F32_3XTF32)
     got = dc.to_array((m, n), np.float32)
     assert np.all(np.isfinite(got))
-    assert max_rel_err(got, want) <= F32_TOL * k
+    assert max_rel_err(got, want) <= (F32_TOL * k if acc == "tf32" else 4e-6 + 1.2e-7 * k)
 
 
 @pytest.mark.parametrize("mode", [0, 2])
@@ -92,6 +97,69 @@ def test_gemm_f32_tcgen05_submatrix_views(oracle, mode):
     got = dc.to_array((400, ld), np.float32)
     assert np.array_equal(got[m:, :], big_c[m:, :]) and np.array_equal(got[:, n:], big_c[:, n:])
     assert max_rel_err(got[:m, :n], want[:m, :n]) <= F32_TOL * k
+
+
+@pytest.mark.parametrize("acc", ["3xtf32", "tf32"])
+def test_gemm_f32_signed_inputs_error_vs_abs_product(oracle, acc):
+    """Signed fp32 inputs (sums cancel, so an error relative to the RESULT is meaningless): the error is measured against
+    |A|.|B| (round-1 advisor finding).  Default mode: fp32-grade, within 4e-6 + 1.2e-7*k of |A||B| -- the same order as
+    the reference's own sequential fp32 loop (k * 2^-24); opt-in TF32: 2 * 2^-11 per product."""
+    m, k, n = 384, 1024, 512
+    a = (oracle.fill((m, k), 11, np.float32) - np.float32(0.5)).astype(np.float32)
+    b = (oracle.fill((k, n), 12, np.float32) - np.float32(0.5)).astype(np.float32)
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    absprod = np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)
+    ref = oracle.gemm(a, b)  # the reference's fp32 loop order
+    ref_err = float(np.max(np.abs(ref.astype(np.float64) - exact) / absprod))
+    c = np.empty((m, n), dtype=np.float32)
+    check(lib().la_set_gemm_f32_mode(_cabi.LA_F32_TF32 if acc == "tf32" else _cabi.LA_F32_3XTF32))
+    try:
+        check(lib().la_gemm_f32_host(a.ctypes.data, b.ctypes.data, c.ctypes.data, m, k, n))
+    finally:
+        lib().la_set_gemm_f32_mode(_cabi.LA_F32_3XTF32)
+    err = float(np.max(np.abs(c.astype(np.float64) - exact) / absprod))
+    if acc == "tf32":
+        assert err <= 1.1e-3
+    else:
+        assert err <= 4e-6 + 1.2e-7 * k
+        assert err <= max(10 * ref_err, 4e-6), (err, ref_err)  # comparable with the reference's own rounding error
+
+
+def test_gemm_f32_default_mode_is_fp32_grade():
+    mode = __import__("ctypes").c_int(-1)
+    check(lib().la_get_gemm_f32_mode(__import__("ctypes").byref(mode)))
+    assert mode.value == _cabi.LA_F32_3XTF32
+
+
+@pytest.mark.parametrize("acc", ["tf32", "3xtf32"])
+def test_gemm_f32_full_size_config4_sampled_rows(oracle, acc):
+    """BASELINE config 4 at full size: f32 65536 x 1024 times 1024 x 16384, inputs generated on the device, 64 sampled
+    full rows against the fp32 oracle (rows of a product are independent, so the sample is exact): <= 1e-4 * k in the
+    TF32 mode the config names, fp32-grade in the default mode; plus the column-sum checksum over a 4096-row band."""
+    m, k, n = 65536, 1024, 16384
+    da, db, dc = DevBuf(m * k * 4), DevBuf(k * n * 4), DevBuf(m * n * 4)
+    fill_hash(da, m * k, 1, np.float32)
+    fill_hash(db, k * n, 2, np.float32)
+    check(lib().la_set_gemm_f32_mode(_cabi.LA_F32_TF32 if acc == "tf32" else _cabi.LA_F32_3XTF32))
+    try:
+        gemm_dev(da, k, db, n, dc, n, m, k, n, 0, np.float32)
+        sync()
+    finally:
+        lib().la_set_gemm_f32_mode(_cabi.LA_F32_3XTF32)
+    b = oracle.fill((k, n), 2, np.float32)
+    rows = np.unique(np.concatenate([[0, 1, 127, 128, 8191, 8192, m - 1], np.random.default_rng(4).integers(0, m, 57)]))
+    worst = 0.0
+    for r in rows:
+        a_row = oracle.fill((1, k), 1, np.float32, first_idx=int(r) * k)
+        ref = oracle.gemm_rows(a_row, b, 0, 1)
+        got = dc.to_array((1, n), np.float32, byte_offset=int(r) * n * 4)
+        worst = max(worst, max_rel_err(got, ref))
+    assert worst <= (F32_TOL * k if acc == "tf32" else 4e-6 + 1.2e-7 * k), worst
+    band = dc.to_array((4096, n), np.float32, byte_offset=20480 * n * 4).astype(np.float64)
+    a_band = oracle.fill((4096, k), 1, np.float32, first_idx=20480 * k).astype(np.float64)
+    lhs = a_band.sum(axis=0) @ b.astype(np.float64)
+    rhs = band.sum(axis=0)
+    assert np.max(np.abs(lhs - rhs) / np.abs(lhs)) <= (1e-3 if acc == "tf32" else 1e-5)
 
 
 def test_gemm_signed_inputs_absolute_error(oracle):

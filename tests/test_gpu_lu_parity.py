@@ -63,6 +63,15 @@ def test_lu_f32_parity(oracle, shape):
     check_lu(oracle, a, 1e-4)
 
 
+@pytest.mark.parametrize("shape,dtype", [((8000, 128), np.float64), ((16384, 64), np.float64), ((20000, 100), np.float64),
+                                         ((8000, 128), np.float32), ((20000, 100), np.float32), ((7000, 96), np.float64)])
+def test_lu_tall_skinny_single_panel(oracle, shape, dtype):
+    """Tall single-panel matrices: the bit-exact panel keeps two shared-memory arrays per row, so the rows per CTA must be
+    clamped to the shared-memory budget (round-1 advisor finding: 8000 x 128 asked for 258 KB and failed to launch)."""
+    a = oracle.fill(shape, 9, dtype)
+    check_lu(oracle, a, 1e-12 if dtype == np.float64 else 1e-4)
+
+
 def test_lu_input_untouched_and_odd_sizes(oracle):
     a = oracle.fill((333, 333), 2)
     keep = a.copy()
