@@ -199,6 +199,62 @@ LA_API int la_chol_solve_f32(const la_buf* L, size_t n, const la_buf* B, size_t 
 LA_API int la_chol_solve_f64_host(const double* L, size_t n, const double* B, size_t nx, double* X);
 LA_API int la_chol_solve_f32_host(const float* L, size_t n, const float* B, size_t nx, float* X);
 
+/* ---- QR (widening step) ----------------------------------------------------- */
+/* `QRDecomposition::new` (src/decomp/qr.rs:26-106), in place on a device buffer holding the m x n matrix: on return the
+ * buffer is the reference's packed `qr` (R strictly above the diagonal, the UNNORMALISED Householder vectors u_k = x - a e_k
+ * from the diagonal down) and `rdiag` holds min(m, n) values a_k = -+|x| (:58).  Blocked compact-WY on the device; `tmat`
+ * (la_qr_tmat_elems values) receives the triangular factor T' of every 128-column block, which la_qr_get_q needs. */
+LA_API int la_qr_tmat_elems(size_t m, size_t n, int device, size_t elem_bytes, size_t* elems_out);
+LA_API int la_qr_factor_f64(la_buf* QR_inout, size_t m, size_t n, la_buf* rdiag, la_buf* tmat);
+LA_API int la_qr_factor_f32(la_buf* QR_inout, size_t m, size_t n, la_buf* rdiag, la_buf* tmat);
+LA_API int la_qr_factor_f64_host(const double* A, double* QR_out, double* rdiag_out, size_t m, size_t n);
+LA_API int la_qr_factor_f32_host(const float* A, float* QR_out, float* rdiag_out, size_t m, size_t n);
+LA_API int la_qr_factor_f64_dev(double* QR_inout, size_t m, size_t n, double* rdiag, double* tmat, void* cuda_stream);
+LA_API int la_qr_factor_f32_dev(float* QR_inout, size_t m, size_t n, float* rdiag, float* tmat, void* cuda_stream);
+/* `get_r` (qr.rs:138-152): R (m x n) = strict upper part of qr with rdiag on the diagonal, device-resident so that
+ * pinverse's `(r.t() * &r).inverse() * &a.t()` (src/matrix/mod.rs:1049-1057) stays in HBM. */
+LA_API int la_qr_get_r_f64(const la_buf* QR, size_t m, size_t n, const la_buf* rdiag, la_buf* R);
+LA_API int la_qr_get_r_f32(const la_buf* QR, size_t m, size_t n, const la_buf* rdiag, la_buf* R);
+/* `get_q` (qr.rs:155-194): Q (m x m) = H_1 (H_2 (... I')), I' the identity on the first min(m, n) diagonal entries. */
+LA_API int la_qr_get_q_f64(const la_buf* QR, size_t m, size_t n, const la_buf* tmat, la_buf* Q);
+LA_API int la_qr_get_q_f32(const la_buf* QR, size_t m, size_t n, const la_buf* tmat, la_buf* Q);
+/* `solve` (qr.rs:199-238), the arithmetic only: X is the reference's full m x nx work array after both phases (the
+ * caller returns its first n rows when m == n and reproduces the panic of `Matrix::new(cols, nx, ..)` (:237) otherwise;
+ * `is_full_rank` (:110-117) is the caller's check on rdiag).  Requires n <= m.  The first phase applies I - u u'/u_k as
+ * the reference does (not a reflection for these unnormalised vectors): parity, not least squares. */
+LA_API int la_qr_solve_f64(const la_buf* QR, size_t m, size_t n, const la_buf* rdiag, const la_buf* B, size_t nx, la_buf* X);
+LA_API int la_qr_solve_f32(const la_buf* QR, size_t m, size_t n, const la_buf* rdiag, const la_buf* B, size_t nx, la_buf* X);
+
+/* ---- elementwise operators and norms on device-resident data ------------------ */
+enum la_elementwise_op {
+  LA_EW_ADD = 0,   /* `Add`      src/matrix/mod.rs:874-890:  c[i] = a[i] + b[i]       */
+  LA_EW_SUB = 1,   /* `Sub`      src/matrix/mod.rs:913-929:  c[i] = a[i] - b[i]       */
+  LA_EW_MUL = 2,   /* `elem_mul` src/matrix/mod.rs:499-512:  c[i] = a[i] * b[i]       */
+  LA_EW_DIV = 3,   /* `elem_div` src/matrix/mod.rs:514-527:  c[i] = a[i] / b[i]       */
+  LA_EW_SCALE = 4, /* `scale`    src/matrix/mod.rs:487-497:  c[i] = scalar * a[i]     */
+  LA_EW_NEG = 5    /* `Neg`      src/matrix/mod.rs:853-866:  c[i] = -a[i]             */
+};
+enum la_reduce_kind {
+  LA_RED_SUMSQ = 0,   /* `frobenius_norm` / `vector_euclidean_norm` src/matrix/mod.rs:1059-1068, :1094-1101: sqrt(sum a[i]^2) */
+  LA_RED_ABS_SUM = 1, /* `vector_1_norm` src/matrix/mod.rs:1075-1084: sum |a[i]|                                           */
+  LA_RED_ABS_MAX = 2, /* `vector_inf_norm` src/matrix/mod.rs:1103-1115: max |a[i]| (strict `>`: a NaN never replaces)      */
+  LA_RED_DOT = 3      /* `dot` src/matrix/mod.rs:529-: sum a[i] * b[i]                                                      */
+};
+/* One IEEE operation per element, `count` elements (shape checks are the caller's panics): bit-identical to the reference.
+ * B may be NULL for LA_EW_SCALE / LA_EW_NEG; C may alias A or B. */
+LA_API int la_elementwise_f64(int op, const la_buf* A, const la_buf* B, double scalar, la_buf* C, size_t count);
+LA_API int la_elementwise_f32(int op, const la_buf* A, const la_buf* B, float scalar, la_buf* C, size_t count);
+LA_API int la_elementwise_f64_dev(int op, const double* A, const double* B, double scalar, double* C, size_t count,
+                                  void* cuda_stream);
+LA_API int la_elementwise_f32_dev(int op, const float* A, const float* B, float scalar, float* C, size_t count,
+                                  void* cuda_stream);
+/* Reductions to one host scalar (synchronous).  Fixed-shape tree instead of the reference's sequential sum: equal up to
+ * rounding (<= count * eps relative for the sums of non-negative terms), exact for LA_RED_ABS_MAX. */
+LA_API int la_reduce_f64(int kind, const la_buf* A, const la_buf* B, size_t count, double* out);
+LA_API int la_reduce_f32(int kind, const la_buf* A, const la_buf* B, size_t count, float* out);
+LA_API int la_reduce_f64_dev(int kind, const double* A, const double* B, size_t count, double* out_host, void* cuda_stream);
+LA_API int la_reduce_f32_dev(int kind, const float* A, const float* B, size_t count, float* out_host, void* cuda_stream);
+
 /* ---- aux ------------------------------------------------------------------------------------------ */
 /* `Matrix::id` (src/matrix/mod.rs:416-426), the RHS of `inverse` (mod.rs:1034-1037) */
 LA_API int la_identity_f64(la_buf* dst, size_t n);

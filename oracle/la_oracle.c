@@ -419,3 +419,123 @@ ORACLE_API double oracle_lu_backward_error_f32(const float* a, const float* lu, 
   }
 DEFINE_CHOL(double, f64, sqrt)
 DEFINE_CHOL(float, f32, sqrtf)
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * QR: QRDecomposition::new  src/decomp/qr.rs:26-106 (Householder reflections, the
+ * k-th vector u = x - a e_k left UNNORMALISED in column k from the diagonal down, a = -+|x| in rdiag[k]; a zero column
+ * is skipped :62), get_q :151-194, solve :199-238.
+ *   canon : the literal loop nests (column walks with stride n).
+ *   fast  : per reflection, rows outermost and columns innermost, columns split over threads -- every dot product
+ *           still receives its terms row-ascending with separately rounded multiply/add, so the packed qr and rdiag
+ *           are bit-identical to canon (tests/test_oracle_qr.py).
+ * Quirks kept by the callers (oracle.py / the mirrors), not here: is_full_rank indexes rdiag[0..cols) (:110-117,
+ * out of bounds for m < n) and solve builds Matrix::new(cols, nx, <m*nx values>) (:237, panics unless m == n).
+ * --------------------------------------------------------------------------------------------------------------- */
+#define DEFINE_QR(T, SUF, SQRT)                                                                             \
+  ORACLE_API void oracle_qr_canon_##SUF(const T* a, size_t m, size_t n, T* qr, T* rdiag) {                  \
+    memcpy(qr, a, m * n * sizeof(T));                                                                       \
+    size_t dc = m < n ? m : n;                                                                              \
+    for (size_t minor = 0; minor < dc; ++minor) {                                                           \
+      T x_norm_sqr = (T)0;                                                                                  \
+      for (size_t i = minor; i < m; ++i) {                                  /* qr.rs:50-53 */                \
+        T c = qr[i * n + minor];                                                                            \
+        x_norm_sqr = x_norm_sqr + c * c;                                                                    \
+      }                                                                                                     \
+      T aa = qr[minor * n + minor] > (T)0 ? -SQRT(x_norm_sqr) : SQRT(x_norm_sqr); /* :58 */                 \
+      rdiag[minor] = aa;                                                                                    \
+      if (aa != (T)0) {                                                     /* :62 */                        \
+        qr[minor * n + minor] = qr[minor * n + minor] - aa;                 /* :77 */                        \
+        for (size_t column = minor + 1; column < n; ++column) {             /* :94-105 */                    \
+          T x_dot_u = (T)0;                                                                                 \
+          for (size_t row = minor; row < m; ++row) x_dot_u = x_dot_u + qr[row * n + minor] * qr[row * n + column]; \
+          T factor = x_dot_u / (aa * qr[minor * n + minor]);                                                \
+          for (size_t row = minor; row < m; ++row)                                                          \
+            qr[row * n + column] = qr[row * n + column] + factor * qr[row * n + minor];                     \
+        }                                                                                                   \
+      }                                                                                                     \
+    }                                                                                                       \
+  }                                                                                                         \
+  ORACLE_API void oracle_qr_fast_##SUF(const T* a, size_t m, size_t n, T* qr, T* rdiag) {                   \
+    memcpy(qr, a, m * n * sizeof(T));                                                                       \
+    size_t dc = m < n ? m : n;                                                                              \
+    T* dots = (T*)malloc(n * sizeof(T));                                                                    \
+    T* u = (T*)malloc(m * sizeof(T));                                                                       \
+    for (size_t minor = 0; minor < dc; ++minor) {                                                           \
+      T x_norm_sqr = (T)0;                                                                                  \
+      for (size_t i = minor; i < m; ++i) {                                                                  \
+        T c = qr[i * n + minor];                                                                            \
+        x_norm_sqr = x_norm_sqr + c * c;                                                                    \
+      }                                                                                                     \
+      T aa = qr[minor * n + minor] > (T)0 ? -SQRT(x_norm_sqr) : SQRT(x_norm_sqr);                           \
+      rdiag[minor] = aa;                                                                                    \
+      if (aa == (T)0) continue;                                                                             \
+      qr[minor * n + minor] = qr[minor * n + minor] - aa;                                                   \
+      for (size_t row = minor; row < m; ++row) u[row] = qr[row * n + minor];                                \
+      const T den = aa * qr[minor * n + minor];                                                             \
+      const size_t c0 = minor + 1;                                                                          \
+      _Pragma("omp parallel")                                                                               \
+      {                                                                                                     \
+        int nt = 1, tid = 0;                                                                                \
+        OMP_IDS(nt, tid)                                                                                    \
+        size_t span = n - c0, per = (span + (size_t)nt - 1) / (size_t)nt;                                   \
+        size_t lo = c0 + per * (size_t)tid, hi = lo + per;                                                  \
+        if (hi > n) hi = n;                                                                                 \
+        if (lo < hi) {                                                                                      \
+          for (size_t c = lo; c < hi; ++c) dots[c] = (T)0;                                                  \
+          for (size_t row = minor; row < m; ++row) {                                                        \
+            const T ur = u[row];                                                                            \
+            const T* r = qr + row * n;                                                                      \
+            for (size_t c = lo; c < hi; ++c) dots[c] = dots[c] + ur * r[c];                                 \
+          }                                                                                                 \
+          for (size_t c = lo; c < hi; ++c) dots[c] = dots[c] / den;                                         \
+          for (size_t row = minor; row < m; ++row) {                                                        \
+            const T ur = u[row];                                                                            \
+            T* r = qr + row * n;                                                                            \
+            for (size_t c = lo; c < hi; ++c) r[c] = r[c] + dots[c] * ur;                                    \
+          }                                                                                                 \
+        }                                                                                                   \
+      }                                                                                                     \
+    }                                                                                                       \
+    free(dots);                                                                                             \
+    free(u);                                                                                                \
+  }                                                                                                         \
+  /* get_q :151-194: the reflections applied in reverse order to the m x m identity (columns minor.. only) */ \
+  ORACLE_API void oracle_qr_get_q_##SUF(const T* qr, const T* rdiag, size_t m, size_t n, T* q) {            \
+    size_t dc = m < n ? m : n;                                                                              \
+    for (size_t i = 0; i < m * m; ++i) q[i] = (T)0;                                                         \
+    for (size_t k = 0; k < dc; ++k) q[k * m + k] = (T)1;                                                    \
+    for (size_t minor = dc; minor-- > 0;) {                                                                 \
+      if (qr[minor * n + minor] == (T)0) continue;                          /* :166 */                       \
+      const T den = rdiag[minor] * qr[minor * n + minor];                                                   \
+      _Pragma("omp parallel for schedule(static)")                                                          \
+      for (size_t column = minor; column < m; ++column) {                                                   \
+        T x_dot_u = (T)0;                                                                                   \
+        for (size_t row = minor; row < m; ++row) x_dot_u = x_dot_u + qr[row * n + minor] * q[row * m + column]; \
+        T factor = x_dot_u / den;                                                                           \
+        for (size_t row = minor; row < m; ++row) q[row * m + column] = q[row * m + column] + factor * qr[row * n + minor]; \
+      }                                                                                                     \
+    }                                                                                                       \
+  }                                                                                                         \
+  /* solve :199-238 on the full m x nx work array (the caller keeps the reference's shape quirk); x = m*nx values */ \
+  ORACLE_API void oracle_qr_solve_##SUF(const T* qr, const T* rdiag, size_t m, size_t n, const T* b, size_t nx, T* x) { \
+    memcpy(x, b, m * nx * sizeof(T));                                                                       \
+    for (size_t k = 0; k < n; ++k)                                          /* Y = Q' B, :214-224 */         \
+      for (size_t j = 0; j < nx; ++j) {                                                                     \
+        T s = (T)0;                                                                                         \
+        for (size_t i = k; i < m; ++i) s = s + qr[i * n + k] * x[i * nx + j];                               \
+        s = -s / qr[k * n + k];                                                                             \
+        for (size_t i = k; i < m; ++i) x[i * nx + j] = x[i * nx + j] + s * qr[i * n + k];                   \
+      }                                                                                                     \
+    for (size_t k = n; k-- > 0;) {                                          /* R X = Y, :227-236 */          \
+      for (size_t j = 0; j < nx; ++j) x[k * nx + j] = x[k * nx + j] / rdiag[k];                             \
+      for (size_t i = 0; i < k; ++i)                                                                        \
+        for (size_t j = 0; j < nx; ++j) x[i * nx + j] = x[i * nx + j] - x[k * nx + j] * qr[i * n + k];      \
+    }                                                                                                       \
+  }
+#ifdef _OPENMP
+#define OMP_IDS(nt, tid) nt = omp_get_num_threads(); tid = omp_get_thread_num();
+#else
+#define OMP_IDS(nt, tid)
+#endif
+DEFINE_QR(double, f64, sqrt)
+DEFINE_QR(float, f32, sqrtf)

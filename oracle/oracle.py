@@ -63,6 +63,10 @@ def _declare(L):
             f = getattr(L, f"oracle_chol_{form}_{suf}")
             f.argtypes, f.restype = [_p, _sz, _p], _int
         getattr(L, f"oracle_chol_solve_{suf}").argtypes = [_p, _sz, _p, _sz, _p]
+        for form in ("canon", "fast"):
+            getattr(L, f"oracle_qr_{form}_{suf}").argtypes = [_p, _sz, _sz, _p, _p]
+        getattr(L, f"oracle_qr_get_q_{suf}").argtypes = [_p, _p, _sz, _sz, _p]
+        getattr(L, f"oracle_qr_solve_{suf}").argtypes = [_p, _p, _sz, _sz, _p, _sz, _p]
         f = getattr(L, f"oracle_lu_backward_error_{suf}")
         f.argtypes, f.restype = [_p, _p, _sz, _sz, _p], ctypes.c_double
     L.oracle_gemm_canon_i64.argtypes = [_p, _p, _p, _sz, _sz, _sz]
@@ -216,3 +220,60 @@ def chol_solve(l, b):
     x = np.empty_like(b)
     getattr(lib(), f"oracle_chol_solve_{_suf(l.dtype)}")(_ptr(l), l.shape[0], _ptr(b), b.shape[1], _ptr(x))
     return x
+
+
+def qr(a, form="fast"):
+    """QRDecomposition::new (src/decomp/qr.rs:26-106): (packed qr, rdiag)."""
+    a = np.ascontiguousarray(a)
+    m, n = a.shape
+    packed = np.empty_like(a)
+    rdiag = np.empty(min(m, n), dtype=a.dtype)
+    getattr(lib(), f"oracle_qr_{'canon' if form == 'canon' else 'fast'}_{_suf(a.dtype)}")(_ptr(a), m, n, _ptr(packed),
+                                                                                        _ptr(rdiag))
+    return packed, rdiag
+
+
+def qr_is_full_rank(packed, rdiag):
+    """is_full_rank (qr.rs:110-117): indexes rdiag[0..cols) -- out of bounds (a panic) when m < n."""
+    n = packed.shape[1]
+    if n > len(rdiag):
+        raise IndexError("index out of bounds: rdiag has min(m, n) entries (qr.rs:112)")
+    return not bool(np.any(rdiag[:n] == 0))
+
+
+def qr_get_h(packed):
+    """get_h (qr.rs:121-135): lower trapezoid holding the Householder vectors."""
+    return np.tril(packed)
+
+
+def qr_get_r(packed, rdiag):
+    """get_r (qr.rs:138-152): m x n, strict upper part of qr, rdiag on the diagonal."""
+    r = np.triu(packed, 1)
+    k = len(rdiag)
+    r[np.arange(k), np.arange(k)] = rdiag
+    return r
+
+
+def qr_get_q(packed, rdiag):
+    """get_q (qr.rs:155-194): m x m."""
+    packed = np.ascontiguousarray(packed)
+    m, n = packed.shape
+    q = np.empty((m, m), dtype=packed.dtype)
+    getattr(lib(), f"oracle_qr_get_q_{_suf(packed.dtype)}")(_ptr(packed), _ptr(np.ascontiguousarray(rdiag)), m, n, _ptr(q))
+    return q
+
+
+def qr_solve(packed, rdiag, b):
+    """solve (qr.rs:199-238): None when not full rank; the result is Matrix::new(cols, nx, <m*nx values>), which panics
+    (AssertionError here) unless m == n -- the reference's least-squares solve only ever returns for square systems."""
+    packed = np.ascontiguousarray(packed)
+    b = np.ascontiguousarray(b)
+    m, n = packed.shape
+    assert b.shape[0] == m  # qr.rs:200
+    if not qr_is_full_rank(packed, rdiag):
+        return None
+    x = np.empty_like(b)
+    getattr(lib(), f"oracle_qr_solve_{_suf(packed.dtype)}")(_ptr(packed), _ptr(np.ascontiguousarray(rdiag)), m, n, _ptr(b),
+                                                            b.shape[1], _ptr(x))
+    assert n * b.shape[1] == x.size, "Matrix::new(cols, nx, data): rows * cols != data.len() (mod.rs:208)"
+    return x.reshape(n, b.shape[1])

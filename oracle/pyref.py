@@ -101,3 +101,70 @@ def get_u(lu, m, n):
 def permute_rows(a, m, n, piv):
     """P*A = A(piv,:). src/decomp/lu.rs:217-220 via Matrix::permute_rows."""
     return [a[piv[i] * n + j] for i in range(m) for j in range(n)]
+
+
+def qr_new(a, m, n):
+    """Returns (qr, rdiag). src/decomp/qr.rs:26-106 (pure-Python floats: binary64, never fused)."""
+    import math
+    qr = list(a)
+    dc = min(m, n)
+    rdiag = [None] * dc
+    for minor in range(dc):
+        x_norm_sqr = 0.0
+        for i in range(minor, m):
+            c = qr[i * n + minor]
+            x_norm_sqr = x_norm_sqr + c * c
+        aa = -math.sqrt(x_norm_sqr) if qr[minor * n + minor] > 0.0 else math.sqrt(x_norm_sqr)
+        rdiag[minor] = aa
+        if aa != 0.0:
+            qr[minor * n + minor] = qr[minor * n + minor] - aa
+            for column in range(minor + 1, n):
+                x_dot_u = 0.0
+                for row in range(minor, m):
+                    x_dot_u = x_dot_u + qr[row * n + minor] * qr[row * n + column]
+                factor = x_dot_u / (aa * qr[minor * n + minor])
+                for row in range(minor, m):
+                    qr[row * n + column] = qr[row * n + column] + factor * qr[row * n + minor]
+    return qr, rdiag
+
+
+def qr_get_r(qr, rdiag, m, n):
+    """src/decomp/qr.rs:138-152."""
+    return [qr[i * n + j] if i < j else (rdiag[i] if i == j else 0.0) for i in range(m) for j in range(n)]
+
+
+def qr_get_q(qr, rdiag, m, n):
+    """src/decomp/qr.rs:155-194."""
+    q = [0.0] * (m * m)
+    for minor in range(min(m, n)):
+        q[minor * m + minor] = 1.0
+    for minor in reversed(range(min(m, n))):
+        if qr[minor * n + minor] != 0.0:
+            for column in range(minor, m):
+                x_dot_u = 0.0
+                for row in range(minor, m):
+                    x_dot_u = x_dot_u + qr[row * n + minor] * q[row * m + column]
+                factor = x_dot_u / (rdiag[minor] * qr[minor * n + minor])
+                for row in range(minor, m):
+                    q[row * m + column] = q[row * m + column] + factor * qr[row * n + minor]
+    return q
+
+
+def qr_solve(qr, rdiag, m, n, b, nx):
+    """src/decomp/qr.rs:199-238: the m*nx work array after both phases (the reference then calls Matrix::new(n, nx, ..))."""
+    x = list(b)
+    for k in range(n):
+        for j in range(nx):
+            s = 0.0
+            for i in range(k, m):
+                s = s + qr[i * n + k] * x[i * nx + j]
+            s = -s / qr[k * n + k]
+            for i in range(k, m):
+                x[i * nx + j] = x[i * nx + j] + s * qr[i * n + k]
+    for k in reversed(range(n)):
+        for j in range(nx):
+            x[k * nx + j] = x[k * nx + j] / rdiag[k]
+        for i in range(k):
+            for j in range(nx):
+                x[i * nx + j] = x[i * nx + j] - x[k * nx + j] * qr[i * n + k]
+    return x

@@ -401,6 +401,133 @@ int chol_solve_host(const T* L, size_t n, const T* B, size_t nx, T* X) {
 }
 }  // namespace
 
+
+namespace {
+template <typename T>
+int qr_sizes(size_t m, size_t n, size_t* bytes_mn, size_t* bytes_rd) {
+  LA_REQUIRE(m > 0 && n > 0, "la_qr: zero dimension (m=%zu n=%zu)", m, n);
+  LA_REQUIRE(!mul_overflows(m, n, sizeof(T), bytes_mn), "la_qr: size overflow");
+  *bytes_rd = (m < n ? m : n) * sizeof(T);
+  return LA_OK;
+}
+template <typename T>
+int qr_factor_buf(la_buf* QR, size_t m, size_t n, la_buf* rdiag, la_buf* tmat) {
+  size_t bmn = 0, brd = 0, te = 0;
+  LA_REQUIRE(QR && rdiag && tmat, "la_qr_factor: null buffer handle");
+  LA_TRY(qr_sizes<T>(m, n, &bmn, &brd));
+  LA_REQUIRE(QR->device == rdiag->device && QR->device == tmat->device, "la_qr_factor: buffers live on different devices");
+  DeviceGuard g;
+  LA_TRY(g.enter(QR->device));
+  LA_TRY(qr_tmat_elems<T>(m, n, &te));
+  LA_REQUIRE(QR->bytes >= bmn && rdiag->bytes >= brd && tmat->bytes >= te * sizeof(T), "la_qr_factor: buffer too small");
+  cudaStream_t st = cudaStreamPerThread;
+  CallScope scope(QR->device, st);
+  LA_TRY(qr_factor_dev<T>((T*)QR->ptr, m, n, (T*)rdiag->ptr, (T*)tmat->ptr, st));
+  LA_CUDA_TRY(cudaStreamSynchronize(st));
+  return LA_OK;
+}
+template <typename T>
+int qr_factor_host(const T* A, T* QR_out, T* rdiag_out, size_t m, size_t n) {
+  size_t bmn = 0, brd = 0, te = 0;
+  LA_REQUIRE(A && QR_out && rdiag_out, "la_qr_factor_host: null pointer");
+  LA_TRY(qr_sizes<T>(m, n, &bmn, &brd));
+  const DeviceCtx* ctx;
+  LA_TRY(current_device_ctx(&ctx));
+  LA_TRY(qr_tmat_elems<T>(m, n, &te));
+  void *dA, *dR, *dT;
+  LA_TRY(scratch_get(ctx->device, 0, bmn, &dA));
+  LA_TRY(scratch_get(ctx->device, 3, brd + 64, &dR));
+  LA_TRY(scratch_get(ctx->device, 1, te * sizeof(T), &dT));
+  cudaStream_t st = cudaStreamPerThread;
+  CallScope scope(ctx->device, st);
+  LA_CUDA_TRY(cudaMemcpyAsync(dA, A, bmn, cudaMemcpyHostToDevice, st));
+  LA_TRY(qr_factor_dev<T>((T*)dA, m, n, (T*)dR, (T*)dT, st));
+  LA_CUDA_TRY(cudaMemcpyAsync(QR_out, dA, bmn, cudaMemcpyDeviceToHost, st));
+  LA_CUDA_TRY(cudaMemcpyAsync(rdiag_out, dR, brd, cudaMemcpyDeviceToHost, st));
+  LA_CUDA_TRY(cudaStreamSynchronize(st));
+  return LA_OK;
+}
+template <typename T>
+int qr_get_r_buf(const la_buf* QR, size_t m, size_t n, const la_buf* rdiag, la_buf* R) {
+  size_t bmn = 0, brd = 0;
+  LA_REQUIRE(QR && rdiag && R, "la_qr_get_r: null buffer handle");
+  LA_TRY(qr_sizes<T>(m, n, &bmn, &brd));
+  LA_REQUIRE(QR->bytes >= bmn && rdiag->bytes >= brd && R->bytes >= bmn, "la_qr_get_r: buffer too small");
+  LA_REQUIRE(QR->device == rdiag->device && QR->device == R->device && QR->ptr != R->ptr,
+             "la_qr_get_r: buffers must be distinct and on one device");
+  DeviceGuard g;
+  LA_TRY(g.enter(QR->device));
+  cudaStream_t st = cudaStreamPerThread;
+  CallScope scope(QR->device, st);
+  return qr_get_r_dev<T>((const T*)QR->ptr, m, n, (const T*)rdiag->ptr, (T*)R->ptr, st);
+}
+template <typename T>
+int qr_get_q_buf(const la_buf* QR, size_t m, size_t n, const la_buf* tmat, la_buf* Q) {
+  size_t bmn = 0, brd = 0, bq = 0, te = 0;
+  LA_REQUIRE(QR && tmat && Q, "la_qr_get_q: null buffer handle");
+  LA_TRY(qr_sizes<T>(m, n, &bmn, &brd));
+  LA_REQUIRE(!mul_overflows(m, m, sizeof(T), &bq), "la_qr_get_q: size overflow");
+  LA_REQUIRE(QR->device == tmat->device && QR->device == Q->device && QR->ptr != Q->ptr,
+             "la_qr_get_q: buffers must be distinct and on one device");
+  DeviceGuard g;
+  LA_TRY(g.enter(QR->device));
+  LA_TRY(qr_tmat_elems<T>(m, n, &te));
+  LA_REQUIRE(QR->bytes >= bmn && tmat->bytes >= te * sizeof(T) && Q->bytes >= bq, "la_qr_get_q: buffer too small");
+  cudaStream_t st = cudaStreamPerThread;
+  CallScope scope(QR->device, st);
+  LA_TRY(qr_get_q_dev<T>((const T*)QR->ptr, m, n, (const T*)tmat->ptr, (T*)Q->ptr, st));
+  LA_CUDA_TRY(cudaStreamSynchronize(st));
+  return LA_OK;
+}
+template <typename T>
+int qr_solve_buf(const la_buf* QR, size_t m, size_t n, const la_buf* rdiag, const la_buf* B, size_t nx, la_buf* X) {
+  size_t bmn = 0, brd = 0, bx = 0;
+  LA_REQUIRE(QR && rdiag && B && X && nx > 0, "la_qr_solve: bad arguments");
+  LA_TRY(qr_sizes<T>(m, n, &bmn, &brd));
+  LA_REQUIRE(!mul_overflows(m, nx, sizeof(T), &bx), "la_qr_solve: size overflow");
+  LA_REQUIRE(QR->bytes >= bmn && rdiag->bytes >= brd && B->bytes >= bx && X->bytes >= bx, "la_qr_solve: buffer too small");
+  LA_REQUIRE(QR->device == rdiag->device && QR->device == B->device && QR->device == X->device,
+             "la_qr_solve: buffers live on different devices");
+  DeviceGuard g;
+  LA_TRY(g.enter(QR->device));
+  cudaStream_t st = cudaStreamPerThread;
+  CallScope scope(QR->device, st);
+  LA_TRY(qr_solve_dev<T>((const T*)QR->ptr, m, n, (const T*)rdiag->ptr, (const T*)B->ptr, nx, (T*)X->ptr, st));
+  LA_CUDA_TRY(cudaStreamSynchronize(st));
+  return LA_OK;
+}
+}  // namespace
+
+
+namespace {
+template <typename T>
+int elementwise_buf(int op, const la_buf* A, const la_buf* B, T scalar, la_buf* C, size_t count) {
+  LA_REQUIRE(A && C && count > 0, "la_elementwise: bad arguments");
+  LA_REQUIRE(count <= SIZE_MAX / sizeof(T), "la_elementwise: size overflow");
+  const size_t bytes = count * sizeof(T);
+  LA_REQUIRE(A->bytes >= bytes && C->bytes >= bytes && (!B || B->bytes >= bytes), "la_elementwise: buffer too small");
+  LA_REQUIRE(A->device == C->device && (!B || B->device == A->device), "la_elementwise: buffers live on different devices");
+  DeviceGuard g;
+  LA_TRY(g.enter(A->device));
+  cudaStream_t st = cudaStreamPerThread;
+  CallScope scope(A->device, st);
+  return elementwise_dev<T>(op, (const T*)A->ptr, B ? (const T*)B->ptr : nullptr, scalar, (T*)C->ptr, count, st);
+}
+template <typename T>
+int reduce_buf(int kind, const la_buf* A, const la_buf* B, size_t count, T* out) {
+  LA_REQUIRE(A && out && count > 0, "la_reduce: bad arguments");
+  LA_REQUIRE(count <= SIZE_MAX / sizeof(T), "la_reduce: size overflow");
+  const size_t bytes = count * sizeof(T);
+  LA_REQUIRE(A->bytes >= bytes && (!B || B->bytes >= bytes), "la_reduce: buffer too small");
+  LA_REQUIRE(!B || B->device == A->device, "la_reduce: buffers live on different devices");
+  DeviceGuard g;
+  LA_TRY(g.enter(A->device));
+  cudaStream_t st = cudaStreamPerThread;
+  CallScope scope(A->device, st);
+  return reduce_dev<T>(kind, (const T*)A->ptr, B ? (const T*)B->ptr : nullptr, count, out, st);
+}
+}  // namespace
+
 extern "C" {
 
 int la_version(void) { return 1; }
@@ -654,6 +781,62 @@ int la_chol_solve_f64_host(const double* L, size_t n, const double* B, size_t nx
 }
 int la_chol_solve_f32_host(const float* L, size_t n, const float* B, size_t nx, float* X) {
   return chol_solve_host<float>(L, n, B, nx, X);
+}
+int la_qr_tmat_elems(size_t m, size_t n, int device, size_t elem_bytes, size_t* elems_out) {
+  LA_REQUIRE(elems_out && (elem_bytes == 4 || elem_bytes == 8), "la_qr_tmat_elems: bad arguments");
+  DeviceGuard g;
+  LA_TRY(g.enter(device));
+  return elem_bytes == 8 ? qr_tmat_elems<double>(m, n, elems_out) : qr_tmat_elems<float>(m, n, elems_out);
+}
+int la_qr_factor_f64(la_buf* QR, size_t m, size_t n, la_buf* rdiag, la_buf* tmat) { return qr_factor_buf<double>(QR, m, n, rdiag, tmat); }
+int la_qr_factor_f32(la_buf* QR, size_t m, size_t n, la_buf* rdiag, la_buf* tmat) { return qr_factor_buf<float>(QR, m, n, rdiag, tmat); }
+int la_qr_factor_f64_host(const double* A, double* QR_out, double* rdiag_out, size_t m, size_t n) {
+  return qr_factor_host<double>(A, QR_out, rdiag_out, m, n);
+}
+int la_qr_factor_f32_host(const float* A, float* QR_out, float* rdiag_out, size_t m, size_t n) {
+  return qr_factor_host<float>(A, QR_out, rdiag_out, m, n);
+}
+int la_qr_factor_f64_dev(double* QR, size_t m, size_t n, double* rdiag, double* tmat, void* stream) {
+  DEV_SCOPE(stream);
+  return qr_factor_dev<double>(QR, m, n, rdiag, tmat, resolve_stream(stream));
+}
+int la_qr_factor_f32_dev(float* QR, size_t m, size_t n, float* rdiag, float* tmat, void* stream) {
+  DEV_SCOPE(stream);
+  return qr_factor_dev<float>(QR, m, n, rdiag, tmat, resolve_stream(stream));
+}
+int la_qr_get_r_f64(const la_buf* QR, size_t m, size_t n, const la_buf* rdiag, la_buf* R) { return qr_get_r_buf<double>(QR, m, n, rdiag, R); }
+int la_qr_get_r_f32(const la_buf* QR, size_t m, size_t n, const la_buf* rdiag, la_buf* R) { return qr_get_r_buf<float>(QR, m, n, rdiag, R); }
+int la_qr_get_q_f64(const la_buf* QR, size_t m, size_t n, const la_buf* tmat, la_buf* Q) { return qr_get_q_buf<double>(QR, m, n, tmat, Q); }
+int la_qr_get_q_f32(const la_buf* QR, size_t m, size_t n, const la_buf* tmat, la_buf* Q) { return qr_get_q_buf<float>(QR, m, n, tmat, Q); }
+int la_qr_solve_f64(const la_buf* QR, size_t m, size_t n, const la_buf* rdiag, const la_buf* B, size_t nx, la_buf* X) {
+  return qr_solve_buf<double>(QR, m, n, rdiag, B, nx, X);
+}
+int la_qr_solve_f32(const la_buf* QR, size_t m, size_t n, const la_buf* rdiag, const la_buf* B, size_t nx, la_buf* X) {
+  return qr_solve_buf<float>(QR, m, n, rdiag, B, nx, X);
+}
+int la_elementwise_f64(int op, const la_buf* A, const la_buf* B, double scalar, la_buf* C, size_t count) {
+  return elementwise_buf<double>(op, A, B, scalar, C, count);
+}
+int la_elementwise_f32(int op, const la_buf* A, const la_buf* B, float scalar, la_buf* C, size_t count) {
+  return elementwise_buf<float>(op, A, B, scalar, C, count);
+}
+int la_elementwise_f64_dev(int op, const double* A, const double* B, double scalar, double* C, size_t count, void* stream) {
+  DEV_SCOPE(stream);
+  return elementwise_dev<double>(op, A, B, scalar, C, count, resolve_stream(stream));
+}
+int la_elementwise_f32_dev(int op, const float* A, const float* B, float scalar, float* C, size_t count, void* stream) {
+  DEV_SCOPE(stream);
+  return elementwise_dev<float>(op, A, B, scalar, C, count, resolve_stream(stream));
+}
+int la_reduce_f64(int kind, const la_buf* A, const la_buf* B, size_t count, double* out) { return reduce_buf<double>(kind, A, B, count, out); }
+int la_reduce_f32(int kind, const la_buf* A, const la_buf* B, size_t count, float* out) { return reduce_buf<float>(kind, A, B, count, out); }
+int la_reduce_f64_dev(int kind, const double* A, const double* B, size_t count, double* out_host, void* stream) {
+  DEV_SCOPE(stream);
+  return reduce_dev<double>(kind, A, B, count, out_host, resolve_stream(stream));
+}
+int la_reduce_f32_dev(int kind, const float* A, const float* B, size_t count, float* out_host, void* stream) {
+  DEV_SCOPE(stream);
+  return reduce_dev<float>(kind, A, B, count, out_host, resolve_stream(stream));
 }
 int la_fill_hash_f64_dev(double* dst, size_t count, uint64_t seed, uint64_t first_idx, void* stream) {
   return fill_hash_dev<double>(dst, count, seed, first_idx, resolve_stream(stream));

@@ -93,6 +93,20 @@ int chol_factor_dev(T* A, size_t n, int* flags_dev, cudaStream_t st);  // choles
 template <typename T>
 int chol_solve_dev(const T* L, size_t n, const T* B, size_t nx, T* X, cudaStream_t st);
 template <typename T>
+int elementwise_dev(int op, const T* A, const T* B, T scalar, T* C, size_t count, cudaStream_t st);  // elementwise.cu
+template <typename T>
+int reduce_dev(int kind, const T* A, const T* B, size_t count, T* out_host, cudaStream_t st);
+template <typename T>
+int qr_tmat_elems(size_t m, size_t n, size_t* out);  // qr.cu
+template <typename T>
+int qr_factor_dev(T* QR, size_t m, size_t n, T* rdiag, T* tmat, cudaStream_t st);
+template <typename T>
+int qr_get_r_dev(const T* QR, size_t m, size_t n, const T* rdiag, T* R, cudaStream_t st);
+template <typename T>
+int qr_get_q_dev(const T* QR, size_t m, size_t n, const T* tmat, T* Q, cudaStream_t st);
+template <typename T>
+int qr_solve_dev(const T* QR, size_t m, size_t n, const T* rdiag, const T* B, size_t nx, T* X, cudaStream_t st);
+template <typename T>
 int transpose_dev(const T* src, T* dst, size_t rows, size_t cols, cudaStream_t st);
 template <typename T>
 int permute_rows_dev(const T* src, T* dst, const uint64_t* idx_dev, size_t out_rows, size_t cols, cudaStream_t st);

@@ -30,6 +30,7 @@
 #include <stdio.h>
 
 #include "la_common.cuh"
+#include "ll_exchange.cuh"
 
 namespace la {
 namespace {
@@ -51,48 +52,6 @@ struct MoveList {
   int pad[3];
   int dst[MAX_MOVES];
   int src[MAX_MOVES];
-};
-// Flagged ("LL") exchange words: every 4-byte half of a value travels next to a 4-byte tag in the same naturally
-// atomic 8-byte unit, so a reader that sees the expected tag has the data -- no fence, no atomic, no grid barrier.
-// All accesses are RELAXED at gpu scope (served by L2, free to overlap): volatile ones would be kept in program
-// order by the hardware, which serialises a poll of n words into n L2 round trips.
-__device__ __forceinline__ void st_relaxed_2x64(void* p, unsigned long long a, unsigned long long b) {
-  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
-}
-__device__ __forceinline__ void ld_relaxed_2x64(const void* p, unsigned long long& a, unsigned long long& b) {
-  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
-}
-__device__ __forceinline__ unsigned long long ll_pack(unsigned v, unsigned tag) {
-  return ((unsigned long long)tag << 32) | v;
-}
-template <typename T>
-struct LL;
-template <>
-struct LL<double> {
-  typedef uint4 word;
-  static __device__ __forceinline__ void store(word* p, double v, unsigned tag) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-    st_relaxed_2x64(p, ll_pack((unsigned)b, tag), ll_pack((unsigned)(b >> 32), tag));
-  }
-  static __device__ __forceinline__ bool load(const word* p, unsigned tag, double& v) {
-    unsigned long long a, b;
-    ld_relaxed_2x64(p, a, b);
-    v = __longlong_as_double((long long)((b << 32) | (a & 0xffffffffull)));
-    return (unsigned)(a >> 32) == tag && (unsigned)(b >> 32) == tag;
-  }
-};
-template <>
-struct LL<float> {
-  typedef uint2 word;
-  static __device__ __forceinline__ void store(word* p, float v, unsigned tag) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(ll_pack(__float_as_uint(v), tag)) : "memory");
-  }
-  static __device__ __forceinline__ bool load(const word* p, unsigned tag, float& v) {
-    unsigned long long a;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
-    v = __uint_as_float((unsigned)a);
-    return (unsigned)(a >> 32) == tag;
-  }
 };
 // One candidate record per CTA and step: |pivot candidate| as a double and its absolute row, packed into two
 // self-validating 8-byte units (16 bytes, one load per record): {key.hi32 | row.hi16 | tag16}, {key.lo32 | row.lo16 |
@@ -943,7 +902,7 @@ namespace {
 // Per host thread and device: the chain stream (highest priority) and the events that fence it against the bulk stream.
 struct LuSide {
   cudaStream_t sp = nullptr, sw = nullptr;
-  cudaEvent_t e_in = nullptr, e_head = nullptr, e_bulk = nullptr, e_panel = nullptr, e_w = nullptr;
+  cudaEvent_t e_in = nullptr, e_head = nullptr, e_bulk = nullptr, e_panel = nullptr, e_w = nullptr, e_u12 = nullptr;
 };
 int lu_side(int device, LuSide** out) {
   static thread_local LuSide side[64];
@@ -959,6 +918,7 @@ int lu_side(int device, LuSide** out) {
     LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e_in, cudaEventDisableTiming));
     LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e_head, cudaEventDisableTiming));
     LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e_bulk, cudaEventDisableTiming));
+    LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e_u12, cudaEventDisableTiming));
   }
   *out = &s;
   return LA_OK;
@@ -1130,6 +1090,18 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
     LA_CUDA_TRY(cudaStreamWaitEvent(sp, side->e_in, 0));
     mark(sp);  // t0
     LA_TRY(launch_panel(0, nb, sp));
+    // Grouped bulk updates: while the trailing matrix is tall, `group` consecutive panels share ONE trailing GEMM of depth
+    // K = group * nb (half the C read-modify-write traffic per flop at group = 2; the K = 128 update is bound by it).
+    // Steps that defer ("S") do only the interchanges and their U12 rows in the bulk -- U12_s = W_s (A12_s - L[s][g..s)
+    // U[g..s)) -- and the step that closes the group adds A22 -= L[:, g..c1) U[g..c1, :] for all columns except the
+    // next-next panel's, which the chain brings up to date itself (same K range, 128 columns wide, high priority) as
+    // soon as the U12 rows exist: the chain never waits for a bulk GEMM.
+    static const int group_max = getenv("LA_LU_GROUP") ? atoi(getenv("LA_LU_GROUP")) : 2;            // 1 = no grouping
+    static const int group_rows = getenv("LA_LU_GROUP_ROWS") ? atoi(getenv("LA_LU_GROUP_ROWS")) : 3072;
+    int gstart = 0;        // first column of the open group (panels whose bulk trailing update is deferred)
+    int gcount = 0;        // panels deferred so far in the open group
+    int strip_k0 = 0;      // the next panel's columns lack the updates of panels [strip_k0, j0) (== j0: none)
+    int prev_mode = 0;     // 0: previous step updated everything (or first step), 1: it deferred, 2: it closed a group
     int it = 0;
     for (int j0 = 0; j0 < kmin; j0 += nb, ++it) {
       const int jb = (kmin - j0 < nb) ? (kmin - j0) : nb;
@@ -1138,6 +1110,16 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
       const bool has_next = c1 < kmin;
       const int nb2 = has_next ? ((kmin - c1 < nb) ? (kmin - c1) : nb) : 0;
       const int c2 = c1 + nb2;
+      if (gcount == 0) gstart = j0;
+      if (prev_mode == 0) strip_k0 = j0;
+      // defer this panel's trailing update?  Needs a full next panel and a full panel after it (whose chain step does the
+      // catch-up), a tall trailing matrix, and room in the group.
+      const bool defer = group_max > 1 && gcount + 1 < group_max && jb == nb && nb2 == nb && c2 + nb <= kmin &&
+                         M - c1 >= group_rows;
+      const int kdef = j0 - gstart;     // depth of the updates the columns right of c2 still lack (0: none)
+      const int kstrip = j0 - strip_k0;  // depth of the updates the next panel's columns still lack
+      // width of the next-next panel: after a group closes, its columns are left to the chain
+      const int w_strip = (kdef > 0 && !defer && c2 < kmin) ? ((kmin - c2 < nb) ? (kmin - c2) : nb) : 0;
       double* W = Wbuf[parity];
       const double* L21 = A + (size_t)c1 * ld + j0;
       auto trailing = [&](int cb, int ce, cudaStream_t s) -> int {  // A22 -= L21 * U12 for columns [cb, ce)
@@ -1156,9 +1138,19 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
         LA_CUDA_TRY(cudaEventRecord(side->e_w, sw));
       }
       // ---- chain ----
+      if (has_next && kstrip > 0) {
+        // catch-up: the next panel's columns lack the updates of the panels [strip_k0, j0); their U rows were
+        // finished by the previous bulk step (e_bulk after a deferring step, e_u12 after a closing one).  This GEMM reads
+        // L columns left of j0, which bulk(i) interchanges: it must precede e_head.
+        LA_CUDA_TRY(cudaStreamWaitEvent(sp, prev_mode == 1 ? side->e_bulk : side->e_u12, 0));
+        LA_TRY(gemm_f64_tensor(A + (size_t)j0 * ld + strip_k0, ld, A + (size_t)strip_k0 * ld + c1, ld,
+                               A + (size_t)j0 * ld + c1, ld, (size_t)(M - j0), (size_t)kstrip, (size_t)(c2 - c1), LA_GEMM_SUB,
+                               sp));
+      }
       LA_TRY(launch_perm(j0, jb, parity, sp));
       LA_CUDA_TRY(cudaEventRecord(side->e_head, sp));
-      if (has_next && it > 0) LA_CUDA_TRY(cudaStreamWaitEvent(sp, side->e_bulk, 0));  // bulk(i-1) updated columns >= c1
+      if (has_next && it > 0 && prev_mode == 0)
+        LA_CUDA_TRY(cudaStreamWaitEvent(sp, side->e_bulk, 0));  // bulk(i-1) updated columns >= c1
       mark(sp);  // [1] perm done and bulk(i-1) done
       if (has_next) {
         lu_head_kernel<T><<<(nb2 + HEAD_COLS - 1) / HEAD_COLS, 256, HEAD_SMEM, sp>>>(LU, n, j0, jb, c1, c2, ws_base, G_cur,
@@ -1199,12 +1191,36 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
       mark(st);  // [5] bulk swaps done
       if (need_w) {
         double* U12 = A + (size_t)j0 * ld + c2;
+        if (kdef > 0)  // this panel's rows of A12 first receive the deferred panels' updates
+          LA_TRY(gemm_f64_tensor(A + (size_t)j0 * ld + gstart, ld, A + (size_t)gstart * ld + c2, ld, U12, ld, (size_t)jb,
+                                 (size_t)kdef, (size_t)(N - c2), LA_GEMM_SUB, st));
         LA_TRY(gemm_f64_tensor(W, MAX_NB, U12, ld, U12, ld, (size_t)jb, (size_t)jb, (size_t)(N - c2), LA_GEMM_ASSIGN,
                                st));  // in place: one tile row, every CTA reads its whole column block first
-        LA_TRY(trailing(c2, N, st));
+        if (!defer) {
+          if (kdef > 0) {  // close the group: one GEMM of depth c1 - gstart, the chain's strip excluded
+            LA_CUDA_TRY(cudaEventRecord(side->e_u12, st));
+            const int cb = c2 + w_strip;
+            if (cb < N && c1 < M)
+              LA_TRY(gemm_f64_tensor(A + (size_t)c1 * ld + gstart, ld, A + (size_t)gstart * ld + cb, ld,
+                                     A + (size_t)c1 * ld + cb, ld, (size_t)(M - c1), (size_t)(c1 - gstart), (size_t)(N - cb),
+                                     LA_GEMM_SUB, st));
+          } else {
+            LA_TRY(trailing(c2, N, st));
+          }
+        }
       }
       LA_CUDA_TRY(cudaEventRecord(side->e_bulk, st));
       mark(st);  // [6] bulk(i) done
+      if (defer) {  // the next panel's columns received this panel's update from the chain, the next-next panel's did not
+        ++gcount;
+        prev_mode = 1;
+        strip_k0 = gstart;
+      } else {
+        // after a closed group the strip [c2, c2 + w_strip) still lacks [gstart, c1): the next chain step catches up
+        prev_mode = (kdef > 0 && w_strip > 0) ? 2 : 0;
+        strip_k0 = gstart;
+        gcount = 0;
+      }
     }
     if (trace_path) {
       LA_CUDA_TRY(cudaStreamSynchronize(sp));

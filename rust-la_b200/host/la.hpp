@@ -7,7 +7,12 @@
 //   la::Matrix<T>            reference src/matrix/mod.rs:26-30; new :207-211, rows :256, cols :260, get_data :264,
 //                            get :557-560, id :416-426, operator* :957-998, mmul (mmatrix.rs:82-98),
 //                            det/solve/inverse/is_singular/is_non_singular :1025-1047
+//                            Device-backed: a Matrix owns a host Vec AND / OR a device buffer, each valid or
+//                            stale; operators run on the device buffers and leave the result there, `get_data()`
+//                            (mod.rs:264) downloads on first use, `get_mut_data()` (mmatrix.rs:11) invalidates the device
+//                            copy -- so `a * b * c`, `a.t() * b`, `a.inverse()` chains keep their intermediates in HBM.
 //   la::LUDecomposition<T>   reference src/decomp/lu.rs:95-278
+//   la::QRDecomposition<T>   reference src/decomp/qr.rs:20-238; Matrix::pinverse mod.rs:1049-1057
 //   la::m<T>({{..},{..}})    the m! macro, src/macros.rs:39-42
 //   la::Panic                the reference `assert!`s (panics); thrown BEFORE any FFI call
 //   std::optional            Option<Matrix<T>> (None on numerical singularity, lu.rs:241-243)
@@ -15,6 +20,7 @@
 #include <cstdint>
 #include <cstring>
 #include <initializer_list>
+#include <memory>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -49,6 +55,16 @@ template <> struct Abi<double> {
   static int solve(const la_buf* lu, size_t m, size_t n, const uint64_t* piv, const la_buf* b, size_t nx, la_buf* x) { return la_lu_solve_f64(lu, m, n, piv, b, nx, x); }
   static int chol_factor(la_buf* a, size_t n, int* ok) { return la_chol_factor_f64(a, n, ok); }
   static int chol_solve(const la_buf* l, size_t n, const la_buf* b, size_t nx, la_buf* x) { return la_chol_solve_f64(l, n, b, nx, x); }
+  static constexpr bool device_backed = true;
+  static int gemm(const la_buf* a, const la_buf* b, la_buf* c, size_t m, size_t k, size_t n) { return la_gemm_f64(a, b, c, m, k, n); }
+  static int transpose(const la_buf* s, la_buf* d, size_t r, size_t c) { return la_transpose_f64(s, d, r, c); }
+  static int identity(la_buf* d, size_t n) { return la_identity_f64(d, n); }
+  static int elementwise(int op, const la_buf* a, const la_buf* b, double s, la_buf* c, size_t n) { return la_elementwise_f64(op, a, b, s, c, n); }
+  static int reduce(int kind, const la_buf* a, const la_buf* b, size_t n, double* out) { return la_reduce_f64(kind, a, b, n, out); }
+  static int qr_factor(la_buf* qr, size_t m, size_t n, la_buf* rd, la_buf* tm) { return la_qr_factor_f64(qr, m, n, rd, tm); }
+  static int qr_get_r(const la_buf* qr, size_t m, size_t n, const la_buf* rd, la_buf* r) { return la_qr_get_r_f64(qr, m, n, rd, r); }
+  static int qr_get_q(const la_buf* qr, size_t m, size_t n, const la_buf* tm, la_buf* q) { return la_qr_get_q_f64(qr, m, n, tm, q); }
+  static int qr_solve(const la_buf* qr, size_t m, size_t n, const la_buf* rd, const la_buf* b, size_t nx, la_buf* x) { return la_qr_solve_f64(qr, m, n, rd, b, nx, x); }
 };
 template <> struct Abi<float> {
   static int gemm_host(const float* a, const float* b, float* c, size_t m, size_t k, size_t n) { return la_gemm_f32_host(a, b, c, m, k, n); }
@@ -58,19 +74,52 @@ template <> struct Abi<float> {
   static int solve(const la_buf* lu, size_t m, size_t n, const uint64_t* piv, const la_buf* b, size_t nx, la_buf* x) { return la_lu_solve_f32(lu, m, n, piv, b, nx, x); }
   static int chol_factor(la_buf* a, size_t n, int* ok) { return la_chol_factor_f32(a, n, ok); }
   static int chol_solve(const la_buf* l, size_t n, const la_buf* b, size_t nx, la_buf* x) { return la_chol_solve_f32(l, n, b, nx, x); }
+  static constexpr bool device_backed = true;
+  static int gemm(const la_buf* a, const la_buf* b, la_buf* c, size_t m, size_t k, size_t n) { return la_gemm_f32(a, b, c, m, k, n); }
+  static int transpose(const la_buf* s, la_buf* d, size_t r, size_t c) { return la_transpose_f32(s, d, r, c); }
+  static int identity(la_buf* d, size_t n) { return la_identity_f32(d, n); }
+  static int elementwise(int op, const la_buf* a, const la_buf* b, float s, la_buf* c, size_t n) { return la_elementwise_f32(op, a, b, s, c, n); }
+  static int reduce(int kind, const la_buf* a, const la_buf* b, size_t n, float* out) { return la_reduce_f32(kind, a, b, n, out); }
+  static int qr_factor(la_buf* qr, size_t m, size_t n, la_buf* rd, la_buf* tm) { return la_qr_factor_f32(qr, m, n, rd, tm); }
+  static int qr_get_r(const la_buf* qr, size_t m, size_t n, const la_buf* rd, la_buf* r) { return la_qr_get_r_f32(qr, m, n, rd, r); }
+  static int qr_get_q(const la_buf* qr, size_t m, size_t n, const la_buf* tm, la_buf* q) { return la_qr_get_q_f32(qr, m, n, tm, q); }
+  static int qr_solve(const la_buf* qr, size_t m, size_t n, const la_buf* rd, const la_buf* b, size_t nx, la_buf* x) { return la_qr_solve_f32(qr, m, n, rd, b, nx, x); }
 };
 template <> struct Abi<int64_t> {
   static int gemm_host(const int64_t* a, const int64_t* b, int64_t* c, size_t m, size_t k, size_t n) { return la_gemm_i64_host(a, b, c, m, k, n); }
+  static constexpr bool device_backed = false;  // integers: host-pointer entry point only
+  static int gemm(const la_buf*, const la_buf*, la_buf*, size_t, size_t, size_t) { return LA_ERR_UNSUPPORTED; }
+  static int transpose(const la_buf*, la_buf*, size_t, size_t) { return LA_ERR_UNSUPPORTED; }
+  static int elementwise(int, const la_buf*, const la_buf*, int64_t, la_buf*, size_t) { return LA_ERR_UNSUPPORTED; }
 };
 
 template <typename T> class LUDecomposition;
+template <typename T> class QRDecomposition;
+
+namespace detail {
+struct DevBuf {
+  la_buf* h = nullptr;
+  size_t bytes = 0;
+  explicit DevBuf(size_t nbytes, int device = 0) : bytes(nbytes) { check(la_buf_alloc(nbytes, device, &h)); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : h(o.h), bytes(o.bytes) { o.h = nullptr; }
+  ~DevBuf() {
+    if (h) la_buf_free(h);
+  }
+};
+}  // namespace detail
+
+// Products below this many multiply-adds between two host-only operands go through the host-pointer entry point (one call,
+// no buffer objects); anything larger, and anything that already has a device copy, stays on the device.
+constexpr size_t kDeviceResidentMinWork = size_t(1) << 21;
 
 template <typename T>
 class Matrix {
  public:
   // Matrix::new, mod.rs:207-211
-  Matrix(size_t no_rows, size_t no_cols, std::vector<T> data) : no_rows_(no_rows), data_(std::move(data)) {
-    LA_ASSERT(no_rows * no_cols == data_.size());
+  Matrix(size_t no_rows, size_t no_cols, std::vector<T> data) : no_rows_(no_rows), no_cols_(no_cols), host_(std::move(data)) {
+    LA_ASSERT(no_rows * no_cols == host_.size());
     LA_ASSERT(no_rows > 0 && no_cols > 0);
   }
   static Matrix id(size_t m, size_t n) {  // mod.rs:416-426
@@ -79,43 +128,85 @@ class Matrix {
     return Matrix(m, n, std::move(d));
   }
   size_t rows() const { return no_rows_; }
-  size_t cols() const { return data_.size() / no_rows_; }
-  const std::vector<T>& get_data() const { return data_; }
-  std::vector<T>& get_mut_data() { return data_; }
-  T get(size_t row, size_t col) const {
-    LA_ASSERT(row < no_rows_ && col < cols());
-    return data_[row * cols() + col];
+  size_t cols() const { return no_cols_; }
+  // get_data, mod.rs:264: the host Vec, downloaded from HBM the first time it is asked for after a device operation
+  const std::vector<T>& get_data() const {
+    sync_host();
+    return host_;
   }
-  bool operator==(const Matrix& o) const { return no_rows_ == o.no_rows_ && data_ == o.data_; }  // derive(PartialEq)
+  // get_mut_data, mmatrix.rs:11: the caller may change the host Vec, so the device copy becomes stale
+  std::vector<T>& get_mut_data() {
+    sync_host();
+    dev_valid_ = false;
+    return host_;
+  }
+  T get(size_t row, size_t col) const {
+    LA_ASSERT(row < no_rows_ && col < no_cols_);
+    return get_data()[row * no_cols_ + col];
+  }
+  bool operator==(const Matrix& o) const {  // derive(PartialEq)
+    return no_rows_ == o.no_rows_ && no_cols_ == o.no_cols_ && get_data() == o.get_data();
+  }
   bool approx_eq(const Matrix& o) const {  // mod.rs:1141-1147, ApproxEq absolute 1e-6
     if (rows() != o.rows() || cols() != o.cols()) return false;
-    for (size_t i = 0; i < data_.size(); ++i) {
-      T d = data_[i] - o.data_[i];
+    const auto &x = get_data(), &y = o.get_data();
+    for (size_t i = 0; i < x.size(); ++i) {
+      T d = x[i] - y[i];
       if (!((d < 0 ? -d : d) < T(1.0e-6))) return false;
     }
     return true;
   }
-  Matrix t() const {
-    std::vector<T> d(data_.size());
-    for (size_t r = 0; r < rows(); ++r)
-      for (size_t c = 0; c < cols(); ++c) d[c * rows() + r] = data_[r * cols() + c];
-    return Matrix(cols(), rows(), std::move(d));
+  Matrix t() const {  // mod.rs:653-669
+    if (Abi<T>::device_backed && dev_valid_) {
+      Matrix out(no_cols_, no_rows_, Dirty{});
+      check(Abi<T>::transpose(dev_->h, out.dev_->h, no_rows_, no_cols_));
+      return out;
+    }
+    const auto& src = get_data();
+    std::vector<T> d(src.size());
+    for (size_t r = 0; r < no_rows_; ++r)
+      for (size_t c = 0; c < no_cols_; ++c) d[c * no_rows_ + r] = src[r * no_cols_ + c];
+    return Matrix(no_cols_, no_rows_, std::move(d));
   }
 
   // impl Mul, mod.rs:957-980: shape assert first (panics before the FFI call), output is a fresh "dirty" buffer
   Matrix operator*(const Matrix& m) const {
-    LA_ASSERT(cols() == m.no_rows_);
-    std::vector<T> d(no_rows_ * m.cols());
-    check(Abi<T>::gemm_host(data_.data(), m.data_.data(), d.data(), no_rows_, cols(), m.cols()));
-    return Matrix(no_rows_, m.cols(), std::move(d));
+    LA_ASSERT(no_cols_ == m.no_rows_);
+    if (use_device(m, no_rows_ * no_cols_ * m.no_cols_)) {
+      Matrix out(no_rows_, m.no_cols_, Dirty{});
+      check(Abi<T>::gemm(device()->h, m.device()->h, out.dev_->h, no_rows_, no_cols_, m.no_cols_));
+      return out;
+    }
+    std::vector<T> d(no_rows_ * m.no_cols_);
+    check(Abi<T>::gemm_host(get_data().data(), m.get_data().data(), d.data(), no_rows_, no_cols_, m.no_cols_));
+    return Matrix(no_rows_, m.no_cols_, std::move(d));
   }
   // Matrix::mmul, mmatrix.rs:82-98
   Matrix& mmul(const Matrix& m, Matrix& dst) const {
-    LA_ASSERT(cols() == m.no_rows_);
+    LA_ASSERT(no_cols_ == m.no_rows_);
     LA_ASSERT(dst.rows() == no_rows_);
     LA_ASSERT(dst.cols() == m.cols());
-    check(Abi<T>::gemm_host(data_.data(), m.data_.data(), dst.data_.data(), no_rows_, cols(), m.cols()));
+    if (use_device(m, no_rows_ * no_cols_ * m.no_cols_)) {
+      if (!dst.dev_) dst.dev_ = std::make_shared<detail::DevBuf>(dst.no_rows_ * dst.no_cols_ * sizeof(T));
+      check(Abi<T>::gemm(device()->h, m.device()->h, dst.dev_->h, no_rows_, no_cols_, m.no_cols_));
+      dst.dev_valid_ = true;
+      dst.host_valid_ = false;
+      return dst;
+    }
+    check(Abi<T>::gemm_host(get_data().data(), m.get_data().data(), dst.get_mut_data().data(), no_rows_, no_cols_, m.no_cols_));
     return dst;
+  }
+  // elementwise operators (mod.rs:487-527, :853-929) on the device copies when either operand has one
+  Matrix operator+(const Matrix& m) const { return elementwise(LA_EW_ADD, &m, T(0)); }
+  Matrix operator-(const Matrix& m) const { return elementwise(LA_EW_SUB, &m, T(0)); }
+  Matrix operator-() const { return elementwise(LA_EW_NEG, nullptr, T(0)); }
+  Matrix scale(T factor) const { return elementwise(LA_EW_SCALE, nullptr, factor); }
+  Matrix elem_mul(const Matrix& m) const { return elementwise(LA_EW_MUL, &m, T(0)); }
+  Matrix elem_div(const Matrix& m) const { return elementwise(LA_EW_DIV, &m, T(0)); }
+  T frobenius_norm() const {  // mod.rs:1094-1101
+    T out = T(0);
+    check(Abi<T>::reduce(LA_RED_SUMSQ, device()->h, nullptr, no_rows_ * no_cols_, &out));
+    return out;
   }
 
   // LU callers, mod.rs:1025-1047 (each re-factorises, like the reference)
@@ -126,6 +217,11 @@ class Matrix {
   std::optional<Matrix> solve(const Matrix& b) const { return LUDecomposition<T>(*this).solve(b); }
   std::optional<Matrix> inverse() const {
     LA_ASSERT(no_rows_ == cols());
+    if (Abi<T>::device_backed && dev_valid_) {  // the identity is generated in HBM as well
+      Matrix eye(no_rows_, no_rows_, Dirty{});
+      check(Abi<T>::identity(eye.dev_->h, no_rows_));
+      return LUDecomposition<T>(*this).solve(eye);
+    }
     return LUDecomposition<T>(*this).solve(Matrix::id(no_rows_, no_rows_));
   }
   bool is_singular() const { return !is_non_singular(); }
@@ -133,10 +229,70 @@ class Matrix {
     LA_ASSERT(no_rows_ == cols());
     return LUDecomposition<T>(*this).is_non_singular();
   }
+  // mod.rs:1049-1057: (r.t() * &r).inverse().unwrap() * &self.t(), r = QRDecomposition::new(self).get_r()
+  Matrix pinverse() const {
+    Matrix r = QRDecomposition<T>(*this).get_r();
+    auto inv = (r.t() * r).inverse();
+    if (!inv.has_value()) throw Panic("called `Option::unwrap()` on a `None` value");
+    return *inv * t();
+  }
+
+  // ---- device backing (not part of the reference API) ----
+  bool on_device() const { return dev_valid_; }          // a current copy lives in HBM
+  bool host_materialised() const { return host_valid_; }  // a current copy lives in the host Vec
+  // current device copy, uploading the host Vec if necessary (kept for later operations)
+  const std::shared_ptr<detail::DevBuf>& device() const {
+    if (!dev_valid_) {
+      if (!dev_) dev_ = std::make_shared<detail::DevBuf>(no_rows_ * no_cols_ * sizeof(T));
+      check(la_buf_upload(dev_->h, 0, host_.data(), host_.size() * sizeof(T)));
+      dev_valid_ = true;
+    }
+    return dev_;
+  }
+  // result of a device operation: a fresh device buffer (alloc_dirty_vec, internalutil.rs:7-13), no host copy yet
+  struct Dirty {};
+  Matrix(size_t no_rows, size_t no_cols, Dirty)
+      : no_rows_(no_rows), no_cols_(no_cols), host_valid_(false),
+        dev_(std::make_shared<detail::DevBuf>(no_rows * no_cols * sizeof(T))), dev_valid_(true) {
+    LA_ASSERT(no_rows > 0 && no_cols > 0);
+  }
 
  private:
-  size_t no_rows_;
-  std::vector<T> data_;
+  bool use_device(const Matrix& other, size_t work) const {
+    return Abi<T>::device_backed && (dev_valid_ || other.dev_valid_ || work >= kDeviceResidentMinWork);
+  }
+  void sync_host() const {
+    if (!host_valid_) {
+      host_.resize(no_rows_ * no_cols_);
+      check(la_buf_download(dev_->h, 0, host_.data(), host_.size() * sizeof(T)));
+      host_valid_ = true;
+    }
+  }
+  Matrix elementwise(int op, const Matrix* m, T scalar) const {
+    if (m) {
+      LA_ASSERT(no_rows_ == m->no_rows_);
+      LA_ASSERT(no_cols_ == m->no_cols_);
+    }
+    if (Abi<T>::device_backed) {
+      Matrix out(no_rows_, no_cols_, Dirty{});
+      check(Abi<T>::elementwise(op, device()->h, m ? m->device()->h : nullptr, scalar, out.dev_->h, no_rows_ * no_cols_));
+      return out;
+    }
+    const auto& x = get_data();
+    std::vector<T> d(x.size());
+    for (size_t i = 0; i < x.size(); ++i) {
+      const T y = m ? m->get_data()[i] : T(0);
+      d[i] = op == LA_EW_ADD ? x[i] + y : op == LA_EW_SUB ? x[i] - y : op == LA_EW_MUL ? x[i] * y
+             : op == LA_EW_DIV ? x[i] / y : op == LA_EW_SCALE ? scalar * x[i] : -x[i];
+    }
+    return Matrix(no_rows_, no_cols_, std::move(d));
+  }
+
+  size_t no_rows_, no_cols_;
+  mutable std::vector<T> host_;
+  mutable bool host_valid_ = true;
+  mutable std::shared_ptr<detail::DevBuf> dev_;
+  mutable bool dev_valid_ = false;
 };
 
 // the m! macro: la::m<double>({{1, 2}, {3, 4}})
@@ -152,18 +308,6 @@ Matrix<T> m(std::initializer_list<std::initializer_list<T>> rows) {
   return Matrix<T>(nr, nc, std::move(d));
 }
 
-namespace detail {
-struct DevBuf {
-  la_buf* h = nullptr;
-  explicit DevBuf(size_t bytes) { check(la_buf_alloc(bytes, 0, &h)); }
-  DevBuf(const DevBuf&) = delete;
-  DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : h(o.h) { o.h = nullptr; }
-  ~DevBuf() {
-    if (h) la_buf_free(h);
-  }
-};
-}  // namespace detail
 
 // LUDecomposition<T>, lu.rs:95-101.  The packed factors stay resident in HBM; host copies are made on demand.
 template <typename T>
@@ -171,7 +315,9 @@ class LUDecomposition {
  public:
   explicit LUDecomposition(const Matrix<T>& a)  // LUDecomposition::new, lu.rs:104-168
       : m_(a.rows()), n_(a.cols()), lu_(a.rows() * a.cols() * sizeof(T)), piv_(a.rows()) {
-    check(la_buf_upload(lu_.h, 0, a.get_data().data(), m_ * n_ * sizeof(T)));  // ludata = a.get_data().clone()
+    // ludata = a.get_data().clone(): device to device when `a` already lives in HBM
+    if (a.on_device()) check(la_buf_copy(lu_.h, a.device()->h, m_ * n_ * sizeof(T)));
+    else check(la_buf_upload(lu_.h, 0, a.get_data().data(), m_ * n_ * sizeof(T)));
     int sign = 1;
     check(Abi<T>::factor(lu_.h, m_, n_, piv_.data(), &sign));
     pospivsign_ = sign != 0;
@@ -221,13 +367,10 @@ class LUDecomposition {
   std::optional<Matrix<T>> solve(const Matrix<T>& b) const {  // lu.rs:237-278
     LA_ASSERT(b.rows() == m_);
     if (!is_non_singular()) return std::nullopt;
-    size_t nx = b.cols(), bytes = m_ * nx * sizeof(T);
-    detail::DevBuf db(bytes), dx(bytes);
-    check(la_buf_upload(db.h, 0, b.get_data().data(), bytes));
-    check(Abi<T>::solve(lu_.h, m_, n_, piv_.data(), db.h, nx, dx.h));
-    std::vector<T> x(m_ * nx);
-    check(la_buf_download(dx.h, 0, x.data(), bytes));
-    return Matrix<T>(m_, nx, std::move(x));
+    LA_ASSERT(m_ == n_);  // lu.rs:257-275 index X with n
+    Matrix<T> x(m_, b.cols(), typename Matrix<T>::Dirty{});  // stays in HBM until somebody asks for get_data()
+    check(Abi<T>::solve(lu_.h, m_, n_, piv_.data(), b.device()->h, b.cols(), x.device()->h));
+    return x;
   }
 
  private:
@@ -235,6 +378,68 @@ class LUDecomposition {
   detail::DevBuf lu_;
   std::vector<uint64_t> piv_;
   bool pospivsign_ = true;
+};
+
+// QRDecomposition<T>, qr.rs:20-238.  The packed factors, rdiag and the block factors of the compact-WY form stay in HBM.
+template <typename T>
+class QRDecomposition {
+ public:
+  explicit QRDecomposition(const Matrix<T>& a)  // QRDecomposition::new, qr.rs:26-43
+      : m_(a.rows()), n_(a.cols()), qr_(a.rows() * a.cols() * sizeof(T)),
+        rd_(((a.rows() < a.cols() ? a.rows() : a.cols()) + 1) * sizeof(T)), tm_(tmat_bytes(a.rows(), a.cols())),
+        rdiag_(a.rows() < a.cols() ? a.rows() : a.cols()) {
+    if (a.on_device()) check(la_buf_copy(qr_.h, a.device()->h, m_ * n_ * sizeof(T)));
+    else check(la_buf_upload(qr_.h, 0, a.get_data().data(), m_ * n_ * sizeof(T)));
+    check(Abi<T>::qr_factor(qr_.h, m_, n_, rd_.h, tm_.h));
+    check(la_buf_download(rd_.h, 0, rdiag_.data(), rdiag_.size() * sizeof(T)));
+  }
+  bool is_full_rank() const {  // qr.rs:110-117: rdiag[j] for j < cols -- out of bounds when m < n
+    for (size_t j = 0; j < n_; ++j) {
+      LA_ASSERT(j < rdiag_.size());
+      if (rdiag_[j] == T(0)) return false;
+    }
+    return true;
+  }
+  const std::vector<T>& get_rdiag() const { return rdiag_; }
+  Matrix<T> get_qr() const {
+    std::vector<T> d(m_ * n_);
+    check(la_buf_download(qr_.h, 0, d.data(), d.size() * sizeof(T)));
+    return Matrix<T>(m_, n_, std::move(d));
+  }
+  Matrix<T> get_h() const {  // qr.rs:121-135
+    auto d = get_qr().get_data();
+    for (size_t i = 0; i < m_; ++i)
+      for (size_t j = i + 1; j < n_; ++j) d[i * n_ + j] = T(0);
+    return Matrix<T>(m_, n_, std::move(d));
+  }
+  Matrix<T> get_r() const {  // qr.rs:138-152, left in HBM
+    Matrix<T> r(m_, n_, typename Matrix<T>::Dirty{});
+    check(Abi<T>::qr_get_r(qr_.h, m_, n_, rd_.h, r.device()->h));
+    return r;
+  }
+  Matrix<T> get_q() const {  // qr.rs:155-194
+    Matrix<T> q(m_, m_, typename Matrix<T>::Dirty{});
+    check(Abi<T>::qr_get_q(qr_.h, m_, n_, tm_.h, q.device()->h));
+    return q;
+  }
+  std::optional<Matrix<T>> solve(const Matrix<T>& b) const {  // qr.rs:199-238, quirks included
+    LA_ASSERT(b.rows() == m_);
+    if (!is_full_rank()) return std::nullopt;
+    LA_ASSERT(n_ * b.cols() == m_ * b.cols());  // Matrix::new(cols, nx, <m * nx values>), :237
+    Matrix<T> x(m_, b.cols(), typename Matrix<T>::Dirty{});
+    check(Abi<T>::qr_solve(qr_.h, m_, n_, rd_.h, b.device()->h, b.cols(), x.device()->h));
+    return x;
+  }
+
+ private:
+  static size_t tmat_bytes(size_t m, size_t n) {
+    size_t e = 0;
+    check(la_qr_tmat_elems(m, n, 0, sizeof(T), &e));
+    return e * sizeof(T);
+  }
+  size_t m_, n_;
+  detail::DevBuf qr_, rd_, tm_;
+  std::vector<T> rdiag_;
 };
 
 // CholeskyDecomposition<T>, cholesky.rs:52-144.  `make` is the reference's `new`: empty unless the matrix is square,
@@ -245,7 +450,8 @@ class CholeskyDecomposition {
   static std::optional<CholeskyDecomposition<T>> make(const Matrix<T>& a) {
     if (a.rows() != a.cols()) return std::nullopt;  // cholesky.rs:57-59
     CholeskyDecomposition<T> c(a.rows());
-    check(la_buf_upload(c.l_.h, 0, a.get_data().data(), c.n_ * c.n_ * sizeof(T)));
+    if (a.on_device()) check(la_buf_copy(c.l_.h, a.device()->h, c.n_ * c.n_ * sizeof(T)));
+    else check(la_buf_upload(c.l_.h, 0, a.get_data().data(), c.n_ * c.n_ * sizeof(T)));
     int ok = 0;
     check(Abi<T>::chol_factor(c.l_.h, c.n_, &ok));
     if (!ok) return std::nullopt;  // not symmetric (:91-93) or not positive definite (:99-102)
@@ -258,13 +464,9 @@ class CholeskyDecomposition {
   }
   Matrix<T> solve(const Matrix<T>& b) const {  // cholesky.rs:116-144
     LA_ASSERT(b.rows() == n_);
-    size_t nx = b.cols(), bytes = n_ * nx * sizeof(T);
-    detail::DevBuf db(bytes), dx(bytes);
-    check(la_buf_upload(db.h, 0, b.get_data().data(), bytes));
-    check(Abi<T>::chol_solve(l_.h, n_, db.h, nx, dx.h));
-    std::vector<T> x(n_ * nx);
-    check(la_buf_download(dx.h, 0, x.data(), bytes));
-    return Matrix<T>(n_, nx, std::move(x));
+    Matrix<T> x(n_, b.cols(), typename Matrix<T>::Dirty{});
+    check(Abi<T>::chol_solve(l_.h, n_, b.device()->h, b.cols(), x.device()->h));
+    return x;
   }
   CholeskyDecomposition(CholeskyDecomposition&&) noexcept = default;
 

@@ -1,6 +1,6 @@
 // test_la.cpp -- the reference's unit tests for the hot path, written against la.hpp (C++ mirror of the crate API).
 // Sources: src/matrix/mod.rs:1479-1571, src/matrix/mmatrix.rs:234-259, src/decomp/lu.rs:281-375,
-// src/decomp/cholesky.rs:146-183.
+// src/decomp/cholesky.rs:146-183, src/decomp/qr.rs:241-262; plus the device-backed Matrix contract.
 // Without a GPU every compute call throws la::LaError (no CPU fallback); `--require-gpu` turns that into a failure,
 // otherwise the binary only checks the host-side contract (panics before FFI) and reports SKIP for the rest.
 #include <cmath>
@@ -130,6 +130,69 @@ int main(int argc, char** argv) {
     CHECK(s.has_value());
     CHECK(s->solve(la::m<double>({{1}, {2}, {3}})).approx_eq(la::m<double>({{-1}, {3}, {3}})));
     should_panic([&] { s->solve(la::m<double>({{1}, {2}, {3}, {4}})); });
+  });
+  run("qr_test / m_over_n / n_over_m (qr.rs:241-262)", [] {
+    typedef la::QRDecomposition<double> QR;
+    for (auto a : {la::m<double>({{12, -51, 4}, {6, 167, -68}, {-4, 24, -41}}), la::m<double>({{1, 2}, {3, 4}, {5, 6}}),
+                   la::m<double>({{1, 2, 3}, {4, 5, 6}})}) {
+      QR qr(a);
+      CHECK((qr.get_q() * qr.get_r()).approx_eq(a));
+    }
+    QR first(la::m<double>({{12, -51, 4}, {6, 167, -68}, {-4, 24, -41}}));
+    CHECK(std::fabs(first.get_rdiag()[0] + 14.0) < 1e-12 && std::fabs(first.get_qr().get(0, 0) - 26.0) < 1e-12);
+    CHECK(first.is_full_rank());
+    should_panic([] { QR(la::m<double>({{1, 2, 3}, {4, 5, 6}})).is_full_rank(); });                // rdiag[j] out of bounds, qr.rs:112
+    should_panic([] { QR(la::m<double>({{1, 2}, {3, 4}, {5, 6}})).solve(la::m<double>({{1}, {2}, {3}})); });  // Matrix::new, qr.rs:237
+    CHECK(!QR(la::m<double>({{0, 0}, {0, 0}})).solve(la::m<double>({{1}, {2}})).has_value());     // not full rank -> None
+  });
+  run("test_pinverse (mod.rs:1549)", [] {
+    auto a = la::m<double>({{1, 2}, {3, 4}, {5, 6}});
+    CHECK((a.pinverse() * a).approx_eq(Md::id(2, 2)));
+  });
+  run("device-backed Matrix: a * b * c keeps intermediates in HBM (SURVEY H2)", [] {
+    const size_t n = 192;
+    std::vector<double> da(n * n), db(n * n), dc(n * n);
+    for (size_t i = 0; i < n * n; ++i) {
+      da[i] = double((i * 7) % 13) - 6.0;
+      db[i] = double((i * 5) % 11) - 5.0;
+      dc[i] = double((i * 3) % 7) - 3.0;
+    }
+    Md a(n, n, da), b(n, n, db), c(n, n, dc);
+    Md ab = a * b;                    // 192^3 multiply-adds >= the device-resident threshold
+    CHECK(ab.on_device() && !ab.host_materialised());
+    CHECK(a.on_device() && a.host_materialised());   // the upload is cached next to the host Vec
+    Md abc = ab * c;
+    CHECK(abc.on_device() && !abc.host_materialised() && !ab.host_materialised());  // ab never came back to the host
+    // small integers: every product and sum is exact, so any evaluation order gives the same doubles
+    std::vector<double> ref(n * n, 0.0), tmp(n * n, 0.0);
+    for (size_t i = 0; i < n; ++i)
+      for (size_t k = 0; k < n; ++k)
+        for (size_t j = 0; j < n; ++j) tmp[i * n + j] += da[i * n + k] * db[k * n + j];
+    for (size_t i = 0; i < n; ++i)
+      for (size_t k = 0; k < n; ++k)
+        for (size_t j = 0; j < n; ++j) ref[i * n + j] += tmp[i * n + k] * dc[k * n + j];
+    CHECK(abc.get_data() == ref);     // get_data() downloads on first use
+    CHECK(abc.host_materialised());
+    // get_mut_data() makes the device copy stale: the next product sees the new host values
+    a.get_mut_data()[0] += 1.0;
+    CHECK(!a.on_device());
+    Md ab2 = a * b;
+    CHECK(ab2.get(0, 0) == tmp[0] + db[0]);
+    // transposes, differences and norms of device-resident values stay there too
+    Md d = (ab.t() - ab.t());
+    CHECK(d.on_device() && d.frobenius_norm() == 0.0);
+    should_panic([&] { a + la::m<double>({{1, 2}, {3, 4}}); });
+  });
+  run("device-backed inverse chain: (a * a.t() + shift).inverse() on device", [] {
+    const size_t n = 160;
+    std::vector<double> da(n * n);
+    for (size_t i = 0; i < n * n; ++i) da[i] = double((i * 37) % 101) / 101.0;
+    Md a(n, n, da);
+    Md spd = a * a.t() + Md::id(n, n).scale(double(n));
+    CHECK(spd.on_device() && !spd.host_materialised());
+    auto inv = spd.inverse();
+    CHECK(inv.has_value() && inv->on_device() && !spd.host_materialised());
+    CHECK((spd * *inv).approx_eq(Md::id(n, n)));
   });
   printf("%d passed, %d skipped, %d failed\n", passed, skipped, failures);
   return failures ? 1 : 0;

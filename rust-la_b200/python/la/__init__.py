@@ -20,7 +20,7 @@ import numpy as np
 from . import _cabi
 from ._cabi import LaError, lib, check  # noqa: F401
 
-__all__ = ["Matrix", "DeviceMatrix", "LUDecomposition", "CholeskyDecomposition", "m", "Panic", "LaError", "APPROX_EPS"]
+__all__ = ["Matrix", "DeviceMatrix", "LUDecomposition", "CholeskyDecomposition", "QRDecomposition", "m", "Panic", "LaError", "APPROX_EPS"]
 
 APPROX_EPS = 1e-6  # src/approxeq.rs:20,36
 
@@ -159,6 +159,11 @@ class Matrix:
         _assert(self.no_rows == self.cols(), "self.no_rows == self.cols()")
         return LUDecomposition.new(self).is_non_singular()
 
+    def pinverse(self):
+        """src/matrix/mod.rs:1049-1057: `(r.t() * &r).inverse().unwrap() * &self.t()` with r = QRDecomposition::get_r;
+        the whole chain runs on device-resident intermediates."""
+        return DeviceMatrix.from_matrix(self).pinverse().to_matrix()
+
 
 class _DeviceBuf:
     """RAII wrapper over la_buf (the device backing of a Matrix / LUDecomposition)."""
@@ -167,6 +172,7 @@ class _DeviceBuf:
         self.handle = ctypes.c_void_p()
         check(lib().la_buf_alloc(nbytes, device, ctypes.byref(self.handle)))
         self.nbytes = nbytes
+        self.device = device
 
     def upload(self, arr):
         check(lib().la_buf_upload(self.handle, 0, _ptr(arr), arr.nbytes))
@@ -265,8 +271,8 @@ class LUDecomposition:
         _assert(self._m == self._n, "solve needs a square factorisation (lu.rs:257-275 index with n)")
         nx = b.cols()
         suf = _suffix(self._dtype)
-        bbuf = _DeviceBuf(b.data.nbytes, 0)
-        xbuf = _DeviceBuf(b.data.nbytes, 0)
+        bbuf = _DeviceBuf(b.data.nbytes, self._buf.device)
+        xbuf = _DeviceBuf(b.data.nbytes, self._buf.device)
         bbuf.upload(b.data)
         check(getattr(lib(), f"la_lu_solve_{suf}")(self._buf.handle, self._m, self._n, _ptr(self.piv), bbuf.handle, nx,
                                                    xbuf.handle))
@@ -306,11 +312,91 @@ class CholeskyDecomposition:
         _assert(b.rows() == self._n, "l.rows() == b.rows()")  # :118
         _assert(b.data.dtype == self._dtype, "same element type")
         nx = b.cols()
-        bbuf = _DeviceBuf(b.data.nbytes)
-        xbuf = _DeviceBuf(b.data.nbytes)
+        bbuf = _DeviceBuf(b.data.nbytes, self._buf.device)
+        xbuf = _DeviceBuf(b.data.nbytes, self._buf.device)
         bbuf.upload(b.data)
         check(getattr(lib(), f"la_chol_solve_{_suffix(self._dtype)}")(self._buf.handle, self._n, bbuf.handle, nx, xbuf.handle))
         x = np.empty(self._n * nx, dtype=self._dtype)
+        xbuf.download(x)
+        return Matrix(self._n, x)
+
+
+class QRDecomposition:
+    """QRDecomposition<T>, src/decomp/qr.rs:20-23: `{ qr: Matrix<T>, rdiag: Vec<T> }`.  The packed factors stay in HBM
+    together with the block factors T' of the compact-WY form (needed by get_q); host copies are made lazily."""
+
+    def __init__(self, m, n, dtype, buf, rdiag_buf, tmat_buf):
+        self._m, self._n, self._dtype = m, n, np.dtype(dtype)
+        self._buf, self._rdiag_buf, self._tmat_buf = buf, rdiag_buf, tmat_buf
+        self._qr_host = None
+        self.rdiag = np.empty(min(m, n), dtype=self._dtype)
+        rdiag_buf.download(self.rdiag)
+
+    @staticmethod
+    def new(a, device=0):
+        """qr.rs:26-43."""
+        m, n, suf = a.rows(), a.cols(), _suffix(a.data.dtype)
+        isz = a.data.dtype.itemsize
+        buf = _DeviceBuf(a.data.nbytes, device)
+        buf.upload(a.data)  # qrdata = m.get_data().clone()
+        te = ctypes.c_size_t(0)
+        check(lib().la_qr_tmat_elems(m, n, device, isz, ctypes.byref(te)))
+        rd = _DeviceBuf(max(min(m, n) * isz, 8), device)
+        tm = _DeviceBuf(te.value * isz, device)
+        check(getattr(lib(), f"la_qr_factor_{suf}")(buf.handle, m, n, rd.handle, tm.handle))
+        return QRDecomposition(m, n, a.data.dtype, buf, rd, tm)
+
+    def get_qr(self):
+        if self._qr_host is None:
+            h = np.empty(self._m * self._n, dtype=self._dtype)
+            self._buf.download(h)
+            self._qr_host = Matrix(self._m, h)
+        return self._qr_host
+
+    def is_full_rank(self):
+        """qr.rs:110-117: loops j over 0..cols and indexes rdiag[j] -- out of bounds (a panic) when m < n."""
+        for j in range(self._n):
+            _assert(j < self.rdiag.size, "index out of bounds: rdiag[j] (qr.rs:112)")
+            if self.rdiag[j] == 0:
+                return False
+        return True
+
+    def get_h(self):
+        """qr.rs:121-135 (host-side unpack): the lower trapezoid holding the Householder vectors."""
+        return Matrix(self._m, np.ascontiguousarray(np.tril(self.get_qr().to_numpy())).reshape(-1))
+
+    def get_r(self):
+        """qr.rs:138-152."""
+        return self.get_r_device().to_matrix()
+
+    def get_r_device(self):
+        out = DeviceMatrix(self._m, self._n, self._dtype, _DeviceBuf(self._m * self._n * self._dtype.itemsize, self._buf.device))
+        check(getattr(lib(), f"la_qr_get_r_{_suffix(self._dtype)}")(self._buf.handle, self._m, self._n, self._rdiag_buf.handle,
+                                                                    out.buf.handle))
+        return out
+
+    def get_q(self):
+        """qr.rs:155-194: m x m, the block reflectors applied in reverse order on the device."""
+        out = DeviceMatrix(self._m, self._m, self._dtype, _DeviceBuf(self._m * self._m * self._dtype.itemsize, self._buf.device))
+        check(getattr(lib(), f"la_qr_get_q_{_suffix(self._dtype)}")(self._buf.handle, self._m, self._n, self._tmat_buf.handle,
+                                                                    out.buf.handle))
+        return out.to_matrix()
+
+    def solve(self, b):
+        """qr.rs:199-238, quirks included: None unless full rank; the result is `Matrix::new(cols, nx, <m * nx values>)`,
+        which panics unless m == n (:237)."""
+        _assert(b.rows() == self._m, "b.rows() == self.qr.rows()")  # :200
+        _assert(b.data.dtype == self._dtype, "same element type")
+        if not self.is_full_rank():
+            return None
+        nx = b.cols()
+        _assert(self._n * nx == self._m * nx, "no_rows * no_cols == data.len()")  # Matrix::new, mod.rs:208
+        bbuf = _DeviceBuf(b.data.nbytes, self._buf.device)
+        xbuf = _DeviceBuf(b.data.nbytes, self._buf.device)
+        bbuf.upload(b.data)
+        check(getattr(lib(), f"la_qr_solve_{_suffix(self._dtype)}")(self._buf.handle, self._m, self._n, self._rdiag_buf.handle,
+                                                                    bbuf.handle, nx, xbuf.handle))
+        x = np.empty(self._m * nx, dtype=self._dtype)
         xbuf.download(x)
         return Matrix(self._n, x)
 
@@ -353,7 +439,7 @@ class DeviceMatrix:
         return self.no_cols
 
     def _like(self, rows, cols):
-        return DeviceMatrix(rows, cols, self.dtype, _DeviceBuf(rows * cols * self.dtype.itemsize))
+        return DeviceMatrix(rows, cols, self.dtype, _DeviceBuf(rows * cols * self.dtype.itemsize, self.buf.device))
 
     def t(self):
         out = self._like(self.no_cols, self.no_rows)
@@ -391,10 +477,87 @@ class DeviceMatrix:
         check(getattr(lib(), f"la_lu_is_nonsingular_{suf}")(lu.buf.handle, n, ctypes.byref(ok)))
         if not ok.value:
             return None
-        eye = DeviceMatrix.id(n, self.dtype)
+        eye = DeviceMatrix.id(n, self.dtype, self.buf.device)
         out = self._like(n, n)
         check(getattr(lib(), f"la_lu_solve_{suf}")(lu.buf.handle, n, n, _ptr(piv), eye.buf.handle, n, out.buf.handle))
         return out
+
+    # ---- elementwise operators and norms (mod.rs:487-527, :853-929, :1059-1115) on device-resident data ----
+    def _same_shape(self, other):
+        _assert(isinstance(other, DeviceMatrix), "rhs is a DeviceMatrix")
+        _assert(self.no_rows == other.no_rows, "self.no_rows == m.no_rows")
+        _assert(self.no_cols == other.no_cols, "self.cols() == m.cols()")
+        _assert(self.dtype == other.dtype, "same element type")
+
+    def _elementwise(self, op, other=None, scalar=0.0):
+        out = self._like(self.no_rows, self.no_cols)
+        check(getattr(lib(), f"la_elementwise_{_suffix(self.dtype)}")(op, self.buf.handle, other.buf.handle if other else None,
+                                                                      scalar, out.buf.handle, self.no_rows * self.no_cols))
+        return out
+
+    def __add__(self, other):
+        self._same_shape(other)
+        return self._elementwise(_cabi.LA_EW_ADD, other)
+
+    def __sub__(self, other):
+        self._same_shape(other)
+        return self._elementwise(_cabi.LA_EW_SUB, other)
+
+    def __neg__(self):
+        return self._elementwise(_cabi.LA_EW_NEG)
+
+    def scale(self, factor):
+        return self._elementwise(_cabi.LA_EW_SCALE, None, float(factor))
+
+    def elem_mul(self, other):
+        self._same_shape(other)
+        return self._elementwise(_cabi.LA_EW_MUL, other)
+
+    def elem_div(self, other):
+        self._same_shape(other)
+        return self._elementwise(_cabi.LA_EW_DIV, other)
+
+    def _reduce(self, kind, other=None):
+        out = ctypes.c_double(0) if self.dtype == np.float64 else ctypes.c_float(0)
+        check(getattr(lib(), f"la_reduce_{_suffix(self.dtype)}")(kind, self.buf.handle, other.buf.handle if other else None,
+                                                                 self.no_rows * self.no_cols, ctypes.byref(out)))
+        return self.dtype.type(out.value)
+
+    def frobenius_norm(self):
+        return self._reduce(_cabi.LA_RED_SUMSQ)
+
+    def vector_euclidean_norm(self):
+        _assert(self.no_cols == 1, "self.cols() == 1")
+        return self._reduce(_cabi.LA_RED_SUMSQ)
+
+    def vector_1_norm(self):
+        _assert(self.no_cols == 1, "self.cols() == 1")
+        return self._reduce(_cabi.LA_RED_ABS_SUM)
+
+    def vector_inf_norm(self):
+        _assert(self.no_cols == 1, "self.cols() == 1")
+        return self._reduce(_cabi.LA_RED_ABS_MAX)
+
+    def dot(self, other):
+        """mod.rs:529-: both are vectors of the same length."""
+        _assert(self.no_rows == other.no_rows and self.no_cols == 1 and other.no_cols == 1, "two column vectors of one length")
+        return self._reduce(_cabi.LA_RED_DOT, other)
+
+    def pinverse(self):
+        """mod.rs:1049-1057: A+ = (R'R)^-1 A' with R from the QR factorisation; panics (unwrap) when R'R is singular."""
+        m, n, suf = self.no_rows, self.no_cols, _suffix(self.dtype)
+        isz, dev = self.dtype.itemsize, self.buf.device
+        qr = self._like(m, n)
+        check(lib().la_buf_copy(qr.buf.handle, self.buf.handle, m * n * isz))
+        te = ctypes.c_size_t(0)
+        check(lib().la_qr_tmat_elems(m, n, dev, isz, ctypes.byref(te)))
+        rd, tm = _DeviceBuf(max(min(m, n) * isz, 8), dev), _DeviceBuf(te.value * isz, dev)
+        check(getattr(lib(), f"la_qr_factor_{suf}")(qr.buf.handle, m, n, rd.handle, tm.handle))
+        r = self._like(m, n)
+        check(getattr(lib(), f"la_qr_get_r_{suf}")(qr.buf.handle, m, n, rd.handle, r.buf.handle))
+        inv = (r.t() * r).inverse()
+        _assert(inv is not None, "called `Option::unwrap()` on a `None` value")
+        return inv * self.t()
 
 
 def m(spec, dtype=None):

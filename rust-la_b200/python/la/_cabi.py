@@ -9,6 +9,8 @@ LIB_PATH = os.environ.get("LA_B200_LIB") or os.path.normpath(os.path.join(_PKG, 
 LA_OK, LA_ERR_INVALID, LA_ERR_CUDA, LA_ERR_NOMEM, LA_ERR_NO_DEVICE, LA_ERR_UNSUPPORTED = range(6)
 LA_GEMM_ASSIGN, LA_GEMM_SUB, LA_GEMM_ADD = 0, 1, 2
 LA_F32_3XTF32, LA_F32_TF32 = 0, 1
+LA_EW_ADD, LA_EW_SUB, LA_EW_MUL, LA_EW_DIV, LA_EW_SCALE, LA_EW_NEG = range(6)
+LA_RED_SUMSQ, LA_RED_ABS_SUM, LA_RED_ABS_MAX, LA_RED_DOT = range(4)
 
 
 class LaError(RuntimeError):
@@ -91,6 +93,27 @@ SIGNATURES = {
     "la_chol_solve_f32": ([_p, _sz, _p, _sz, _p], _i),
     "la_chol_solve_f64_host": ([_p, _sz, _p, _sz, _p], _i),
     "la_chol_solve_f32_host": ([_p, _sz, _p, _sz, _p], _i),
+    "la_qr_tmat_elems": ([_sz, _sz, _i, _sz, _psz], _i),
+    "la_qr_factor_f64": ([_p, _sz, _sz, _p, _p], _i),
+    "la_qr_factor_f32": ([_p, _sz, _sz, _p, _p], _i),
+    "la_qr_factor_f64_host": ([_p, _p, _p, _sz, _sz], _i),
+    "la_qr_factor_f32_host": ([_p, _p, _p, _sz, _sz], _i),
+    "la_qr_factor_f64_dev": ([_p, _sz, _sz, _p, _p, _p], _i),
+    "la_qr_factor_f32_dev": ([_p, _sz, _sz, _p, _p, _p], _i),
+    "la_qr_get_r_f64": ([_p, _sz, _sz, _p, _p], _i),
+    "la_qr_get_r_f32": ([_p, _sz, _sz, _p, _p], _i),
+    "la_qr_get_q_f64": ([_p, _sz, _sz, _p, _p], _i),
+    "la_qr_get_q_f32": ([_p, _sz, _sz, _p, _p], _i),
+    "la_qr_solve_f64": ([_p, _sz, _sz, _p, _p, _sz, _p], _i),
+    "la_qr_solve_f32": ([_p, _sz, _sz, _p, _p, _sz, _p], _i),
+    "la_elementwise_f64": ([_i, _p, _p, ctypes.c_double, _p, _sz], _i),
+    "la_elementwise_f32": ([_i, _p, _p, ctypes.c_float, _p, _sz], _i),
+    "la_elementwise_f64_dev": ([_i, _p, _p, ctypes.c_double, _p, _sz, _p], _i),
+    "la_elementwise_f32_dev": ([_i, _p, _p, ctypes.c_float, _p, _sz, _p], _i),
+    "la_reduce_f64": ([_i, _p, _p, _sz, ctypes.POINTER(ctypes.c_double)], _i),
+    "la_reduce_f32": ([_i, _p, _p, _sz, ctypes.POINTER(ctypes.c_float)], _i),
+    "la_reduce_f64_dev": ([_i, _p, _p, _sz, ctypes.POINTER(ctypes.c_double), _p], _i),
+    "la_reduce_f32_dev": ([_i, _p, _p, _sz, ctypes.POINTER(ctypes.c_float), _p], _i),
     "la_identity_f64": ([_p, _sz], _i),
     "la_identity_f32": ([_p, _sz], _i),
     "la_transpose_f64": ([_p, _p, _sz, _sz], _i),

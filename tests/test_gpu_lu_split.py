@@ -16,7 +16,7 @@ CHILD = textwrap.dedent("""
     import numpy as np
     from oracle import oracle
     from la import LUDecomposition, Matrix
-    for n, m in ((700, 700), (1154, 1154), (900, 640), (640, 900)):
+    for n, m in ((700, 700), (1154, 1154), (900, 640), (640, 900), (1536, 1536), (2000, 1300)):
         a = oracle.fill((n, m), 1)
         ref_lu, ref_piv, ref_sign = oracle.lu(a)
         dec = LUDecomposition.new(Matrix.from_numpy(a))
@@ -35,3 +35,15 @@ def test_split_panel_forced_for_every_panel():
     env = dict(os.environ, LA_LU_SPLIT_ROWS="129")
     out = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "split ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("group", [2, 3, 4])
+def test_grouped_bulk_update_forced(group):
+    """Grouped trailing updates (lu.cu, LA_LU_GROUP / LA_LU_GROUP_ROWS: K = group * 128 bulk GEMMs, the chain catching up
+    the next panel's columns itself) are only taken for trailing matrices of >= 3072 rows by default; force them from the
+    first panel on, with and without split panels."""
+    for split in ("0", "129"):
+        env = dict(os.environ, LA_LU_GROUP=str(group), LA_LU_GROUP_ROWS="1", LA_LU_SPLIT_ROWS=split)
+        out = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "split ok" in out.stdout, out.stdout + out.stderr
