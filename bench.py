@@ -506,6 +506,71 @@ def main():
         del S0, CL, CBm, CX
 
     # =================================================================================================================
+    # QR n = 16384 and the streaming elementwise / norm kernels (rank 4), one GPU
+    # =================================================================================================================
+    qr_leg = None
+    stream_leg = None
+    if n_gpus == 1 and not args.skip_lu:
+        qn = 16384
+        A0 = LU = R = A = B = C = None
+        torch.cuda.empty_cache()
+        QA0 = torch.empty((qn, qn), dtype=f64, device=dev)
+        chk(L.la_fill_hash_f64_dev(QA0.data_ptr(), QA0.numel(), 1, 0, sp))
+        QRm = torch.empty_like(QA0)
+        te = ctypes.c_size_t(0)
+        chk(L.la_qr_tmat_elems(qn, qn, local_rank, 8, ctypes.byref(te)))
+        Qrd = torch.empty((qn,), dtype=f64, device=dev)
+        Qtm = torch.empty((te.value,), dtype=f64, device=dev)
+        q_ms = []
+        for it in range(1 + 3):
+            QRm.copy_(QA0)
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record(stream)
+            chk(L.la_qr_factor_f64_dev(QRm.data_ptr(), qn, qn, Qrd.data_ptr(), Qtm.data_ptr(), sp))
+            q1.record(stream)
+            torch.cuda.synchronize()
+            if it > 0:
+                q_ms.append(q0.elapsed_time(q1))
+        q_t = sum(q_ms) / len(q_ms)
+        # R'R = A'A (Q orthogonal): a backward-error style check that needs neither Q nor the oracle at this size
+        Rm = torch.triu(QRm, 1)
+        Rm.diagonal().copy_(Qrd)
+        qerr = float((Rm.T @ Rm - QA0.T @ QA0).norm() / (QA0.T @ QA0).norm())
+        q_flops = 4.0 / 3.0 * qn ** 3
+        qr_leg = {"workload": "f64 QR (Householder, compact WY) n=16384", "qr_ms": q_t, "qr_ms_min": min(q_ms),
+                  "qr_tflops": q_flops / (q_t * 1e-3) / 1e12, "flops_formula": "4/3 n^3",
+                  "rtr_minus_ata_rel": qerr}
+        del Rm, QRm, Qtm
+        # streaming kernels: C = A + B over 2 x 2 GiB in, 2 GiB out; ||A||_F over 2 GiB
+        SB = torch.empty_like(QA0)
+        SC = torch.empty_like(QA0)
+        chk(L.la_fill_hash_f64_dev(SB.data_ptr(), SB.numel(), 2, 0, sp))
+        cnt = QA0.numel()
+        for _ in range(2):
+            chk(L.la_elementwise_f64_dev(_cabi.LA_EW_ADD, QA0.data_ptr(), SB.data_ptr(), 0.0, SC.data_ptr(), cnt, sp))
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(5):
+            chk(L.la_elementwise_f64_dev(_cabi.LA_EW_ADD, QA0.data_ptr(), SB.data_ptr(), 0.0, SC.data_ptr(), cnt, sp))
+        s1.record(stream)
+        torch.cuda.synchronize()
+        add_ms = s0.elapsed_time(s1) / 5
+        nrm = ctypes.c_double(0)
+        chk(L.la_reduce_f64_dev(_cabi.LA_RED_SUMSQ, QA0.data_ptr(), None, cnt, ctypes.byref(nrm), sp))
+        t0 = time.perf_counter()
+        for _ in range(5):
+            chk(L.la_reduce_f64_dev(_cabi.LA_RED_SUMSQ, QA0.data_ptr(), None, cnt, ctypes.byref(nrm), sp))
+        nrm_ms = (time.perf_counter() - t0) * 1e3 / 5
+        hbm_peak = float(mp.get("hbm_gbs", 6650.0))
+        stream_leg = {"workload": "f64 elementwise add and Frobenius norm over 16384 x 16384 operands",
+                      "add_ms": add_ms, "add_gbs": 3 * 8.0 * cnt / (add_ms * 1e-3) / 1e9,
+                      "add_frac_of_hbm": 3 * 8.0 * cnt / (add_ms * 1e-3) / 1e9 / hbm_peak,
+                      "add_bit_identical_to_torch": bool(torch.equal(SC, QA0 + SB)),
+                      "frobenius_ms_incl_d2h_sync": nrm_ms, "frobenius_gbs": 8.0 * cnt / (nrm_ms * 1e-3) / 1e9,
+                      "frobenius_rel_diff_vs_torch": abs(nrm.value - float(QA0.norm())) / float(QA0.norm())}
+        del QA0, SB, SC
+
+    # =================================================================================================================
     # f32 GEMM 65536x1024 x 1024x16384 (configs[4]): tcgen05 kind::tf32 (the mode the config names) and the default 3xTF32
     # =================================================================================================================
     f32 = None
@@ -649,6 +714,8 @@ def main():
         "cpu_baseline": cpu,
         "lu": lu,
         "cholesky": chol,
+        "qr": qr_leg,
+        "streaming": stream_leg,
         "f32": f32,
     }
     print(json.dumps(line))

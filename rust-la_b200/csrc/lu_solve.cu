@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "la_common.cuh"
+#include "ll_exchange.cuh"
 
 namespace la {
 int gemm_f64_tensor(const double* A, size_t lda, const double* B, size_t ldb, double* C, size_t ldc, size_t m, size_t k,
@@ -318,6 +319,170 @@ solve_sweep_kernel(const double* __restrict__ LU, size_t n, const uint64_t* __re
     if (FORWARD ? rd > g : rd < g) *((volatile unsigned*)(flags + (size_t)rd * G + g)) = 1u;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Second-generation sweep (default): the same block-row ownership and cp.async streaming of LU, but
+//   * the 128 x 128 x 16 block products run on DMMA.8x8x4 (mma.sync m8n8k4 f64) with ALL eight warps: warp w owns rows
+//     [16 w, 16 w + 16) as 2 x 2 accumulator tiles; per 4-deep k-step it needs 4 shared-memory loads for 4 MMAs (the
+//     CUDA-core version needed 10 128-bit loads per 32 FMAs and ran on four warps);
+//   * the solved blocks travel as FLAGGED WORDS (value halves next to a per-call tag, ll_exchange.cuh): the producer
+//     stores its 128 x 16 block once, every consumer polls the data itself -- no __threadfence, no flag array, no
+//     separate fetch of X after the flag (one L2 round trip instead of three on the dependent chain).
+// Shared memory: two 64-column halves of the LU block (swizzled 16-byte chunks, as above) + the X block as the MMA's
+// B operand with a 24-double row stride (4 k-rows x 8 columns of a fragment load then cover all 32 banks twice).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int XS_LD = 24;
+constexpr int SWEEP2_SMEM = (2 * PB * PH + PB * XS_LD) * (int)sizeof(double);
+typedef LL<double>::word XWord;
+
+template <bool FORWARD>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1)
+solve_sweep_mma_kernel(const double* __restrict__ LU, size_t n, const uint64_t* __restrict__ piv, const double* __restrict__ B,
+                       double* __restrict__ X, int nx, XWord* __restrict__ xbuf /* [G][PB * 16] flagged words */,
+                       unsigned tag, const double* __restrict__ Winv /* [G][128][128] inverted diagonal blocks */) {
+  extern __shared__ __align__(16) unsigned char sweep_smem[];
+  double* Lbuf = reinterpret_cast<double*>(sweep_smem);  // [2][PB][PH]
+  double* Xs = Lbuf + 2 * PB * PH;                       // [PB][XS_LD]: MINUS block k of the solution / this block's rhs
+  const int G = gridDim.x, g = blockIdx.x;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int gid = lane >> 2, tig = lane & 3;             // MMA fragment coordinates
+  const int N = (int)n;
+  const int r0 = g * PB;
+  const int nr = min(PB, N - r0);
+  const uint32_t lbuf_s = (uint32_t)__cvta_generic_to_shared(Lbuf);
+
+  auto issue_half = [&](int kb, int hh) {
+    const int cbase = kb * PB + hh * PH;
+    const double* wsrc = Winv + (size_t)g * PB * PB + hh * PH;
+#pragma unroll 4
+    for (int i = 0; i < (PB * PH / 2) / SWEEP_THREADS; ++i) {
+      const int id = t + SWEEP_THREADS * i;
+      const int rr = id >> 5, cc = id & 31;
+      const uint32_t dst = lbuf_s + (uint32_t)(((hh * PB + rr) * PH + ((cc ^ (rr & 7)) << 1)) * sizeof(double));
+      if (kb < 0) {
+        cp_async16(dst, wsrc + (size_t)rr * PB + 2 * cc, 16);
+      } else {
+        const int col = cbase + 2 * cc;
+        const bool ok = r0 + rr < N && col < N;  // n is even: a pair of columns is inside or outside as a whole
+        cp_async16(dst, ok ? LU + (size_t)(r0 + rr) * n + col : LU, ok ? 16 : 0);
+      }
+    }
+    cp_async_commit();
+  };
+
+  // acc[mt][nt][0..1] = element (row 16 warp + 8 mt + gid, columns 8 nt + 2 tig, + 1) of this block's right-hand sides
+  double acc[2][2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int rr = 16 * warp + 8 * mt + gid, col = 8 * nt + 2 * tig + e;
+        double v = 0.0;
+        if (rr < nr && col < nx)  // X = B(piv,:), lu.rs:246-254
+          v = FORWARD ? B[(size_t)(piv ? piv[r0 + rr] : (uint64_t)(r0 + rr)) * nx + col] : X[(size_t)(r0 + rr) * nx + col];
+        acc[mt][nt][e] = v;
+      }
+  // d += (rows of buffer hh) * (rows [64 hh, 64 hh + 64) of Xs)
+  auto mma_half = [&](int hh, double (&d)[2][2][2]) {
+    const int row_a0 = 16 * warp + gid;
+    const double* La0 = Lbuf + (size_t)(hh * PB + row_a0) * PH;
+    const double* La1 = La0 + 8 * PH;
+    const int sw = row_a0 & 7;  // == (row_a0 + 8) & 7
+    const double* Xb = Xs + (size_t)(hh * PH + tig) * XS_LD + gid;
+#pragma unroll 8
+    for (int ks = 0; ks < PH / 4; ++ks) {
+      const int col = 4 * ks + tig;
+      const int off = (((col >> 1) ^ sw) << 1) + (col & 1);
+      const double a0 = La0[off], a1 = La1[off];
+      const double b0 = Xb[(size_t)(4 * ks) * XS_LD], b1 = Xb[(size_t)(4 * ks) * XS_LD + 8];
+      dmma884(d[0][0][0], d[0][0][1], a0, b0);
+      dmma884(d[0][1][0], d[0][1][1], a0, b1);
+      dmma884(d[1][0][0], d[1][0][1], a1, b0);
+      dmma884(d[1][1][0], d[1][1][1], a1, b1);
+    }
+  };
+
+  const int nsteps = FORWARD ? g : G - 1 - g;  // blocks of the solution this CTA consumes before its own
+  auto step_block = [&](int s) { return FORWARD ? s : G - 1 - s; };
+  {
+    const int kb = nsteps > 0 ? step_block(0) : -1;
+    issue_half(kb, 0);
+    issue_half(kb, 1);
+  }
+  for (int s = 0; s < nsteps; ++s) {
+    const int kb = step_block(s);
+    const int next_kb = (s + 1 < nsteps) ? step_block(s + 1) : -1;  // the CTA's own inverted diagonal block comes last
+    // ---- block kb of the solution: poll the producer's flagged words (8 per thread), store MINUS the values ----
+    {
+      const XWord* src = xbuf + (size_t)kb * (PB * 16);
+      double v[8];
+      bool ok[8];
+      {
+        bool first = false;
+        while (!first) first = LL<double>::load(src + t, tag, v[0]);  // one word per thread while nothing has arrived
+        ok[0] = true;
+      }
+      bool all;
+#pragma unroll
+      for (int u = 1; u < 8; ++u) ok[u] = false;
+      do {
+        all = true;
+#pragma unroll
+        for (int u = 1; u < 8; ++u)
+          if (!ok[u]) {
+            ok[u] = LL<double>::load(src + t + SWEEP_THREADS * u, tag, v[u]);
+            all = all && ok[u];
+          }
+      } while (!all);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = t + SWEEP_THREADS * u;
+        Xs[(size_t)(idx >> 4) * XS_LD + (idx & 15)] = -v[u];
+      }
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      cp_async_wait<1>();
+      __syncthreads();  // buffer hh (and, the first time round, Xs) is ready
+      mma_half(hh, acc);
+      __syncthreads();  // everyone is done with buffer hh
+      issue_half(next_kb, hh);
+    }
+  }
+  // ---- X_g = W_g * (right-hand sides of this block): the same MMA loop on the inverted diagonal block ----
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int rr = 16 * warp + 8 * mt + gid, col = 8 * nt + 2 * tig;
+      *reinterpret_cast<double2*>(&Xs[(size_t)rr * XS_LD + col]) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+    }
+  cp_async_wait<0>();
+  __syncthreads();  // W_g is in the two buffers, the block's right-hand sides in Xs
+  double res[2][2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) res[mt][nt][0] = res[mt][nt][1] = 0.0;
+  mma_half(0, res);
+  mma_half(1, res);
+  // publish: flagged words for the CTAs that still need this block, plain values into X
+  const bool has_readers = FORWARD ? g + 1 < G : g > 0;
+  XWord* dst = xbuf + (size_t)g * (PB * 16);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int rr = 16 * warp + 8 * mt + gid, col = 8 * nt + 2 * tig + e;
+        const double v = res[mt][nt][e];
+        if (has_readers) LL<double>::store(dst + rr * 16 + col, (rr < nr && col < nx) ? v : 0.0, tag);
+        if (rr < nr && col < nx) X[(size_t)(r0 + rr) * nx + col] = v;
+      }
+}
+
 template <typename T>
 __global__ void nonsingular_kernel(const T* __restrict__ LU, size_t n, int* __restrict__ flag) {
   // flag starts at 1; any exact zero on the diagonal clears it (lu.rs:176-180)
@@ -379,6 +544,28 @@ int tri_sweeps_dev(const double* Lmat, const double* Umat, size_t n, const uint6
     LA_CUDA_TRY(cudaMemsetAsync(dp, 0, 2 * sizeof(unsigned long long) * 8 * G, st));
     d0 = (unsigned long long*)dp;
     d1 = d0 + 8 * G;
+  }
+  static const int old_sweep = getenv("LA_SOLVE_OLD_SWEEP") ? atoi(getenv("LA_SOLVE_OLD_SWEEP")) : 0;  // A/B knob
+  if (!old_sweep && !trace) {
+    // flagged-word exchange buffers of the two sweeps; tags are unique per call of this host thread (never 0)
+    void* xb = nullptr;
+    const size_t words = (size_t)G * PB * 16;
+    LA_TRY(scratch_get(ctx->device, 38, 2 * words * sizeof(XWord), &xb));
+    static thread_local unsigned call_tag = 0;
+    call_tag += 2;
+    if (call_tag == 0) call_tag = 2;
+    XWord* xb0 = (XWord*)xb;
+    XWord* xb1 = xb0 + words;
+    unsigned t0 = call_tag, t1 = call_tag + 1;
+    LA_CUDA_TRY(cudaFuncSetAttribute(solve_sweep_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP2_SMEM));
+    LA_CUDA_TRY(cudaFuncSetAttribute(solve_sweep_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP2_SMEM));
+    void* m0[] = {&lu_p, &nn, &piv_dev, &b_p, &x_p, &nxi, &xb0, &t0, &wl};
+    void* m1[] = {&uu_p, &nn, &piv_dev, &b_p, &x_p, &nxi, &xb1, &t1, &wu};
+    LA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)solve_sweep_mma_kernel<true>, dim3(G), dim3(SWEEP_THREADS), m0,
+                                            SWEEP2_SMEM, st));
+    LA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)solve_sweep_mma_kernel<false>, dim3(G), dim3(SWEEP_THREADS), m1,
+                                            SWEEP2_SMEM, st));
+    return LA_OK;
   }
   void* a0[] = {&lu_p, &nn, &piv_dev, &b_p, &x_p, &nxi, &f0, &wl, &d0};
   void* a1[] = {&uu_p, &nn, &piv_dev, &b_p, &x_p, &nxi, &f1, &wu, &d1};

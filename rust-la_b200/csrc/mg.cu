@@ -158,6 +158,21 @@ struct DevGuard {
 
 size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// LA_MG_TRACE=1: stage markers of every rank on stderr (diagnostic)
+bool mg_trace_on() {
+  static const bool v = getenv("LA_MG_TRACE") && atoi(getenv("LA_MG_TRACE")) != 0;
+  return v;
+}
+#define MG_TRACE(c, ...)                                                     \
+  do {                                                                       \
+    if (mg_trace_on()) {                                                     \
+      fprintf(stderr, "[mg rank %d epoch %u] ", (c)->rank, (c)->epoch);      \
+      fprintf(stderr, __VA_ARGS__);                                          \
+      fprintf(stderr, "\n");                                                 \
+      fflush(stderr);                                                        \
+    }                                                                        \
+  } while (0)
+
 // Block partition of `total` into `parts` pieces whose boundaries are multiples of `align` where possible.
 void block_range(size_t total, int parts, int idx, size_t align, size_t* b0, size_t* b1) {
   const size_t units = (total + align - 1) / align;
@@ -259,8 +274,10 @@ int mg_rank_host(la_mg* c, const T* A, const T* Bblk, size_t ldb_host, T* C, siz
   const size_t o0 = c->col0[c->rank], o1 = c->col1[c->rank], ow = o1 - o0;
   LA_REQUIRE(ldb_host >= ow, "la_gemm_mg_rank_host: ldb smaller than the column block");
   void *dA, *dC;
+  MG_TRACE(c, "host call: m_local=%zu, allocating scratch", m_local);
   LA_TRY(scratch_get(c->device, 21, m_local * k * es, &dA));
   LA_TRY(scratch_get(c->device, 22, m_local * n * es, &dC));
+  MG_TRACE(c, "scratch ready");
   T* Ad = (T*)dA;
   T* Cd = (T*)dC;
   T* B = reinterpret_cast<T*>(c->base);
@@ -279,9 +296,11 @@ int mg_rank_host(la_mg* c, const T* A, const T* Bblk, size_t ldb_host, T* C, siz
   const bool deep = k >= 2048 && ow > 0;
   if (ow > 0)
     LA_CUDA_TRY(cudaMemcpy2DAsync(B + o0, n * es, Bblk, ldb_host * es, ow * es, k, cudaMemcpyHostToDevice, up));
+  MG_TRACE(c, "own block upload queued");
   mg_publish_kernel<<<1, 1, 0, up>>>(c->flags, e);
   LA_CUDA_TRY(cudaGetLastError());
   LA_TRY(mg_queue_pulls(c, e));
+  MG_TRACE(c, "publish + pulls queued");
   if (deep) {
     const size_t kp = 2048;
     size_t p = 0;
@@ -339,9 +358,12 @@ int mg_rank_host(la_mg* c, const T* A, const T* Bblk, size_t ldb_host, T* C, siz
     LA_CUDA_TRY(cudaStreamWaitEvent(down, c->ev_blk[b], 0));
     LA_CUDA_TRY(cudaMemcpyAsync(C + r0 * n, Cd + r0 * n, blk[b] * n * es, cudaMemcpyDeviceToHost, down));
   }
+  MG_TRACE(c, "all work queued, synchronising");
   LA_CUDA_TRY(cudaStreamSynchronize(down));
+  MG_TRACE(c, "downloads done");
   LA_CUDA_TRY(cudaStreamSynchronize(st));
   LA_CUDA_TRY(cudaStreamSynchronize(c->s_pull));  // our acks are out: the peers may move on
+  MG_TRACE(c, "call complete");
   return LA_OK;
 }
 

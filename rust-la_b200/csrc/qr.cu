@@ -41,6 +41,7 @@ constexpr int QR_THREADS = 256;
 constexpr int QR_NB = 128;                      // block width (also the stride of the stored T' blocks)
 constexpr size_t QR_SMEM_BUDGET = 200 * 1024;   // panel rows per CTA * (nb | 1) * sizeof(T)
 constexpr int QR_SMEM_EXTRA = 5 * QR_NB * 8 + 64;
+constexpr int QR_MAX_PER_LANE = 6;             // exchange words per lane: supports up to 6 * 32 - 1 = 191 CTAs
 
 template <typename T>
 using LLW = typename LL<T>::word;
@@ -73,28 +74,36 @@ qr_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rpc, LL
     const int r = idx / jb, cc = idx - r * jb;
     P[(size_t)r * stride + cc] = A[(size_t)(row0 + r) * ld + j0 + cc];
   }
+  // S beyond the block (the inversion works on all QR_NB rows): identity, so that no stale value or 0/0 can leak in
+  if (c == 0)
+    for (int idx = tid; idx < QR_NB * QR_NB; idx += QR_THREADS) {
+      const int i = idx / QR_NB, jj = idx - i * QR_NB;
+      if (i >= jb || jj >= jb) S[idx] = (i == jj) ? (T)1 : (T)0;
+    }
   __syncthreads();
 
   const int j = tid & (QR_NB - 1), h = tid >> 7;  // column slot and row half of this thread
+  // partial dots of column 0 with every column of the panel; later columns get theirs from the fused update pass
+  {
+    const int rbeg = max(0, j0 - row0);
+    T a0 = (T)0, a1 = (T)0, a2 = (T)0, a3 = (T)0;
+    if (j < jb) {
+      int r = rbeg + h;
+      for (; r + 6 < nrows; r += 8) {
+        a0 = fma(P[(size_t)r * stride], P[(size_t)r * stride + j], a0);
+        a1 = fma(P[(size_t)(r + 2) * stride], P[(size_t)(r + 2) * stride + j], a1);
+        a2 = fma(P[(size_t)(r + 4) * stride], P[(size_t)(r + 4) * stride + j], a2);
+        a3 = fma(P[(size_t)(r + 6) * stride], P[(size_t)(r + 6) * stride + j], a3);
+      }
+      for (; r < nrows; r += 2) a0 = fma(P[(size_t)r * stride], P[(size_t)r * stride + j], a0);
+    }
+    gp[h * QR_NB + j] = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();
   for (int k = 0; k < jb; ++k) {
     const int lk = j0 + k - row0;   // local index of the diagonal row (negative: above this CTA, >= nrows: below)
     const int rbeg = max(0, lk);    // rows >= the diagonal take part
-    // ---- partial dots of column k with every column of the panel ----
-    {
-      T a0 = (T)0, a1 = (T)0, a2 = (T)0, a3 = (T)0;
-      if (j < jb) {
-        int r = rbeg + h;
-        for (; r + 6 < nrows; r += 8) {
-          a0 = fma(P[(size_t)r * stride + k], P[(size_t)r * stride + j], a0);
-          a1 = fma(P[(size_t)(r + 2) * stride + k], P[(size_t)(r + 2) * stride + j], a1);
-          a2 = fma(P[(size_t)(r + 4) * stride + k], P[(size_t)(r + 4) * stride + j], a2);
-          a3 = fma(P[(size_t)(r + 6) * stride + k], P[(size_t)(r + 6) * stride + j], a3);
-        }
-        for (; r < nrows; r += 2) a0 = fma(P[(size_t)r * stride + k], P[(size_t)r * stride + j], a0);
-      }
-      gp[h * QR_NB + j] = (a0 + a1) + (a2 + a3);
-    }
-    __syncthreads();
+    // ---- grid-wide sums of the partial dots (gp) + the diagonal row, to every CTA ----
     if (G == 1) {
       if (tid < jb) {
         g[tid] = gp[tid] + gp[QR_NB + tid];
@@ -107,37 +116,52 @@ qr_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rpc, LL
         LL<T>::store(&part[((size_t)par * QR_NB + tid) * (G + 1) + c], gp[tid] + gp[QR_NB + tid], tag);
         if (lk >= 0 && lk < nrows) LL<T>::store(&part[((size_t)par * QR_NB + tid) * (G + 1) + G], P[(size_t)lk * stride + tid], tag);
       }
-      // owners: component jj belongs to CTA jj mod G; one warp per owned component, fixed summation order
+      // owners: component jj belongs to CTA jj mod G; one warp per owned component.  All of a lane's words are requested
+      // before any is examined (a poll per word would serialise the L2 round trips); fixed summation order.
       for (int jj = c + warp * G; jj < jb; jj += (QR_THREADS / 32) * G) {
         const LLW<T>* src = part + ((size_t)par * QR_NB + jj) * (G + 1);
-        T s = (T)0;
-        for (int cc = lane; cc < G; cc += 32) {
-          T v;
-          while (!LL<T>::load(&src[cc], tag, v)) {
-          }
-          s += v;
+        T v[QR_MAX_PER_LANE];
+        bool ok[QR_MAX_PER_LANE];
+#pragma unroll
+        for (int u = 0; u < QR_MAX_PER_LANE; ++u) {
+          v[u] = (T)0;
+          ok[u] = lane + 32 * u > G;  // entries 0..G-1 are the partials, entry G is the diagonal row's value
+        }
+        bool all;
+        do {
+          all = true;
+#pragma unroll
+          for (int u = 0; u < QR_MAX_PER_LANE; ++u)
+            if (!ok[u]) {
+              ok[u] = LL<T>::load(&src[lane + 32 * u], tag, v[u]);
+              all = all && ok[u];
+            }
+        } while (!all);
+        T sum = (T)0, rk = (T)0;
+#pragma unroll
+        for (int u = 0; u < QR_MAX_PER_LANE; ++u) {
+          if (lane + 32 * u < G) sum += v[u];
+          if (lane + 32 * u == G) rk = v[u];
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        T rk = (T)0;
-        if (lane == 0) {
-          while (!LL<T>::load(&src[G], tag, rk)) {
-          }
+        for (int off = 16; off > 0; off >>= 1) {
+          sum += __shfl_xor_sync(0xffffffffu, sum, off);
+          rk += __shfl_xor_sync(0xffffffffu, rk, off);  // exactly one lane holds a non-zero contribution (or all zero)
         }
-        rk = __shfl_sync(0xffffffffu, rk, 0);
         for (int cc = lane; cc < G; cc += 32) {
           LLW<T>* dst = tot + (((size_t)par * G + cc) * QR_NB + jj) * 2;
-          LL<T>::store(dst, s, tag);
+          LL<T>::store(dst, sum, tag);
           LL<T>::store(dst + 1, rk, tag);
         }
       }
       if (tid < jb) {
         const LLW<T>* src = tot + (((size_t)par * G + c) * QR_NB + tid) * 2;
-        T v, w;
-        while (!LL<T>::load(src, tag, v)) {
-        }
-        while (!LL<T>::load(src + 1, tag, w)) {
-        }
+        T v = (T)0, w = (T)0;
+        bool okv = false, okw = false;
+        do {
+          if (!okv) okv = LL<T>::load(src, tag, v);
+          if (!okw) okw = LL<T>::load(src + 1, tag, w);
+        } while (!(okv && okw));
         g[tid] = v;
         rowk[tid] = w;
       }
@@ -149,21 +173,51 @@ qr_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rpc, LL
     const T a = xkk > (T)0 ? -nrm : nrm;
     const T ukk = xkk - a;
     const T den = a * ukk;
+    const bool reflect = a != (T)0;  // :62
     if (c == 0) {  // bookkeeping by the first CTA: rdiag, column k of S = T^-1
       if (tid == 0) {
         rdiag[j0 + k] = a;
-        S[(size_t)k * QR_NB + k] = (a != (T)0) ? -den : (T)1;
+        S[(size_t)k * QR_NB + k] = reflect ? -den : (T)1;
       }
-      if (tid < k) S[(size_t)tid * QR_NB + k] = (a != (T)0) ? g[tid] - a * rowk[tid] : (T)0;
+      if (tid < k) S[(size_t)tid * QR_NB + k] = reflect ? g[tid] - a * rowk[tid] : (T)0;
     }
-    if (a != (T)0) {
-      if (tid == 0 && lk >= 0 && lk < nrows) P[(size_t)lk * stride + k] = ukk;  // :77
-      __syncthreads();
-      if (j > k && j < jb) {
-        const T f = (g[j] - a * rowk[j]) / den;  // <a_j, u> / (a u_k)
-        for (int r = rbeg + h; r < nrows; r += 2)
-          P[(size_t)r * stride + j] = fma(f, P[(size_t)r * stride + k], P[(size_t)r * stride + j]);
+    if (reflect && tid == 0 && lk >= 0 && lk < nrows) P[(size_t)lk * stride + k] = ukk;  // :77
+    const bool has_next = k + 1 < jb;
+    // factors <a_j, u> / (a u_k) of this thread's column and of column k + 1 (every thread needs the latter)
+    const T f = (reflect && j > k && j < jb) ? (g[j] - a * rowk[j]) / den : (T)0;
+    const T fn = (reflect && has_next) ? (g[k + 1] - a * rowk[k + 1]) / den : (T)0;
+    __syncthreads();
+    // ---- column k+1 first (one row per thread): every thread of the fused pass below reads its UPDATED values ----
+    if (reflect && has_next)
+      for (int r = rbeg + tid; r < nrows; r += QR_THREADS)
+        P[(size_t)r * stride + k + 1] = fma(fn, P[(size_t)r * stride + k], P[(size_t)r * stride + k + 1]);
+    __syncthreads();
+    // ---- fused pass over the rows >= k: apply the reflection to column j (> k+1) and accumulate column k+1's dot
+    //      products with the updated values of every column ----
+    {
+      T a0 = (T)0, a1 = (T)0;
+      if (j < jb) {
+        const int kn = has_next ? k + 1 : k;
+        const bool upd = reflect && j > k + 1;
+        for (int r = rbeg + h; r < nrows; r += 4) {
+          const int r2 = r + 2;
+          T x0 = P[(size_t)r * stride + j];
+          if (upd) {
+            x0 = fma(f, P[(size_t)r * stride + k], x0);
+            P[(size_t)r * stride + j] = x0;
+          }
+          if (r > lk) a0 = fma(P[(size_t)r * stride + kn], x0, a0);  // rows below this diagonal = rows >= the next one
+          if (r2 < nrows) {
+            T x1 = P[(size_t)r2 * stride + j];
+            if (upd) {
+              x1 = fma(f, P[(size_t)r2 * stride + k], x1);
+              P[(size_t)r2 * stride + j] = x1;
+            }
+            if (r2 > lk) a1 = fma(P[(size_t)r2 * stride + kn], x1, a1);
+          }
+        }
       }
+      gp[h * QR_NB + j] = a0 + a1;
     }
     __syncthreads();
   }
@@ -364,8 +418,7 @@ int qr_factor_dev(T* QR, size_t m, size_t n, T* rdiag, T* tmat, cudaStream_t st)
     LA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)qr_panel_kernel<T>, dim3(G), dim3(QR_THREADS), args, smem, st));
     tag += QR_NB;
     T* Tt = tmat + (size_t)blk * QR_NB * QR_NB;
-    LA_TRY(tri_block_inverses<T>(sc.S, QR_NB, 1, 0, 1, Tt, 1, st));  // T' = inv(S)'
-    // tri_block_inverses clamps the block to the matrix order it is given (QR_NB): rows/columns >= jb of S must be inert
+    LA_TRY(tri_block_inverses<T>(sc.S, QR_NB, 1, 0, 1, Tt, 1, st));  // T' = inv(S)' (S is the identity beyond jb)
     const int c1 = j0 + jb;
     if (c1 < N) {
       LA_TRY(qr_extract<T>(QR, n, M, j0, jb, sc, st));

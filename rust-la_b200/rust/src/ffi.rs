@@ -6,6 +6,21 @@ use std::os::raw::{c_char, c_int, c_void};
 pub struct la_buf {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct la_mg {
+    _private: [u8; 0],
+}
+pub const LA_MG_HANDLE_BYTES: usize = 256;
+pub const LA_EW_ADD: c_int = 0;
+pub const LA_EW_SUB: c_int = 1;
+pub const LA_EW_MUL: c_int = 2;
+pub const LA_EW_DIV: c_int = 3;
+pub const LA_EW_SCALE: c_int = 4;
+pub const LA_EW_NEG: c_int = 5;
+pub const LA_RED_SUMSQ: c_int = 0;
+pub const LA_RED_ABS_SUM: c_int = 1;
+pub const LA_RED_ABS_MAX: c_int = 2;
+pub const LA_RED_DOT: c_int = 3;
 
 pub const LA_OK: c_int = 0;
 pub const LA_ERR_INVALID: c_int = 1;
@@ -94,6 +109,43 @@ extern "C" {
                                dst: *mut la_buf) -> c_int;
     pub fn la_permute_rows_f32(src: *const la_buf, rows: usize, cols: usize, idx: *const u64, out_rows: usize,
                                dst: *mut la_buf) -> c_int;
+    // ---- multi-GPU Mul, QR, elementwise operators / norms, fp32 accuracy mode (added in round 2) ----
+    pub fn la_elementwise_f32(op: c_int, a: *const la_buf, b: *const la_buf, scalar: f32, c: *mut la_buf, count: usize) -> c_int;
+    pub fn la_elementwise_f32_dev(op: c_int, a: *const f32, b: *const f32, scalar: f32, c: *mut f32, count: usize, cuda_stream: *mut c_void) -> c_int;
+    pub fn la_elementwise_f64(op: c_int, a: *const la_buf, b: *const la_buf, scalar: f64, c: *mut la_buf, count: usize) -> c_int;
+    pub fn la_elementwise_f64_dev(op: c_int, a: *const f64, b: *const f64, scalar: f64, c: *mut f64, count: usize, cuda_stream: *mut c_void) -> c_int;
+    pub fn la_gemm_f32_mg(ngpus: c_int, devices: *const c_int, a: *const f32, b: *const f32, c: *mut f32, m: usize, k: usize, n: usize) -> c_int;
+    pub fn la_gemm_f32_mg_rank(ctx: *mut la_mg, a_shard: *const f32, lda: usize, c_shard: *mut f32, ldc: usize, m_local: usize, cuda_stream: *mut c_void) -> c_int;
+    pub fn la_gemm_f32_mg_rank_host(ctx: *mut la_mg, a_shard: *const f32, b_block: *const f32, ldb: usize, c_shard: *mut f32, m_local: usize) -> c_int;
+    pub fn la_gemm_f64_mg(ngpus: c_int, devices: *const c_int, a: *const f64, b: *const f64, c: *mut f64, m: usize, k: usize, n: usize) -> c_int;
+    pub fn la_gemm_f64_mg_rank(ctx: *mut la_mg, a_shard: *const f64, lda: usize, c_shard: *mut f64, ldc: usize, m_local: usize, cuda_stream: *mut c_void) -> c_int;
+    pub fn la_gemm_f64_mg_rank_host(ctx: *mut la_mg, a_shard: *const f64, b_block: *const f64, ldb: usize, c_shard: *mut f64, m_local: usize) -> c_int;
+    pub fn la_get_gemm_f32_mode(out: *mut c_int) -> c_int;
+    pub fn la_mg_b_block(ctx: *const la_mg, block_dev: *mut *mut c_void, ldb: *mut usize, col0: *mut usize, col1: *mut usize) -> c_int;
+    pub fn la_mg_connect(ctx: *mut la_mg, handles: *const c_void) -> c_int;
+    pub fn la_mg_create(rank: c_int, nranks: c_int, device: c_int, elem_bytes: usize, k: usize, n: usize, out: *mut *mut la_mg) -> c_int;
+    pub fn la_mg_destroy(ctx: *mut la_mg) -> c_int;
+    pub fn la_mg_handle(ctx: *const la_mg, handle_out: *mut c_void) -> c_int;
+    pub fn la_mg_quiesce(ctx: *mut la_mg, cuda_stream: *mut c_void) -> c_int;
+    pub fn la_mg_shard(nranks: c_int, rank: c_int, m: usize, n: usize, elem_bytes: usize, row0: *mut usize, row1: *mut usize, col0: *mut usize, col1: *mut usize) -> c_int;
+    pub fn la_qr_factor_f32(qr_inout: *mut la_buf, m: usize, n: usize, rdiag: *mut la_buf, tmat: *mut la_buf) -> c_int;
+    pub fn la_qr_factor_f32_dev(qr_inout: *mut f32, m: usize, n: usize, rdiag: *mut f32, tmat: *mut f32, cuda_stream: *mut c_void) -> c_int;
+    pub fn la_qr_factor_f32_host(a: *const f32, qr_out: *mut f32, rdiag_out: *mut f32, m: usize, n: usize) -> c_int;
+    pub fn la_qr_factor_f64(qr_inout: *mut la_buf, m: usize, n: usize, rdiag: *mut la_buf, tmat: *mut la_buf) -> c_int;
+    pub fn la_qr_factor_f64_dev(qr_inout: *mut f64, m: usize, n: usize, rdiag: *mut f64, tmat: *mut f64, cuda_stream: *mut c_void) -> c_int;
+    pub fn la_qr_factor_f64_host(a: *const f64, qr_out: *mut f64, rdiag_out: *mut f64, m: usize, n: usize) -> c_int;
+    pub fn la_qr_get_q_f32(qr: *const la_buf, m: usize, n: usize, tmat: *const la_buf, q: *mut la_buf) -> c_int;
+    pub fn la_qr_get_q_f64(qr: *const la_buf, m: usize, n: usize, tmat: *const la_buf, q: *mut la_buf) -> c_int;
+    pub fn la_qr_get_r_f32(qr: *const la_buf, m: usize, n: usize, rdiag: *const la_buf, r: *mut la_buf) -> c_int;
+    pub fn la_qr_get_r_f64(qr: *const la_buf, m: usize, n: usize, rdiag: *const la_buf, r: *mut la_buf) -> c_int;
+    pub fn la_qr_solve_f32(qr: *const la_buf, m: usize, n: usize, rdiag: *const la_buf, b: *const la_buf, nx: usize, x: *mut la_buf) -> c_int;
+    pub fn la_qr_solve_f64(qr: *const la_buf, m: usize, n: usize, rdiag: *const la_buf, b: *const la_buf, nx: usize, x: *mut la_buf) -> c_int;
+    pub fn la_qr_tmat_elems(m: usize, n: usize, device: c_int, elem_bytes: usize, elems_out: *mut usize) -> c_int;
+    pub fn la_reduce_f32(kind: c_int, a: *const la_buf, b: *const la_buf, count: usize, out: *mut f32) -> c_int;
+    pub fn la_reduce_f32_dev(kind: c_int, a: *const f32, b: *const f32, count: usize, out_host: *mut f32, cuda_stream: *mut c_void) -> c_int;
+    pub fn la_reduce_f64(kind: c_int, a: *const la_buf, b: *const la_buf, count: usize, out: *mut f64) -> c_int;
+    pub fn la_reduce_f64_dev(kind: c_int, a: *const f64, b: *const f64, count: usize, out_host: *mut f64, cuda_stream: *mut c_void) -> c_int;
+    pub fn la_set_gemm_f32_mode(mode: c_int) -> c_int;
     pub fn la_fill_hash_f64_dev(dst: *mut f64, count: usize, seed: u64, first_idx: u64, cuda_stream: *mut c_void) -> c_int;
     pub fn la_fill_hash_f32_dev(dst: *mut f32, count: usize, seed: u64, first_idx: u64, cuda_stream: *mut c_void) -> c_int;
     pub fn la_debug_set_gemm_path(path: c_int) -> c_int;

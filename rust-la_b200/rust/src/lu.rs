@@ -3,8 +3,8 @@
 use std::os::raw::c_int;
 use std::ptr;
 
-use ffi;
-use matrix::Matrix;
+use crate::ffi;
+use crate::matrix::Matrix;
 
 /// f32 / f64 dispatch to the typed C-ABI entry points.
 pub trait LuScalar: Copy + PartialEq {
@@ -38,9 +38,13 @@ macro_rules! lu_scalar {
 lu_scalar!(f64, la_lu_factor_f64, la_lu_is_nonsingular_f64, la_lu_det_f64, la_lu_solve_f64);
 lu_scalar!(f32, la_lu_factor_f32, la_lu_is_nonsingular_f32, la_lu_det_f32, la_lu_solve_f32);
 
-struct DevBuf(*mut ffi::la_buf);
+pub(crate) struct DevBuf(pub(crate) *mut ffi::la_buf);
+// The C ABI is thread-safe (include/la_cabi.h: per-thread streams and scratch, no unguarded global state) and a la_buf is
+// only a handle to device memory, so the decompositions stay Send + Sync like the reference's plain-Vec structs.
+unsafe impl Send for DevBuf {}
+unsafe impl Sync for DevBuf {}
 impl DevBuf {
-    fn new(bytes: usize) -> DevBuf {
+    pub(crate) fn new(bytes: usize) -> DevBuf {
         let mut h: *mut ffi::la_buf = ptr::null_mut();
         ffi::check(unsafe { ffi::la_buf_alloc(bytes, 0, &mut h) });
         DevBuf(h)

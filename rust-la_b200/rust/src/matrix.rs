@@ -7,7 +7,7 @@
 use std::ops::Mul;
 use std::os::raw::c_int;
 
-use ffi;
+use crate::ffi;
 
 mod sealed {
     pub trait Sealed {}
