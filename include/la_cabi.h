@@ -138,6 +138,11 @@ LA_API int la_gemm_f64_mg_rank_host(la_mg* ctx, const double* A_shard, const dou
                                     size_t m_local);
 LA_API int la_gemm_f32_mg_rank_host(la_mg* ctx, const float* A_shard, const float* B_block, size_t ldb, float* C_shard,
                                     size_t m_local);
+/* Sizes the context's device copies of a host shard of `m_local` rows (la_gemm_*_mg_rank_host allocates on demand
+ * otherwise).  Call it on every rank after la_mg_connect and before the ranks start multiplying when several ranks share
+ * a device or a process: cudaMalloc may wait for the device, and a rank that allocates before it has published its block
+ * would then wait for peers whose kernels are waiting for that block. */
+LA_API int la_mg_reserve(la_mg* ctx, size_t m_local);
 /* Before a rank rewrites its column block IN PLACE for the next product: makes `cuda_stream` wait until every peer has
  * finished pulling the block of the previous product. */
 LA_API int la_mg_quiesce(la_mg* ctx, void* cuda_stream);

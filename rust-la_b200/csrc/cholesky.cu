@@ -326,7 +326,7 @@ int chol_solve_dev(const T* L, size_t n, const T* B, size_t nx, T* X, cudaStream
       LA_TRY(transpose_dev<double>(L, LT, n, n, st));
       LA_TRY(tri_block_inverses<double>(L, n, 2, 0, G, WL, 0, st));
       LA_TRY(tri_block_inverses<double>(LT, n, 1, 0, G, WU, 0, st));
-      if (nx <= 16 && G <= ctx->sm_count && ctx->coop)  // few right-hand sides: the LU solve's persistent sweep kernels
+      if (nx <= 16 && ctx->coop)  // few right-hand sides: the LU solve's persistent sweep kernels
         return tri_sweeps_dev(L, LT, n, nullptr, B, nx, X, WL, WU, st);
       for (int b = 0; b < G; ++b) {  // L Y = B
         const size_t r0 = (size_t)b * CB, nr = (n - r0 < (size_t)CB) ? (n - r0) : (size_t)CB;

@@ -336,8 +336,9 @@ typedef LL<double>::word XWord;
 
 template <bool FORWARD>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1)
-solve_sweep_mma_kernel(const double* __restrict__ LU, size_t n, const uint64_t* __restrict__ piv, const double* __restrict__ B,
-                       double* __restrict__ X, int nx, XWord* __restrict__ xbuf /* [G][PB * 16] flagged words */,
+solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const uint64_t* __restrict__ piv,
+                       const double* __restrict__ B, double* __restrict__ X, int nx,
+                       XWord* __restrict__ xbuf /* [G][PB * 16] flagged words */,
                        unsigned tag, const double* __restrict__ Winv /* [G][128][128] inverted diagonal blocks */) {
   extern __shared__ __align__(16) unsigned char sweep_smem[];
   double* Lbuf = reinterpret_cast<double*>(sweep_smem);  // [2][PB][PH]
@@ -363,7 +364,7 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t n, const uint64_t* 
       } else {
         const int col = cbase + 2 * cc;
         const bool ok = r0 + rr < N && col < N;  // n is even: a pair of columns is inside or outside as a whole
-        cp_async16(dst, ok ? LU + (size_t)(r0 + rr) * n + col : LU, ok ? 16 : 0);
+        cp_async16(dst, ok ? LU + (size_t)(r0 + rr) * ld + col : LU, ok ? 16 : 0);
       }
     }
     cp_async_commit();
@@ -547,26 +548,61 @@ int tri_sweeps_dev(const double* Lmat, const double* Umat, size_t n, const uint6
   }
   static const int old_sweep = getenv("LA_SOLVE_OLD_SWEEP") ? atoi(getenv("LA_SOLVE_OLD_SWEEP")) : 0;  // A/B knob
   if (!old_sweep && !trace) {
-    // flagged-word exchange buffers of the two sweeps; tags are unique per call of this host thread (never 0)
+    // flagged-word exchange buffers of the two sweeps; tags are unique per launch pair of this host thread (never 0)
     void* xb = nullptr;
-    const size_t words = (size_t)G * PB * 16;
+    const int max_g = ctx->sm_count;  // cooperative grid: one CTA per SM
+    const int Gp = G < max_g ? G : max_g;
+    const size_t words = (size_t)Gp * PB * 16;
     LA_TRY(scratch_get(ctx->device, 38, 2 * words * sizeof(XWord), &xb));
     static thread_local unsigned call_tag = 0;
-    call_tag += 2;
-    if (call_tag == 0) call_tag = 2;
     XWord* xb0 = (XWord*)xb;
     XWord* xb1 = xb0 + words;
-    unsigned t0 = call_tag, t1 = call_tag + 1;
     LA_CUDA_TRY(cudaFuncSetAttribute(solve_sweep_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP2_SMEM));
     LA_CUDA_TRY(cudaFuncSetAttribute(solve_sweep_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP2_SMEM));
-    void* m0[] = {&lu_p, &nn, &piv_dev, &b_p, &x_p, &nxi, &xb0, &t0, &wl};
-    void* m1[] = {&uu_p, &nn, &piv_dev, &b_p, &x_p, &nxi, &xb1, &t1, &wu};
-    LA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)solve_sweep_mma_kernel<true>, dim3(G), dim3(SWEEP_THREADS), m0,
-                                            SWEEP2_SMEM, st));
-    LA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)solve_sweep_mma_kernel<false>, dim3(G), dim3(SWEEP_THREADS), m1,
-                                            SWEEP2_SMEM, st));
+    size_t ldm = n;
+    auto sweep = [&](bool fwd, const double* M, size_t rows, const uint64_t* pv, const double* rhs, double* out,
+                     const double* winv) -> int {
+      call_tag += 1;
+      if (call_tag == 0) call_tag = 1;
+      unsigned tg = call_tag;
+      XWord* xw = fwd ? xb0 : xb1;
+      int gp = (int)((rows + PB - 1) / PB);
+      void* args[] = {&M, &ldm, &rows, &pv, &rhs, &out, &nxi, &xw, &tg, &winv};
+      LA_CUDA_TRY(cudaLaunchCooperativeKernel(fwd ? (const void*)solve_sweep_mma_kernel<true>
+                                                  : (const void*)solve_sweep_mma_kernel<false>,
+                                              dim3(gp), dim3(SWEEP_THREADS), args, SWEEP2_SMEM, st));
+      return LA_OK;
+    };
+    if (G <= max_g) {
+      LA_TRY(sweep(true, Lmat, n, piv_dev, B, X, wl));
+      LA_TRY(sweep(false, Umat, n, piv_dev, B, X, wu));
+      return LA_OK;
+    }
+    // More block rows than SMs: leading parts of sm_count block rows each; between the parts the solved rows update the
+    // remaining right-hand sides with one GEMM (the triangular system is block triangular in the parts as well).
+    {
+      size_t blocks = (n * nx + 255) / 256;
+      const size_t cap = (size_t)ctx->sm_count * 8;
+      if (piv_dev) gather_rows_kernel<double><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(B, X, piv_dev, n, nx);
+      else LA_CUDA_TRY(cudaMemcpyAsync(X, B, n * nx * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      LA_CUDA_TRY(cudaGetLastError());
+    }
+    const size_t part = (size_t)max_g * PB;
+    for (size_t p0 = 0; p0 < n; p0 += part) {  // forward
+      const size_t rows = n - p0 < part ? n - p0 : part, p1 = p0 + rows;
+      LA_TRY(sweep(true, Lmat + p0 * n + p0, rows, nullptr, X + p0 * nx, X + p0 * nx, wl + (p0 / PB) * PB * PB));
+      if (p1 < n)
+        LA_TRY(gemm_dev<double>(Lmat + p1 * n + p0, n, X + p0 * nx, nx, X + p1 * nx, nx, n - p1, rows, nx, LA_GEMM_SUB, st));
+    }
+    const size_t nparts = (n + part - 1) / part;
+    for (size_t ip = nparts; ip-- > 0;) {  // backward
+      const size_t p0 = ip * part, rows = n - p0 < part ? n - p0 : part;
+      LA_TRY(sweep(false, Umat + p0 * n + p0, rows, nullptr, X + p0 * nx, X + p0 * nx, wu + (p0 / PB) * PB * PB));
+      if (p0 > 0) LA_TRY(gemm_dev<double>(Umat + p0, n, X + p0 * nx, nx, X, nx, p0, rows, nx, LA_GEMM_SUB, st));
+    }
     return LA_OK;
   }
+  LA_REQUIRE(G <= ctx->sm_count, "la_lu_solve: the first-generation sweep kernel needs ceil(n / 128) <= SM count");
   void* a0[] = {&lu_p, &nn, &piv_dev, &b_p, &x_p, &nxi, &f0, &wl, &d0};
   void* a1[] = {&uu_p, &nn, &piv_dev, &b_p, &x_p, &nxi, &f1, &wu, &d1};
   LA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)solve_sweep_kernel<true>, dim3(G), dim3(SWEEP_THREADS), a0,
@@ -605,7 +641,7 @@ int lu_solve_dev(const T* LU, size_t n, const uint64_t* piv_dev, const T* B, siz
   if constexpr (std::is_same<T, double>::value) {
     const int G = (N + PB - 1) / PB;
     static const int no_sweep = getenv("LA_SOLVE_NO_SWEEP") ? atoi(getenv("LA_SOLVE_NO_SWEEP")) : 0;  // debug knob
-    if (!no_sweep && nx <= 16 && N >= 4 * PB && N % 2 == 0 && (uintptr_t)LU % 16 == 0 && G <= ctx->sm_count && ctx->coop) {
+    if (!no_sweep && nx <= 16 && N >= 4 * PB && N % 2 == 0 && (uintptr_t)LU % 16 == 0 && ctx->coop) {
       void* wbuf = nullptr;
       LA_TRY(scratch_get(ctx->device, 15, sizeof(double) * 2 * (size_t)G * PB * PB, &wbuf));
       double* wl = (double*)wbuf;

@@ -134,6 +134,11 @@ struct la_mg {
   size_t col0[MG_MAX_RANKS] = {}, col1[MG_MAX_RANKS] = {};
   unsigned epoch = 0;
   bool connected = false;
+  // device copies of the host shards (la_gemm_*_mg_rank_host): owned by the context, not by the calling thread, so that
+  // la_mg_reserve can size them while no rank is inside a product (cudaMalloc / cudaFree may wait for the whole device --
+  // a rank that allocated BEFORE publishing its block would wait for peers whose kernels are spinning on that block)
+  void *shard_a = nullptr, *shard_c = nullptr;
+  size_t shard_a_bytes = 0, shard_c_bytes = 0;
   cudaStream_t s_pull = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_begin = nullptr, ev_pull[2] = {nullptr, nullptr}, ev_up = nullptr, ev_blk[16] = {}, ev_own = nullptr;
 };
@@ -220,6 +225,28 @@ int mg_queue_pulls(la_mg* c, unsigned e) {
   return LA_OK;
 }
 
+int mg_reserve(la_mg* c, size_t m_local) {
+  LA_REQUIRE(c && m_local > 0, "la_mg_reserve: bad arguments");
+  DevGuard g;
+  LA_TRY(g.enter(c->device));
+  const size_t need_a = m_local * c->k * c->elem, need_c = m_local * c->n * c->elem;
+  if (c->shard_a_bytes < need_a) {
+    if (c->shard_a) LA_CUDA_TRY(cudaFree(c->shard_a));
+    c->shard_a = nullptr;
+    c->shard_a_bytes = 0;
+    LA_CUDA_TRY(cudaMalloc(&c->shard_a, need_a));
+    c->shard_a_bytes = need_a;
+  }
+  if (c->shard_c_bytes < need_c) {
+    if (c->shard_c) LA_CUDA_TRY(cudaFree(c->shard_c));
+    c->shard_c = nullptr;
+    c->shard_c_bytes = 0;
+    LA_CUDA_TRY(cudaMalloc(&c->shard_c, need_c));
+    c->shard_c_bytes = need_c;
+  }
+  return LA_OK;
+}
+
 template <typename T>
 int mg_check(const la_mg* c, const char* who) {
   LA_REQUIRE(c != nullptr, "%s: null context", who);
@@ -273,13 +300,11 @@ int mg_rank_host(la_mg* c, const T* A, const T* Bblk, size_t ldb_host, T* C, siz
   const size_t n = c->n, k = c->k, es = sizeof(T);
   const size_t o0 = c->col0[c->rank], o1 = c->col1[c->rank], ow = o1 - o0;
   LA_REQUIRE(ldb_host >= ow, "la_gemm_mg_rank_host: ldb smaller than the column block");
-  void *dA, *dC;
-  MG_TRACE(c, "host call: m_local=%zu, allocating scratch", m_local);
-  LA_TRY(scratch_get(c->device, 21, m_local * k * es, &dA));
-  LA_TRY(scratch_get(c->device, 22, m_local * n * es, &dC));
-  MG_TRACE(c, "scratch ready");
-  T* Ad = (T*)dA;
-  T* Cd = (T*)dC;
+  MG_TRACE(c, "host call: m_local=%zu", m_local);
+  LA_TRY(mg_reserve(c, m_local));  // no-op after la_mg_reserve / an earlier call with the same shard height
+  MG_TRACE(c, "shard buffers ready");
+  T* Ad = (T*)c->shard_a;
+  T* Cd = (T*)c->shard_c;
   T* B = reinterpret_cast<T*>(c->base);
   cudaStream_t st = cudaStreamPerThread, up = c->s_h2d, down = c->s_d2h;
   CallScope scope(c->device, st);
@@ -491,6 +516,8 @@ int mg_destroy(la_mg* c) {
   cudaEventDestroy(c->ev_own);
   for (int i = 0; i < 16; ++i) cudaEventDestroy(c->ev_blk[i]);
   cudaFree(c->base);
+  if (c->shard_a) cudaFree(c->shard_a);
+  if (c->shard_c) cudaFree(c->shard_c);
   cudaGetLastError();
   delete c;
   return LA_OK;
@@ -626,6 +653,20 @@ int gemm_mg(int ngpus, const int* devices, const T* A, const T* B, T* C, size_t 
   std::lock_guard<std::mutex> lock(G->busy);
   std::vector<int> status((size_t)eff, LA_OK);
   std::vector<std::string> text((size_t)eff);
+  // phase 1: every rank sizes its shard buffers; nobody publishes or pulls before all allocations are done
+  for (int r = 0; r < eff; ++r) {
+    G->workers[(size_t)r]->submit([&, r] {
+      size_t r0, r1;
+      block_range(m, eff, r, 128, &r0, &r1);
+      const int s = mg_reserve(G->ctx[(size_t)r], r1 - r0);
+      status[(size_t)r] = s;
+      if (s != LA_OK) text[(size_t)r] = error_text();
+    });
+  }
+  for (int r = 0; r < eff; ++r) G->workers[(size_t)r]->wait();
+  for (int r = 0; r < eff; ++r)
+    if (status[(size_t)r] != LA_OK) return fail(status[(size_t)r], "la_gemm_mg (rank %d): %s", r, text[(size_t)r].c_str());
+  // phase 2: the product
   for (int r = 0; r < eff; ++r) {
     G->workers[(size_t)r]->submit([&, r] {
       la_mg* c = G->ctx[(size_t)r];
@@ -671,6 +712,7 @@ int la_mg_b_block(const la_mg* ctx, void** block_dev, size_t* ldb, size_t* col0,
   *col1 = ctx->col1[ctx->rank];
   return LA_OK;
 }
+int la_mg_reserve(la_mg* ctx, size_t m_local) { return mg_reserve(ctx, m_local); }
 int la_mg_quiesce(la_mg* ctx, void* cuda_stream) {
   LA_REQUIRE(ctx && ctx->connected, "la_mg_quiesce: context not connected");
   DevGuard g;

@@ -324,6 +324,27 @@ struct QrScratch {
   T *Vc, *Vt, *W, *W2, *S, *Tn;
   size_t ldvt, ldw;
 };
+// Per host thread and device: the chain stream (highest priority) of the look-ahead pipeline and its fences.
+struct QrSide {
+  cudaStream_t sp = nullptr;
+  cudaEvent_t e_in = nullptr, e_panel = nullptr, e_bulk = nullptr, e_tail = nullptr;
+};
+int qr_side(int device, QrSide** out) {
+  static thread_local QrSide side[64];
+  LA_REQUIRE(device >= 0 && device < 64, "device ordinal out of range");
+  QrSide& s = side[device];
+  if (!s.sp) {
+    int lo = 0, hi = 0;
+    LA_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    LA_CUDA_TRY(cudaStreamCreateWithPriority(&s.sp, cudaStreamNonBlocking, hi));
+    LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e_in, cudaEventDisableTiming));
+    LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e_panel, cudaEventDisableTiming));
+    LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e_bulk, cudaEventDisableTiming));
+    LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e_tail, cudaEventDisableTiming));
+  }
+  *out = &s;
+  return LA_OK;
+}
 template <typename T>
 int qr_scratch(int device, size_t rows, size_t cols, QrScratch<T>* out) {
   out->ldvt = (rows + 3) & ~(size_t)3;
@@ -340,6 +361,23 @@ int qr_scratch(int device, size_t rows, size_t cols, QrScratch<T>* out) {
   LA_TRY(scratch_get(device, 35, sizeof(T) * 2 * QR_NB * QR_NB, &p));
   out->S = (T*)p;
   out->Tn = out->S + QR_NB * QR_NB;
+  return LA_OK;
+}
+// The look-ahead pipeline keeps the clean V copies of two consecutive blocks alive (the bulk stream applies block i while
+// the chain stream already builds block i + 1) and gives the chain its own 128-column W panels.
+template <typename T>
+int qr_scratch_lookahead(int device, size_t rows, QrScratch<T>* odd, QrScratch<T>* chain, const QrScratch<T>& even) {
+  *odd = even;
+  *chain = even;
+  void* p;
+  LA_TRY(scratch_get(device, 39, sizeof(T) * rows * QR_NB, &p));
+  odd->Vc = (T*)p;
+  LA_TRY(scratch_get(device, 40, sizeof(T) * even.ldvt * QR_NB, &p));
+  odd->Vt = (T*)p;
+  LA_TRY(scratch_get(device, 41, sizeof(T) * 2 * QR_NB * QR_NB, &p));
+  chain->W = (T*)p;
+  chain->W2 = chain->W + QR_NB * QR_NB;
+  chain->ldw = QR_NB;
   return LA_OK;
 }
 
@@ -399,12 +437,17 @@ int qr_factor_dev(T* QR, size_t m, size_t n, T* rdiag, T* tmat, cudaStream_t st)
   LA_CUDA_TRY(cudaFuncSetAttribute(qr_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)QR_SMEM_BUDGET + QR_SMEM_EXTRA));
   unsigned tag = 1;
-  int blk = 0;
-  for (int j0 = 0; j0 < dc; j0 += nb, ++blk) {
-    const int jb = dc - j0 < nb ? dc - j0 : nb;
+  // panel of block `blk` on stream s: reflections, S -> T' into tmat; few full CTAs while a bulk update runs beside it
+  auto run_panel = [&](int j0, int jb, int blk, bool beside_bulk, cudaStream_t s) -> int {
     const int R = M - j0;
     int rpc = (R + sms - 1) / sms;
-    if (rpc < 16) rpc = 16;  // two row halves x eight-row unroll: fewer, fuller CTAs for short panels
+    if (beside_bulk) {  // a panel CTA owns its SM (shared memory): fewer, fuller CTAs leave the rest to the DMMA GEMMs
+      const int fit = (int)(QR_SMEM_BUDGET / ((size_t)(jb | 1) * sizeof(T)));
+      int want = R / 48;
+      if (want > fit) want = fit;
+      if (rpc < want) rpc = want;
+    }
+    if (rpc < 16) rpc = 16;  // two row halves, a few rows each: short panels run on fewer CTAs
     const int G = (R + rpc - 1) / rpc;
     const size_t smem = (size_t)rpc * (jb | 1) * sizeof(T) + 4 * QR_NB * sizeof(T);
     T* a = QR;
@@ -415,16 +458,64 @@ int qr_factor_dev(T* QR, size_t m, size_t n, T* rdiag, T* tmat, cudaStream_t st)
     T* rd = rdiag;
     T* Sp = sc.S;
     void* args[] = {&a, &ld, &mm, &jj0, &jjb, &rr, &wsw, &tg, &rd, &Sp};
-    LA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)qr_panel_kernel<T>, dim3(G), dim3(QR_THREADS), args, smem, st));
+    LA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)qr_panel_kernel<T>, dim3(G), dim3(QR_THREADS), args, smem, s));
     tag += QR_NB;
-    T* Tt = tmat + (size_t)blk * QR_NB * QR_NB;
-    LA_TRY(tri_block_inverses<T>(sc.S, QR_NB, 1, 0, 1, Tt, 1, st));  // T' = inv(S)' (S is the identity beyond jb)
-    const int c1 = j0 + jb;
-    if (c1 < N) {
-      LA_TRY(qr_extract<T>(QR, n, M, j0, jb, sc, st));
-      LA_TRY(qr_apply_block<T>(sc, Tt, QR + (size_t)j0 * n + c1, n, (size_t)R, (size_t)jb, (size_t)(N - c1), st));
+    return tri_block_inverses<T>(sc.S, QR_NB, 1, 0, 1, tmat + (size_t)blk * QR_NB * QR_NB, 1, s);  // T' = inv(S)'
+  };
+  static const int lookahead = getenv("LA_QR_LOOKAHEAD") ? atoi(getenv("LA_QR_LOOKAHEAD")) : 1;
+  const int nblk = (dc + nb - 1) / nb;
+  if (!lookahead || nblk < 3) {
+    for (int blk = 0; blk < nblk; ++blk) {
+      const int j0 = blk * nb, jb = dc - j0 < nb ? dc - j0 : nb, c1 = j0 + jb;
+      LA_TRY(run_panel(j0, jb, blk, false, st));
+      if (c1 < N) {
+        LA_TRY(qr_extract<T>(QR, n, M, j0, jb, sc, st));
+        LA_TRY(qr_apply_block<T>(sc, tmat + (size_t)blk * QR_NB * QR_NB, QR + (size_t)j0 * n + c1, n, (size_t)(M - j0),
+                                 (size_t)jb, (size_t)(N - c1), st));
+      }
     }
+    return LA_OK;
   }
+  // ---- look-ahead: chain stream sp (high priority): reflector i on the NEXT block's columns -> panel(i+1) -> T', V copies;
+  //      bulk stream st: reflector i on everything right of the next block.  Chain step i needs bulk(i-1) (which
+  //      updated the next block's columns); bulk(i) needs chain step i-1 (V_i, T_i).  V copies alternate by block parity.
+  QrSide* side;
+  LA_TRY(qr_side(ctx->device, &side));
+  cudaStream_t sp = side->sp;
+  QrScratch<T> vbuf[2], chain;
+  vbuf[0] = sc;
+  LA_TRY(qr_scratch_lookahead<T>(ctx->device, m, &vbuf[1], &chain, sc));
+  LA_CUDA_TRY(cudaEventRecord(side->e_in, st));
+  LA_CUDA_TRY(cudaStreamWaitEvent(sp, side->e_in, 0));
+  LA_TRY(run_panel(0, dc < nb ? dc : nb, 0, false, sp));
+  LA_TRY(qr_extract<T>(QR, n, M, 0, dc < nb ? dc : nb, vbuf[0], sp));
+  LA_CUDA_TRY(cudaEventRecord(side->e_panel, sp));
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int j0 = blk * nb, jb = dc - j0 < nb ? dc - j0 : nb, c1 = j0 + jb;
+    const bool has_next = blk + 1 < nblk;
+    const int jb2 = has_next ? (dc - c1 < nb ? dc - c1 : nb) : 0, c2 = c1 + jb2;
+    const QrScratch<T>& vb = vbuf[blk & 1];
+    const T* Tt = tmat + (size_t)blk * QR_NB * QR_NB;
+    // bulk(i) is queued first: it only needs what chain step i-1 produced
+    LA_CUDA_TRY(cudaStreamWaitEvent(st, side->e_panel, 0));
+    if (c2 < N)
+      LA_TRY(qr_apply_block<T>(vb, Tt, QR + (size_t)j0 * n + c2, n, (size_t)(M - j0), (size_t)jb, (size_t)(N - c2), st));
+    // chain step i
+    if (has_next) {
+      if (blk > 0) LA_CUDA_TRY(cudaStreamWaitEvent(sp, side->e_bulk, 0));  // bulk(i-1) updated the next block's columns
+      QrScratch<T> cv = vb;  // V_i with the chain's own W panels
+      cv.W = chain.W;
+      cv.W2 = chain.W2;
+      cv.ldw = chain.ldw;
+      LA_TRY(qr_apply_block<T>(cv, Tt, QR + (size_t)j0 * n + c1, n, (size_t)(M - j0), (size_t)jb, (size_t)jb2, sp));
+      LA_TRY(run_panel(c1, jb2, blk + 1, c2 < N, sp));
+      LA_TRY(qr_extract<T>(QR, n, M, c1, jb2, vbuf[(blk + 1) & 1], sp));
+      LA_CUDA_TRY(cudaEventRecord(side->e_panel, sp));
+    }
+    LA_CUDA_TRY(cudaEventRecord(side->e_bulk, st));
+  }
+  LA_CUDA_TRY(cudaEventRecord(side->e_tail, sp));
+  LA_CUDA_TRY(cudaStreamWaitEvent(st, side->e_tail, 0));
   return LA_OK;
 }
 

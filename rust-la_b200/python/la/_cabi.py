@@ -64,6 +64,7 @@ SIGNATURES = {
     "la_gemm_f32_mg_rank": ([_p, _p, _sz, _p, _sz, _sz, _p], _i),
     "la_gemm_f64_mg_rank_host": ([_p, _p, _p, _sz, _p, _sz], _i),
     "la_gemm_f32_mg_rank_host": ([_p, _p, _p, _sz, _p, _sz], _i),
+    "la_mg_reserve": ([_p, _sz], _i),
     "la_mg_quiesce": ([_p, _p], _i),
     "la_lu_factor_f64": ([_p, _sz, _sz, _p, _pi], _i),
     "la_lu_factor_f32": ([_p, _sz, _sz, _p, _pi], _i),

@@ -92,6 +92,10 @@ class MgContext:
         check(getattr(lib(), f"la_gemm_{self.suf}_mg_rank_host")(self.h, a_shard.ctypes.data, b_block.ctypes.data,
                                                                b_block.shape[1], c_shard.ctypes.data, a_shard.shape[0]))
 
+    def reserve(self, m_local):
+        """Size the device copies of a host shard while no rank is inside a product (la_mg_reserve)."""
+        check(lib().la_mg_reserve(self.h, m_local))
+
     def quiesce(self, stream=None):
         check(lib().la_mg_quiesce(self.h, stream))
 

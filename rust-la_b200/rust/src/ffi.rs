@@ -126,6 +126,7 @@ extern "C" {
     pub fn la_mg_create(rank: c_int, nranks: c_int, device: c_int, elem_bytes: usize, k: usize, n: usize, out: *mut *mut la_mg) -> c_int;
     pub fn la_mg_destroy(ctx: *mut la_mg) -> c_int;
     pub fn la_mg_handle(ctx: *const la_mg, handle_out: *mut c_void) -> c_int;
+    pub fn la_mg_reserve(ctx: *mut la_mg, m_local: usize) -> c_int;
     pub fn la_mg_quiesce(ctx: *mut la_mg, cuda_stream: *mut c_void) -> c_int;
     pub fn la_mg_shard(nranks: c_int, rank: c_int, m: usize, n: usize, elem_bytes: usize, row0: *mut usize, row1: *mut usize, col0: *mut usize, col1: *mut usize) -> c_int;
     pub fn la_qr_factor_f32(qr_inout: *mut la_buf, m: usize, n: usize, rdiag: *mut la_buf, tmat: *mut la_buf) -> c_int;

@@ -80,3 +80,40 @@ def test_lu_16384_solve_16_rhs_residual():
     torch.cuda.synchronize()
     res = float((R - B).norm() / (A0.norm() * X.norm()))
     assert res <= 1e-14, res
+
+
+@pytest.mark.parametrize("n,nx", [(19200, 5), (19454, 16)])
+def test_solve_with_more_block_rows_than_sms(n, nx):
+    """n > 148 * 128 = 18944: the sweep kernels run one CTA per 128-row block and per SM, so larger systems are solved
+    in leading parts with a GEMM update of the remaining right-hand sides in between (lu_solve.cu).  Property check:
+    A x == b through the CUDA GEMM, and agreement with the many-right-hand-side path (a different code path, GEMM sweeps)
+    on the same factors."""
+    torch = pytest.importorskip("torch")
+    L = lib()
+    dev = torch.device("cuda", 0)
+    sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    f64 = torch.float64
+    A0 = torch.empty((n, n), dtype=f64, device=dev)
+    B = torch.empty((n, nx), dtype=f64, device=dev)
+    check(L.la_fill_hash_f64_dev(A0.data_ptr(), A0.numel(), 1, 0, sp))
+    check(L.la_fill_hash_f64_dev(B.data_ptr(), B.numel(), 3, 0, sp))
+    LU = A0.clone()
+    piv = torch.empty((n,), dtype=torch.int64, device=dev)
+    sign = torch.empty((1,), dtype=torch.int32, device=dev)
+    X = torch.full((n, nx), float("nan"), dtype=f64, device=dev)
+    check(L.la_lu_factor_f64_dev(LU.data_ptr(), n, n, piv.data_ptr(), sign.data_ptr(), sp))
+    check(L.la_lu_solve_f64_dev(LU.data_ptr(), n, piv.data_ptr(), B.data_ptr(), nx, X.data_ptr(), sp))
+    R = torch.empty((n, nx), dtype=f64, device=dev)
+    check(L.la_gemm_f64_dev(A0.data_ptr(), n, X.data_ptr(), nx, R.data_ptr(), nx, n, n, nx, 0, sp))
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(X).all())
+    res = float((R - B).norm() / (A0.norm() * X.norm()))
+    assert res <= 1e-14, res
+    # the same system with 18 right-hand sides (the first nx are B) takes the GEMM-sweep path
+    B2 = torch.zeros((n, 18), dtype=f64, device=dev)
+    B2[:, :nx] = B
+    X2 = torch.empty((n, 18), dtype=f64, device=dev)
+    check(L.la_lu_solve_f64_dev(LU.data_ptr(), n, piv.data_ptr(), B2.data_ptr(), 18, X2.data_ptr(), sp))
+    torch.cuda.synchronize()
+    diff = float((X2[:, :nx] - X).abs().max() / X.abs().max())
+    assert diff <= 1e-9, diff
