@@ -81,7 +81,7 @@ template <int MODE, int BN>
 __global__ void __launch_bounds__(TileCfg<BN>::THREADS, TileCfg<BN>::CTAS_PER_SM)
 gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     double* __restrict__ C, size_t ldc, int M, int N, int K, int tiles_m, int tiles_n, int stagger_lo,
-                    int stagger_hi, unsigned stagger_ns) {
+                    int stagger_hi, unsigned stagger_ns, int kt_per_slice, size_t c_slab) {
   using Cfg = TileCfg<BN>;
   // Shallow-K launches run two CTAs per SM so that one CTA's epilogue (HBM-bound C tile read-modify-write) overlaps the
   // other's main loop -- which only works if the two are out of phase.  CTAs launched together stay in lock step, so
@@ -119,7 +119,11 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   __syncthreads();
 
-  const int ktiles = (K + BK - 1) / BK;
+  // split-K (gridDim.y slices): slice y contracts k-tiles [y * kt_per_slice, ...) into its own copy of C at C + y * c_slab
+  // (tall-skinny products such as the QR's W = V' A have too few output tiles to fill the machine otherwise)
+  const int kt_first = (int)blockIdx.y * kt_per_slice;
+  const int ktiles = min(kt_per_slice, (K + BK - 1) / BK - kt_first);
+  C += (size_t)blockIdx.y * c_slab;
   const uint32_t smem_base = smem_u32(smem);
 
   // C -= P / C += P: pull the C tile into L2 now so the epilogue's loads do not pay an HBM round trip
@@ -138,9 +142,9 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint8_t* sA = smem + s * STAGE_BYTES;
     uint8_t* sB = sA + A_STAGE_BYTES;
     mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-    tma_load_2d(sA, &tmA, &full[s], p * BK, m0);
+    tma_load_2d(sA, &tmA, &full[s], (kt_first + p) * BK, m0);
 #pragma unroll
-    for (int j = 0; j < BN / 16; ++j) tma_load_2d(sB + j * B_BOX_BYTES, &tmB, &full[s], n0 + j * 16, p * BK);
+    for (int j = 0; j < BN / 16; ++j) tma_load_2d(sB + j * B_BOX_BYTES, &tmB, &full[s], n0 + j * 16, (kt_first + p) * BK);
   };
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -278,7 +282,7 @@ int g_gemm_path = 0;  // test hook: 0 auto, 1 SIMT, 2 TMA/DMMA (auto tile), 3 TM
 
 template <int MODE, int BN>
 int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, size_t ldc, int M, int N, int K,
-               cudaStream_t st) {
+               cudaStream_t st, int slices = 1, size_t c_slab = 0) {
   using Cfg = TileCfg<BN>;
   static const int extra_smem = getenv("LA_GEMM_EXTRA_SMEM") ? atoi(getenv("LA_GEMM_EXTRA_SMEM")) : 0;  // debug knob
   LA_CUDA_TRY(cudaFuncSetAttribute(gemm_f64_tma_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -296,8 +300,10 @@ int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, size_t
     stagger_hi = 2 * ctx->sm_count;
     stagger_ns = (unsigned)(ktiles * 520 + 2000);  // ~half of (main loop at full DMMA rate + prologue + epilogue)
   }
-  gemm_f64_tma_kernel<MODE, BN><<<tiles_m * tiles_n, Cfg::THREADS, Cfg::SMEM_BYTES + extra_smem, st>>>(
-      tmA, tmB, C, ldc, M, N, K, tiles_m, tiles_n, stagger_lo, stagger_hi, stagger_ns);
+  const int kt_per_slice = (ktiles + slices - 1) / slices;
+  const int nslices = (ktiles + kt_per_slice - 1) / kt_per_slice;  // every slice gets at least one k-tile
+  gemm_f64_tma_kernel<MODE, BN><<<dim3(tiles_m * tiles_n, nslices), Cfg::THREADS, Cfg::SMEM_BYTES + extra_smem, st>>>(
+      tmA, tmB, C, ldc, M, N, K, tiles_m, tiles_n, stagger_lo, stagger_hi, stagger_ns, kt_per_slice, c_slab);
   LA_CUDA_TRY(cudaGetLastError());
   return LA_OK;
 }
@@ -348,6 +354,49 @@ int gemm_f64_dev(const double* A, size_t lda, const double* B, size_t ldb, doubl
   if (g_gemm_path == 4) narrow = false;
   return narrow ? launch_tma_mode<64>(mode, tmA, tmB, C, ldc, (int)m, (int)n, (int)k, st)
                 : launch_tma_mode<128>(mode, tmA, tmB, C, ldc, (int)m, (int)n, (int)k, st);
+}
+
+// Split-K product for short-and-wide outputs (m <= 128 rows, deep k): slice y of `slices` writes its partial product to
+// Cslabs + y * slab_elems (ASSIGN); *slices_out receives the number of slabs actually written (every one holds at least
+// one k-tile).  The caller sums the slabs (gemm_f64_sum_slabs) -- a fixed order, so results are reproducible.
+int gemm_f64_splitk(const double* A, size_t lda, const double* B, size_t ldb, double* Cslabs, size_t ldc, size_t slab_elems,
+                    size_t m, size_t k, size_t n, int slices, int* slices_out, cudaStream_t st) {
+  const bool aligned = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)Cslabs % 16 == 0) &&
+                       lda % 2 == 0 && ldb % 2 == 0 && ldc % 2 == 0 && slab_elems % 2 == 0;
+  if (!aligned || m == 0 || n == 0 || k == 0 || slices < 1)
+    return fail(LA_ERR_INVALID, "internal: split-K GEMM requested for operands that are not TMA-addressable");
+  CUtensorMap tmA, tmB;
+  LA_TRY(encode_tensor_map_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, A, k, m, lda * 8, BK, BM,
+                              CU_TENSOR_MAP_SWIZZLE_128B));
+  LA_TRY(encode_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, B, n, k, ldb * 8, 16, BK,
+                              CU_TENSOR_MAP_SWIZZLE_128B));
+  const int ktiles = (int)((k + BK - 1) / BK);
+  const int per = (ktiles + slices - 1) / slices;
+  *slices_out = (ktiles + per - 1) / per;
+  return launch_tma<LA_GEMM_ASSIGN, 128>(tmA, tmB, Cslabs, ldc, (int)m, (int)n, (int)k, st, slices, slab_elems);
+}
+
+__global__ void __launch_bounds__(256) sum_slabs_kernel(const double* __restrict__ slabs, size_t slab_elems, int nslabs,
+                                                        double* __restrict__ out, size_t count) {
+  for (size_t i = ((size_t)blockIdx.x * 256 + threadIdx.x) * 2; i < count; i += (size_t)gridDim.x * 512) {
+    double2 acc = *reinterpret_cast<const double2*>(slabs + i);
+    for (int s = 1; s < nslabs; ++s) {
+      const double2 v = *reinterpret_cast<const double2*>(slabs + (size_t)s * slab_elems + i);
+      acc.x += v.x;
+      acc.y += v.y;
+    }
+    *reinterpret_cast<double2*>(out + i) = acc;
+  }
+}
+// out[0..count) = sum of the slabs (count even, 16-byte aligned); out may be slab 0 itself
+int gemm_f64_sum_slabs(const double* slabs, size_t slab_elems, int nslabs, double* out, size_t count, cudaStream_t st) {
+  const DeviceCtx* ctx;
+  LA_TRY(current_device_ctx(&ctx));
+  size_t blocks = (count / 2 + 255) / 256;
+  const size_t cap = (size_t)ctx->sm_count * 8;
+  sum_slabs_kernel<<<(unsigned)(blocks < cap ? (blocks ? blocks : 1) : cap), 256, 0, st>>>(slabs, slab_elems, nslabs, out, count);
+  LA_CUDA_TRY(cudaGetLastError());
+  return LA_OK;
 }
 
 // Tensor kernel regardless of problem size (the LU driver needs its in-place-safe tile structure: with m <= 128 there

@@ -141,6 +141,8 @@ struct la_mg {
   size_t shard_a_bytes = 0, shard_c_bytes = 0;
   cudaStream_t s_pull = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_begin = nullptr, ev_pull[2] = {nullptr, nullptr}, ev_up = nullptr, ev_blk[16] = {}, ev_own = nullptr;
+  static constexpr int MAX_A_PANELS = 48;
+  cudaEvent_t ev_a[MAX_A_PANELS] = {};  // one per uploaded K-panel of the A shard
 };
 
 namespace {
@@ -324,25 +326,41 @@ int mg_rank_host(la_mg* c, const T* A, const T* Bblk, size_t ldb_host, T* C, siz
   MG_TRACE(c, "own block upload queued");
   mg_publish_kernel<<<1, 1, 0, up>>>(c->flags, e);
   LA_CUDA_TRY(cudaGetLastError());
-  LA_TRY(mg_queue_pulls(c, e));
-  MG_TRACE(c, "publish + pulls queued");
+  // The A shard goes up in K-panels (first one narrow) so that the multiply of the own block starts under its own upload.
+  // EVERY upload is queued before the pulls: a copy from pageable memory is staged by the driver and would otherwise
+  // wait behind this rank's own pull kernels, which spin until the peers have published.
+  struct Panel {
+    size_t k0, w;
+  };
+  Panel pan[la_mg::MAX_A_PANELS];
+  int npan = 0;
   if (deep) {
     const size_t kp = 2048;
-    size_t p = 0;
-    for (size_t k0 = 0; k0 < k; ++p) {
-      size_t w = (p == 0) ? 512 : ((p == 1) ? kp - 512 : kp);
-      if (w > k - k0) w = k - k0;
-      LA_CUDA_TRY(cudaMemcpy2DAsync(Ad + k0, k * es, A + k0, k * es, w * es, m_local, cudaMemcpyHostToDevice, up));
-      LA_CUDA_TRY(cudaEventRecord(c->ev_up, up));
-      LA_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_up, 0));
-      LA_TRY(gemm_dev<T>(Ad + k0, k, B + k0 * n + o0, n, Cd + o0, n, m_local, w, ow, p == 0 ? LA_GEMM_ASSIGN : LA_GEMM_ADD, st));
+    for (size_t k0 = 0; k0 < k;) {
+      size_t w = (npan == 0) ? 512 : ((npan == 1) ? kp - 512 : kp);
+      if (w > k - k0 || npan == la_mg::MAX_A_PANELS - 1) w = k - k0;
+      pan[npan++] = {k0, w};
       k0 += w;
     }
   } else {
-    LA_CUDA_TRY(cudaMemcpyAsync(Ad, A, m_local * k * es, cudaMemcpyHostToDevice, up));
-    LA_CUDA_TRY(cudaEventRecord(c->ev_up, up));
-    LA_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_up, 0));
-    if (ow > 0) LA_TRY(gemm_dev<T>(Ad, k, B + o0, n, Cd + o0, n, m_local, k, ow, LA_GEMM_ASSIGN, st));
+    pan[npan++] = {0, k};
+  }
+  for (int p = 0; p < npan; ++p) {
+    if (npan == 1)
+      LA_CUDA_TRY(cudaMemcpyAsync(Ad, A, m_local * k * es, cudaMemcpyHostToDevice, up));
+    else
+      LA_CUDA_TRY(cudaMemcpy2DAsync(Ad + pan[p].k0, k * es, A + pan[p].k0, k * es, pan[p].w * es, m_local,
+                                    cudaMemcpyHostToDevice, up));
+    LA_CUDA_TRY(cudaEventRecord(c->ev_a[p], up));
+  }
+  MG_TRACE(c, "A shard uploads queued");
+  LA_TRY(mg_queue_pulls(c, e));
+  MG_TRACE(c, "publish + pulls queued");
+  for (int p = 0; p < npan; ++p) {
+    LA_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_a[p], 0));
+    if (ow > 0)
+      LA_TRY(gemm_dev<T>(Ad + pan[p].k0, k, B + pan[p].k0 * n + o0, n, Cd + o0, n, m_local, pan[p].w, ow,
+                         p == 0 ? LA_GEMM_ASSIGN : LA_GEMM_ADD, st));
   }
   // ---- the other column ranges; the LAST non-empty one runs in row blocks with the download of C behind it ----
   struct Range {
@@ -434,6 +452,7 @@ int mg_create(int rank, int nranks, int device, size_t elem, size_t k, size_t n,
   LA_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
   LA_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_own, cudaEventDisableTiming));
   for (int i = 0; i < 16; ++i) LA_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_blk[i], cudaEventDisableTiming));
+  for (int i = 0; i < la_mg::MAX_A_PANELS; ++i) LA_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_a[i], cudaEventDisableTiming));
   c->peer_base[rank] = c->base;
   c->peer_flags[rank] = c->flags;
   if (nranks == 1) c->connected = true;
@@ -515,6 +534,7 @@ int mg_destroy(la_mg* c) {
   cudaEventDestroy(c->ev_up);
   cudaEventDestroy(c->ev_own);
   for (int i = 0; i < 16; ++i) cudaEventDestroy(c->ev_blk[i]);
+  for (int i = 0; i < la_mg::MAX_A_PANELS; ++i) cudaEventDestroy(c->ev_a[i]);
   cudaFree(c->base);
   if (c->shard_a) cudaFree(c->shard_a);
   if (c->shard_c) cudaFree(c->shard_c);

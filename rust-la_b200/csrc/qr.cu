@@ -32,6 +32,9 @@
 #include "ll_exchange.cuh"
 
 namespace la {
+int gemm_f64_splitk(const double* A, size_t lda, const double* B, size_t ldb, double* Cslabs, size_t ldc, size_t slab_elems,
+                    size_t m, size_t k, size_t n, int slices, int* slices_out, cudaStream_t st);  // gemm_f64.cu
+int gemm_f64_sum_slabs(const double* slabs, size_t slab_elems, int nslabs, double* out, size_t count, cudaStream_t st);
 template <typename T>
 int tri_block_inverses(const T* M, size_t n, int mode, int first_block, int nblocks, T* W, int trans_out, cudaStream_t st);
 
@@ -323,6 +326,7 @@ template <typename T>
 struct QrScratch {
   T *Vc, *Vt, *W, *W2, *S, *Tn;
   size_t ldvt, ldw;
+  int slab_slot = 42;  // scratch slot of the split-K partial products (the chain stream of the look-ahead has its own)
 };
 // Per host thread and device: the chain stream (highest priority) of the look-ahead pipeline and its fences.
 struct QrSide {
@@ -361,6 +365,12 @@ int qr_scratch(int device, size_t rows, size_t cols, QrScratch<T>* out) {
   LA_TRY(scratch_get(device, 35, sizeof(T) * 2 * QR_NB * QR_NB, &p));
   out->S = (T*)p;
   out->Tn = out->S + QR_NB * QR_NB;
+  {  // split-K partial products: slices * 128 * ldw with slices * ceil(nc / 128) <= SM count, at most 32 slices
+    const DeviceCtx* ctx;
+    LA_TRY(current_device_ctx(&ctx));
+    LA_TRY(scratch_get(device, 42, sizeof(T) * (size_t)(ctx->sm_count + 32) * QR_NB * (QR_NB + 4), &p));
+    LA_TRY(scratch_get(device, 43, sizeof(T) * 32 * QR_NB * (QR_NB + 4), &p));
+  }
   return LA_OK;
 }
 // The look-ahead pipeline keeps the clean V copies of two consecutive blocks alive (the bulk stream applies block i while
@@ -378,15 +388,40 @@ int qr_scratch_lookahead(int device, size_t rows, QrScratch<T>* odd, QrScratch<T
   chain->W = (T*)p;
   chain->W2 = chain->W + QR_NB * QR_NB;
   chain->ldw = QR_NB;
+  chain->slab_slot = 43;
   return LA_OK;
 }
 
 // C[rows j0.., cols c0..c0+nc) <- (I - V op(T) V') C for the block whose clean copies sit in sc; Tm is op(T), ld QR_NB.
 template <typename T>
 int qr_apply_block(const QrScratch<T>& sc, const T* Tm, T* C, size_t ldc, size_t R, size_t jb, size_t nc, cudaStream_t st) {
-  LA_TRY(gemm_dev<T>(sc.Vt, sc.ldvt, C, ldc, sc.W, sc.ldw, jb, R, nc, LA_GEMM_ASSIGN, st));
-  LA_TRY(gemm_dev<T>(Tm, QR_NB, sc.W, sc.ldw, sc.W2, sc.ldw, jb, jb, nc, LA_GEMM_ASSIGN, st));
-  LA_TRY(gemm_dev<T>(sc.Vc, QR_NB, sc.W2, sc.ldw, C, ldc, R, jb, nc, LA_GEMM_SUB, st));
+  const size_t ldw = (nc + 3) & ~(size_t)3;  // compact leading dimension of the two W panels for this call (<= sc.ldw)
+  // W = V' C has one tile row (jb <= 128) and a deep contraction over the rows: too few output tiles to fill the machine
+  // (nc / 128 CTAs), so the contraction is split over the SMs and the partial products are summed in a fixed order.
+  bool done = false;
+  if constexpr (std::is_same<T, double>::value) {
+    const DeviceCtx* ctx;
+    LA_TRY(current_device_ctx(&ctx));
+    const size_t tiles = (nc + 127) / 128;
+    int slices = (int)((size_t)ctx->sm_count / tiles);
+    const int max_by_depth = (int)(R / 512);  // at least 32 k-tiles per slice
+    if (slices > max_by_depth) slices = max_by_depth;
+    if (slices > 32) slices = 32;
+    const bool aligned = ((uintptr_t)C % 16 == 0) && ldc % 2 == 0 && ((uintptr_t)sc.Vt % 16 == 0) && sc.ldvt % 2 == 0 &&
+                         ((uintptr_t)sc.W % 16 == 0);
+    if (slices >= 2 && aligned) {
+      const size_t slab = (size_t)QR_NB * ldw;
+      void* p;
+      LA_TRY(scratch_get(ctx->device, sc.slab_slot, sizeof(double) * slab * (size_t)slices, &p));  // pre-sized: no growth here
+      int used = 1;
+      LA_TRY(gemm_f64_splitk(sc.Vt, sc.ldvt, C, ldc, (double*)p, ldw, slab, jb, R, nc, slices, &used, st));
+      LA_TRY(gemm_f64_sum_slabs((const double*)p, slab, used, sc.W, jb * ldw, st));
+      done = true;
+    }
+  }
+  if (!done) LA_TRY(gemm_dev<T>(sc.Vt, sc.ldvt, C, ldc, sc.W, ldw, jb, R, nc, LA_GEMM_ASSIGN, st));
+  LA_TRY(gemm_dev<T>(Tm, QR_NB, sc.W, ldw, sc.W2, ldw, jb, jb, nc, LA_GEMM_ASSIGN, st));
+  LA_TRY(gemm_dev<T>(sc.Vc, QR_NB, sc.W2, ldw, C, ldc, R, jb, nc, LA_GEMM_SUB, st));
   return LA_OK;
 }
 
@@ -507,6 +542,7 @@ int qr_factor_dev(T* QR, size_t m, size_t n, T* rdiag, T* tmat, cudaStream_t st)
       cv.W = chain.W;
       cv.W2 = chain.W2;
       cv.ldw = chain.ldw;
+      cv.slab_slot = chain.slab_slot;
       LA_TRY(qr_apply_block<T>(cv, Tt, QR + (size_t)j0 * n + c1, n, (size_t)(M - j0), (size_t)jb, (size_t)jb2, sp));
       LA_TRY(run_panel(c1, jb2, blk + 1, c2 < N, sp));
       LA_TRY(qr_extract<T>(QR, n, M, c1, jb2, vbuf[(blk + 1) & 1], sp));

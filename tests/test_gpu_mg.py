@@ -30,9 +30,20 @@ def _ran_in_child(request):
         return False
     env = dict(os.environ, LA_MG_CHILD="1")
     out = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider", request.node.nodeid], cwd=ROOT,
-                         env=env, capture_output=True, text=True, timeout=240)
+                         env=env, capture_output=True, text=True, timeout=150)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
     return True
+
+
+def _pinned(shape, dtype):
+    """numpy view of page-locked host memory (la_host_alloc).  Pageable buffers are staged by the driver, and a staged
+    copy issued while another rank's kernel is spinning on the SAME device can block behind it."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = ctypes.c_void_p()
+    check(lib().la_host_alloc(n, ctypes.byref(p)))
+    buf = (ctypes.c_ubyte * n).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return arr, p
 
 
 def _run_ranks(fn, world):
@@ -76,13 +87,22 @@ def test_mg_ranks_on_one_device_host_shards(request, oracle, dtype, shape, world
             b = oracle.fill((k, n), 2 + 10 * rep, dtype)
             outs = [None] * world
 
+            held = []
+
             def rank_body(r):
                 r0, r1, c0, c1 = sharding.shard(world, r, m, n, np.dtype(dtype).itemsize)
-                c_sh = np.full((r1 - r0, n), np.nan, dtype=dtype)
-                ctxs[r].gemm_host(np.ascontiguousarray(a[r0:r1]), np.ascontiguousarray(b[:, c0:c1]), c_sh)
-                outs[r] = c_sh
+                (a_sh, pa), (b_bl, pb), (c_sh, pc) = (_pinned((r1 - r0, k), dtype), _pinned((k, c1 - c0), dtype),
+                                                      _pinned((r1 - r0, n), dtype))
+                held.extend([pa, pb, pc])
+                a_sh[:] = a[r0:r1]
+                b_bl[:] = b[:, c0:c1]
+                c_sh[:] = np.nan
+                ctxs[r].gemm_host(a_sh, b_bl, c_sh)
+                outs[r] = c_sh.copy()
 
             _run_ranks(rank_body, world)
+            for p in held:
+                lib().la_host_free(p)
             got = np.concatenate(outs, axis=0)
             assert np.all(np.isfinite(got))
             assert max_rel_err(got, oracle.gemm(a, b)) <= tol

@@ -37,7 +37,18 @@ def _parity(oracle, a, tol):
     qr = QRDecomposition.new(Matrix.from_numpy(a))
     got = qr.get_qr().to_numpy().astype(np.float64)
     scale = max(np.max(np.abs(packed)), 1.0)
-    assert np.array_equal(np.sign(qr.rdiag), np.sign(rdiag)), "a reflection took the other sign"
+    # The sign of a reflection is decided by `x_kk > 0` (qr.rs:58) on the partially reduced diagonal entry x_kk = u_kk + a.
+    # Where |x_kk| is at rounding level relative to the column norm |a| either sign is a legitimate outcome of a different
+    # summation order; everything downstream then differs by sign, so element-wise parity only applies when all decisions agree.
+    k = min(m, n)
+    xkk = packed[np.arange(k), np.arange(k)].astype(np.float64) + rdiag.astype(np.float64)
+    flipped = np.sign(qr.rdiag) != np.sign(rdiag)
+    assert np.all(np.abs(xkk[flipped]) <= 50 * tol * np.abs(rdiag[flipped].astype(np.float64))), "a reflection took the other sign"
+    if np.any(flipped):
+        q, r = qr.get_q().to_numpy().astype(np.float64), qr.get_r().to_numpy().astype(np.float64)
+        assert np.max(np.abs(q @ r - a)) <= 10 * tol * max(m, n) * scale  # still a valid factorisation of a
+        assert np.max(np.abs(np.abs(qr.rdiag.astype(np.float64)) - np.abs(rdiag))) <= tol * max(m, n) * np.max(np.abs(rdiag))
+        pytest.skip("a rounding-level diagonal entry took the other sign: element-wise parity does not apply")
     assert np.max(np.abs(qr.rdiag.astype(np.float64) - rdiag)) <= tol * max(m, n) * np.max(np.abs(rdiag))
     assert np.max(np.abs(got - packed)) <= tol * max(m, n) * scale
     return qr, packed, rdiag
