@@ -330,156 +330,178 @@ solve_sweep_kernel(const double* __restrict__ LU, size_t n, const uint64_t* __re
 // Shared memory: two 64-column halves of the LU block (swizzled 16-byte chunks, as above) + the X block as the MMA's
 // B operand with a 24-double row stride (4 k-rows x 8 columns of a fragment load then cover all 32 banks twice).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int XS_LD = 24;
-constexpr int SWEEP2_SMEM = (2 * PB * PH + PB * XS_LD) * (int)sizeof(double);
+// NXC = right-hand-side columns per chain: 16 (one chain, 64-column halves of LU, three 64 KB buffers, one CTA per SM) or
+// 8 (two INDEPENDENT chains for 9..16 right-hand sides -- each column of X is its own triangular system -- or one chain for
+// <= 8; 32-column quarters, three 32 KB buffers, two CTAs per SM).  Two chains halve the block products on the dependent
+// path (each CTA multiplies 128 x 128 x 8), the critical CTAs of the two chains sit on different SMs, and the second reader
+// of every LU block hits L2.
+template <int NXC>
+struct SweepCfg {
+  static constexpr int PHC = NXC == 16 ? 64 : 32;      // LU columns per shared-memory buffer
+  static constexpr int PARTS = PB / PHC;               // buffers per 128-column block
+  static constexpr int NT = NXC / 8;                   // 8-column MMA tiles
+  static constexpr int XLD = NXC == 16 ? 24 : 8;       // row stride of the X block: a fragment load covers all banks twice
+  static constexpr int BUFS = 3;
+  static constexpr int WORDS = PB * NXC;               // flagged words per solved block
+  static constexpr int WPT = WORDS / SWEEP_THREADS;    // ... per thread
+  static constexpr int SMEM = (BUFS * PB * PHC + PB * XLD) * (int)sizeof(double);
+  static constexpr int CTAS_PER_SM = NXC == 16 ? 1 : 2;
+};
 typedef LL<double>::word XWord;
 
-template <bool FORWARD>
-__global__ void __launch_bounds__(SWEEP_THREADS, 1)
+template <bool FORWARD, int NXC>
+__global__ void __launch_bounds__(SWEEP_THREADS, SweepCfg<NXC>::CTAS_PER_SM)
 solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const uint64_t* __restrict__ piv,
-                       const double* __restrict__ B, double* __restrict__ X, int nx,
-                       XWord* __restrict__ xbuf /* [G][PB * 16] flagged words */,
+                       const double* __restrict__ B, double* __restrict__ X, int nx, int G,
+                       XWord* __restrict__ xbuf /* [chains][G][PB * NXC] flagged words */,
                        unsigned tag, const double* __restrict__ Winv /* [G][128][128] inverted diagonal blocks */) {
+  using Cfg = SweepCfg<NXC>;
+  constexpr int PHC = Cfg::PHC, PARTS = Cfg::PARTS, NT = Cfg::NT, XLD = Cfg::XLD, BUFS = Cfg::BUFS, WPT = Cfg::WPT;
   extern __shared__ __align__(16) unsigned char sweep_smem[];
-  double* Lbuf = reinterpret_cast<double*>(sweep_smem);  // [2][PB][PH]
-  double* Xs = Lbuf + 2 * PB * PH;                       // [PB][XS_LD]: MINUS block k of the solution / this block's rhs
-  const int G = gridDim.x, g = blockIdx.x;
+  double* Lbuf = reinterpret_cast<double*>(sweep_smem);  // [BUFS][PB][PHC]
+  double* Xs = Lbuf + BUFS * PB * PHC;                   // [PB][XLD]: MINUS block k of the solution / this block's rhs
+  const int chain = blockIdx.x / G, g = blockIdx.x - chain * G;
+  const int c0 = chain * NXC;                            // first right-hand side of this chain
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int gid = lane >> 2, tig = lane & 3;             // MMA fragment coordinates
   const int N = (int)n;
   const int r0 = g * PB;
   const int nr = min(PB, N - r0);
   const uint32_t lbuf_s = (uint32_t)__cvta_generic_to_shared(Lbuf);
+  xbuf += (size_t)chain * G * Cfg::WORDS;
 
-  auto issue_half = [&](int kb, int hh) {
-    const int cbase = kb * PB + hh * PH;
-    const double* wsrc = Winv + (size_t)g * PB * PB + hh * PH;
+  const int nsteps = FORWARD ? g : G - 1 - g;  // blocks of the solution this CTA consumes before its own
+  auto step_block = [&](int s) { return FORWARD ? s : G - 1 - s; };
+  // The CTA consumes a sequence of PHC-column parts: PARTS per block of LU (steps 0 .. nsteps-1), then the parts of its own
+  // inverted diagonal block.  Part i lives in buffer i % 3 and is requested three parts ahead, so the inverted block is
+  // already (almost) in place when the last update finishes -- its load is off the dependent chain.
+  const int nparts = PARTS * (nsteps + 1);
+  constexpr int CHUNKS = PHC / 2;  // 16-byte chunks per buffer row
+  auto issue_part = [&](int i) {
+    if (i < nparts) {
+      const int s = i / PARTS, hh = i - s * PARTS;
+      const int kb = s < nsteps ? step_block(s) : -1;
+      const int buf = i % BUFS;
+      const int cbase = kb * PB + hh * PHC;
+      const double* wsrc = Winv + (size_t)g * PB * PB + hh * PHC;
 #pragma unroll 4
-    for (int i = 0; i < (PB * PH / 2) / SWEEP_THREADS; ++i) {
-      const int id = t + SWEEP_THREADS * i;
-      const int rr = id >> 5, cc = id & 31;
-      const uint32_t dst = lbuf_s + (uint32_t)(((hh * PB + rr) * PH + ((cc ^ (rr & 7)) << 1)) * sizeof(double));
-      if (kb < 0) {
-        cp_async16(dst, wsrc + (size_t)rr * PB + 2 * cc, 16);
-      } else {
-        const int col = cbase + 2 * cc;
-        const bool ok = r0 + rr < N && col < N;  // n is even: a pair of columns is inside or outside as a whole
-        cp_async16(dst, ok ? LU + (size_t)(r0 + rr) * ld + col : LU, ok ? 16 : 0);
+      for (int q = 0; q < (PB * CHUNKS) / SWEEP_THREADS; ++q) {
+        const int id = t + SWEEP_THREADS * q;
+        const int rr = id / CHUNKS, cc = id % CHUNKS;
+        const uint32_t dst = lbuf_s + (uint32_t)(((buf * PB + rr) * PHC + ((cc ^ (rr & 7)) << 1)) * sizeof(double));
+        if (kb < 0) {
+          cp_async16(dst, wsrc + (size_t)rr * PB + 2 * cc, 16);
+        } else {
+          const int col = cbase + 2 * cc;
+          const bool ok = r0 + rr < N && col < N;  // n is even: a pair of columns is inside or outside as a whole
+          cp_async16(dst, ok ? LU + (size_t)(r0 + rr) * ld + col : LU, ok ? 16 : 0);
+        }
       }
     }
-    cp_async_commit();
+    cp_async_commit();  // always a group (possibly empty): the wait count below stays uniform
   };
 
-  // acc[mt][nt][0..1] = element (row 16 warp + 8 mt + gid, columns 8 nt + 2 tig, + 1) of this block's right-hand sides
-  double acc[2][2][2];
+  // acc[mt][nt][0..1] = element (row 16 warp + 8 mt + gid, columns c0 + 8 nt + 2 tig, + 1) of this block's right-hand sides
+  double acc[2][NT][2];
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int rr = 16 * warp + 8 * mt + gid, col = 8 * nt + 2 * tig + e;
+        const int rr = 16 * warp + 8 * mt + gid, col = c0 + 8 * nt + 2 * tig + e;
         double v = 0.0;
         if (rr < nr && col < nx)  // X = B(piv,:), lu.rs:246-254
           v = FORWARD ? B[(size_t)(piv ? piv[r0 + rr] : (uint64_t)(r0 + rr)) * nx + col] : X[(size_t)(r0 + rr) * nx + col];
         acc[mt][nt][e] = v;
       }
-  // d += (rows of buffer hh) * (rows [64 hh, 64 hh + 64) of Xs)
-  auto mma_half = [&](int hh, double (&d)[2][2][2]) {
+  // d += (rows of buffer buf) * (rows [PHC hh, PHC hh + PHC) of Xs)
+  auto mma_part = [&](int buf, int hh, double (&d)[2][NT][2]) {
     const int row_a0 = 16 * warp + gid;
-    const double* La0 = Lbuf + (size_t)(hh * PB + row_a0) * PH;
-    const double* La1 = La0 + 8 * PH;
+    const double* La0 = Lbuf + (size_t)(buf * PB + row_a0) * PHC;
+    const double* La1 = La0 + 8 * PHC;
     const int sw = row_a0 & 7;  // == (row_a0 + 8) & 7
-    const double* Xb = Xs + (size_t)(hh * PH + tig) * XS_LD + gid;
+    const double* Xb = Xs + (size_t)(hh * PHC + tig) * XLD + gid;
 #pragma unroll 8
-    for (int ks = 0; ks < PH / 4; ++ks) {
+    for (int ks = 0; ks < PHC / 4; ++ks) {
       const int col = 4 * ks + tig;
       const int off = (((col >> 1) ^ sw) << 1) + (col & 1);
       const double a0 = La0[off], a1 = La1[off];
-      const double b0 = Xb[(size_t)(4 * ks) * XS_LD], b1 = Xb[(size_t)(4 * ks) * XS_LD + 8];
-      dmma884(d[0][0][0], d[0][0][1], a0, b0);
-      dmma884(d[0][1][0], d[0][1][1], a0, b1);
-      dmma884(d[1][0][0], d[1][0][1], a1, b0);
-      dmma884(d[1][1][0], d[1][1][1], a1, b1);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const double bv = Xb[(size_t)(4 * ks) * XLD + 8 * nt];
+        dmma884(d[0][nt][0], d[0][nt][1], a0, bv);
+        dmma884(d[1][nt][0], d[1][nt][1], a1, bv);
+      }
     }
   };
 
-  const int nsteps = FORWARD ? g : G - 1 - g;  // blocks of the solution this CTA consumes before its own
-  auto step_block = [&](int s) { return FORWARD ? s : G - 1 - s; };
-  {
-    const int kb = nsteps > 0 ? step_block(0) : -1;
-    issue_half(kb, 0);
-    issue_half(kb, 1);
-  }
-  for (int s = 0; s < nsteps; ++s) {
-    const int kb = step_block(s);
-    const int next_kb = (s + 1 < nsteps) ? step_block(s + 1) : -1;  // the CTA's own inverted diagonal block comes last
-    // ---- block kb of the solution: poll the producer's flagged words (8 per thread), store MINUS the values ----
-    {
-      const XWord* src = xbuf + (size_t)kb * (PB * 16);
-      double v[8];
-      bool ok[8];
-      {
-        bool first = false;
-        while (!first) first = LL<double>::load(src + t, tag, v[0]);  // one word per thread while nothing has arrived
-        ok[0] = true;
-      }
-      bool all;
+  issue_part(0);
+  issue_part(1);
+  issue_part(2);
+  double res[2][NT][2];
+  for (int i = 0; i < nparts; ++i) {
+    const int s = i / PARTS, hh = i - s * PARTS;
+    const bool own = s == nsteps;  // the parts of the inverted diagonal block
+    if (hh == 0) {
+      if (!own) {
+        // ---- block kb of the solution: poll the producer's flagged words (WPT per thread), store MINUS the values ----
+        const XWord* src = xbuf + (size_t)step_block(s) * Cfg::WORDS;
+        double v[WPT];
+        bool ok[WPT];
+        {
+          bool first = false;
+          while (!first) first = LL<double>::load(src + t, tag, v[0]);  // one word per thread while nothing has arrived
+          ok[0] = true;
+        }
+        bool all;
 #pragma unroll
-      for (int u = 1; u < 8; ++u) ok[u] = false;
-      do {
-        all = true;
+        for (int u = 1; u < WPT; ++u) ok[u] = false;
+        do {
+          all = true;
 #pragma unroll
-        for (int u = 1; u < 8; ++u)
-          if (!ok[u]) {
-            ok[u] = LL<double>::load(src + t + SWEEP_THREADS * u, tag, v[u]);
-            all = all && ok[u];
+          for (int u = 1; u < WPT; ++u)
+            if (!ok[u]) {
+              ok[u] = LL<double>::load(src + t + SWEEP_THREADS * u, tag, v[u]);
+              all = all && ok[u];
+            }
+        } while (!all);
+#pragma unroll
+        for (int u = 0; u < WPT; ++u) {
+          const int idx = t + SWEEP_THREADS * u;
+          Xs[(size_t)(idx / NXC) * XLD + (idx % NXC)] = -v[u];
+        }
+      } else {
+        // ---- X_g = W_g * (right-hand sides of this block): the same MMA loop on the inverted diagonal block ----
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const int rr = 16 * warp + 8 * mt + gid, col = 8 * nt + 2 * tig;
+            *reinterpret_cast<double2*>(&Xs[(size_t)rr * XLD + col]) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+            res[mt][nt][0] = res[mt][nt][1] = 0.0;
           }
-      } while (!all);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int idx = t + SWEEP_THREADS * u;
-        Xs[(size_t)(idx >> 4) * XS_LD + (idx & 15)] = -v[u];
       }
     }
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      cp_async_wait<1>();
-      __syncthreads();  // buffer hh (and, the first time round, Xs) is ready
-      mma_half(hh, acc);
-      __syncthreads();  // everyone is done with buffer hh
-      issue_half(next_kb, hh);
-    }
+    cp_async_wait<BUFS - 1>();  // groups are committed in order: all but the two youngest have landed -> part i is in
+    __syncthreads();            // buffer i % 3 (and, for hh == 0, Xs) is ready
+    if (own) mma_part(i % BUFS, hh, res);
+    else mma_part(i % BUFS, hh, acc);
+    __syncthreads();            // everyone is done with buffer i % 3 (and, after the last part, with Xs)
+    issue_part(i + BUFS);
   }
-  // ---- X_g = W_g * (right-hand sides of this block): the same MMA loop on the inverted diagonal block ----
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-      const int rr = 16 * warp + 8 * mt + gid, col = 8 * nt + 2 * tig;
-      *reinterpret_cast<double2*>(&Xs[(size_t)rr * XS_LD + col]) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
-    }
-  cp_async_wait<0>();
-  __syncthreads();  // W_g is in the two buffers, the block's right-hand sides in Xs
-  double res[2][2][2];
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) res[mt][nt][0] = res[mt][nt][1] = 0.0;
-  mma_half(0, res);
-  mma_half(1, res);
   // publish: flagged words for the CTAs that still need this block, plain values into X
   const bool has_readers = FORWARD ? g + 1 < G : g > 0;
-  XWord* dst = xbuf + (size_t)g * (PB * 16);
+  XWord* dst = xbuf + (size_t)g * Cfg::WORDS;
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int rr = 16 * warp + 8 * mt + gid, col = 8 * nt + 2 * tig + e;
+        const int rr = 16 * warp + 8 * mt + gid, cl = 8 * nt + 2 * tig + e, col = c0 + cl;
         const double v = res[mt][nt][e];
-        if (has_readers) LL<double>::store(dst + rr * 16 + col, (rr < nr && col < nx) ? v : 0.0, tag);
+        if (has_readers) LL<double>::store(dst + rr * NXC + cl, (rr < nr && col < nx) ? v : 0.0, tag);
         if (rr < nr && col < nx) X[(size_t)(r0 + rr) * nx + col] = v;
       }
 }
@@ -550,15 +572,25 @@ int tri_sweeps_dev(const double* Lmat, const double* Umat, size_t n, const uint6
   if (!old_sweep && !trace) {
     // flagged-word exchange buffers of the two sweeps; tags are unique per launch pair of this host thread (never 0)
     void* xb = nullptr;
-    const int max_g = ctx->sm_count;  // cooperative grid: one CTA per SM
+    const int max_g = ctx->sm_count;  // cooperative grid: one block row per SM
     const int Gp = G < max_g ? G : max_g;
-    const size_t words = (size_t)Gp * PB * 16;
+    // 9..16 right-hand sides: two independent chains of 8 (two CTAs per SM); <= 8: one chain of 8; LA_SOLVE_CHAINS=1 keeps
+    // the single 16-column chain (A/B knob)
+    static const int chains_knob = getenv("LA_SOLVE_CHAINS") ? atoi(getenv("LA_SOLVE_CHAINS")) : 2;
+    const bool narrow = nx <= 8 || chains_knob >= 2;
+    const int chains = (narrow && nx > 8) ? 2 : 1;
+    const size_t words = (size_t)Gp * PB * 16;  // per sweep, either layout
     LA_TRY(scratch_get(ctx->device, 38, 2 * words * sizeof(XWord), &xb));
     static thread_local unsigned call_tag = 0;
     XWord* xb0 = (XWord*)xb;
     XWord* xb1 = xb0 + words;
-    LA_CUDA_TRY(cudaFuncSetAttribute(solve_sweep_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP2_SMEM));
-    LA_CUDA_TRY(cudaFuncSetAttribute(solve_sweep_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP2_SMEM));
+    const int smem_bytes = narrow ? SweepCfg<8>::SMEM : SweepCfg<16>::SMEM;
+    const void* kf = narrow ? (const void*)solve_sweep_mma_kernel<true, 8> : (const void*)solve_sweep_mma_kernel<true, 16>;
+    const void* kb = narrow ? (const void*)solve_sweep_mma_kernel<false, 8> : (const void*)solve_sweep_mma_kernel<false, 16>;
+    LA_CUDA_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    LA_CUDA_TRY(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    LA_CUDA_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    LA_CUDA_TRY(cudaFuncSetAttribute(kb, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     size_t ldm = n;
     auto sweep = [&](bool fwd, const double* M, size_t rows, const uint64_t* pv, const double* rhs, double* out,
                      const double* winv) -> int {
@@ -567,10 +599,8 @@ int tri_sweeps_dev(const double* Lmat, const double* Umat, size_t n, const uint6
       unsigned tg = call_tag;
       XWord* xw = fwd ? xb0 : xb1;
       int gp = (int)((rows + PB - 1) / PB);
-      void* args[] = {&M, &ldm, &rows, &pv, &rhs, &out, &nxi, &xw, &tg, &winv};
-      LA_CUDA_TRY(cudaLaunchCooperativeKernel(fwd ? (const void*)solve_sweep_mma_kernel<true>
-                                                  : (const void*)solve_sweep_mma_kernel<false>,
-                                              dim3(gp), dim3(SWEEP_THREADS), args, SWEEP2_SMEM, st));
+      void* args[] = {&M, &ldm, &rows, &pv, &rhs, &out, &nxi, &gp, &xw, &tg, &winv};
+      LA_CUDA_TRY(cudaLaunchCooperativeKernel(fwd ? kf : kb, dim3(gp * chains), dim3(SWEEP_THREADS), args, smem_bytes, st));
       return LA_OK;
     };
     if (G <= max_g) {
