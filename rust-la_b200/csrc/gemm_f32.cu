@@ -443,6 +443,16 @@ int gemm_f32_dev(const float* A, size_t lda, const float* B, size_t ldb, float* 
   return launch_tf32<LA_GEMM_ADD>(tmA, tmB, tmA1, tmB1, tmC, (int)m, (int)n, (int)k, kpasses, ctx->sm_count, st);
 }
 
+int gemm_f32_preload() {
+  cudaFuncAttributes fa;
+  LA_CUDA_TRY(cudaFuncGetAttributes(&fa, gemm_f32_tf32_kernel<LA_GEMM_ASSIGN>));
+  LA_CUDA_TRY(cudaFuncGetAttributes(&fa, gemm_f32_tf32_kernel<LA_GEMM_ADD>));
+  LA_CUDA_TRY(cudaFuncGetAttributes(&fa, transpose_f32_kernel<true>));
+  LA_CUDA_TRY(cudaFuncGetAttributes(&fa, transpose_f32_kernel<false>));
+  LA_CUDA_TRY(cudaFuncGetAttributes(&fa, split_f32_kernel));
+  return LA_OK;
+}
+
 template <>
 int gemm_dev<float>(const float* A, size_t lda, const float* B, size_t ldb, float* C, size_t ldc, size_t m, size_t k,
                     size_t n, int mode, cudaStream_t st) {

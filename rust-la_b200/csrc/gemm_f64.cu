@@ -399,6 +399,17 @@ int gemm_f64_sum_slabs(const double* slabs, size_t slab_elems, int nslabs, doubl
   return LA_OK;
 }
 
+int gemm_f64_preload() {
+  cudaFuncAttributes fa;
+  LA_CUDA_TRY(cudaFuncGetAttributes(&fa, gemm_f64_tma_kernel<LA_GEMM_ASSIGN, 64>));
+  LA_CUDA_TRY(cudaFuncGetAttributes(&fa, gemm_f64_tma_kernel<LA_GEMM_SUB, 64>));
+  LA_CUDA_TRY(cudaFuncGetAttributes(&fa, gemm_f64_tma_kernel<LA_GEMM_ADD, 64>));
+  LA_CUDA_TRY(cudaFuncGetAttributes(&fa, gemm_f64_tma_kernel<LA_GEMM_ASSIGN, 128>));
+  LA_CUDA_TRY(cudaFuncGetAttributes(&fa, gemm_f64_tma_kernel<LA_GEMM_SUB, 128>));
+  LA_CUDA_TRY(cudaFuncGetAttributes(&fa, gemm_f64_tma_kernel<LA_GEMM_ADD, 128>));
+  return LA_OK;
+}
+
 // Tensor kernel regardless of problem size (the LU driver needs its in-place-safe tile structure: with m <= 128 there
 // is one tile row and every CTA consumes its whole column block of B before the epilogue writes C == B).
 int gemm_f64_tensor(const double* A, size_t lda, const double* B, size_t ldb, double* C, size_t ldc, size_t m, size_t k,

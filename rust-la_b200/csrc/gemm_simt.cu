@@ -113,6 +113,22 @@ int gemm_simt(const T* A, size_t lda, const T* B, size_t ldb, T* C, size_t ldc, 
   LA_CUDA_TRY(cudaGetLastError());
   return LA_OK;
 }
+// Forces the (lazily loaded) kernels of this file into the context: see gemm_preload in la_common.cuh.
+namespace {
+template <typename T>
+int preload_simt() {
+  cudaFuncAttributes fa;
+  LA_CUDA_TRY(cudaFuncGetAttributes(&fa, gemm_simt_kernel<T, LA_GEMM_ASSIGN>));
+  LA_CUDA_TRY(cudaFuncGetAttributes(&fa, gemm_simt_kernel<T, LA_GEMM_SUB>));
+  LA_CUDA_TRY(cudaFuncGetAttributes(&fa, gemm_simt_kernel<T, LA_GEMM_ADD>));
+  return LA_OK;
+}
+}  // namespace
+int gemm_simt_preload() {
+  LA_TRY(preload_simt<double>());
+  LA_TRY(preload_simt<float>());
+  return LA_OK;
+}
 template int gemm_simt<double>(const double*, size_t, const double*, size_t, double*, size_t, size_t, size_t, size_t,
                                int, cudaStream_t);
 template int gemm_simt<float>(const float*, size_t, const float*, size_t, float*, size_t, size_t, size_t, size_t, int,

@@ -78,6 +78,13 @@ template <typename T>
 int gemm_simt(const T* A, size_t lda, const T* B, size_t ldb, T* C, size_t ldc, size_t m, size_t k, size_t n, int mode,
               cudaStream_t st);
 
+// CUDA loads kernels lazily; the first launch of a kernel may have to wait for the device -- which never happens while a
+// kernel that is itself waiting for that launch is spinning.  The multi-GPU contexts therefore load every kernel a product
+// can launch up front (la_mg_connect).
+int gemm_f64_preload();
+int gemm_f32_preload();
+int gemm_simt_preload();
+
 template <typename T>
 int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, cudaStream_t st);
 template <typename T>

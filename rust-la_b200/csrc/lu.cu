@@ -507,7 +507,8 @@ lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_pe
 #pragma unroll
           for (int q = 0; q < Q; ++q) {
             const int col = lane + 32 * q;
-            v[i][q] = (q >= q0 && col > cn && col < jb) ? (EXACT ? sums[off + col] : rows[off + col]) : (T)0;
+            // (a row that is not live -- the published candidate / diagonal row, being written back by warp 1 -- is not read)
+            v[i][q] = (live[i] && q >= q0 && col > cn && col < jb) ? (EXACT ? sums[off + col] : rows[off + col]) : (T)0;
           }
         }
 #pragma unroll

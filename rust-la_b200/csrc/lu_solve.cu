@@ -354,7 +354,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SweepCfg<NXC>::CTAS_PER_SM)
 solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const uint64_t* __restrict__ piv,
                        const double* __restrict__ B, double* __restrict__ X, int nx, int G,
                        XWord* __restrict__ xbuf /* [chains][G][PB * NXC] flagged words */,
-                       unsigned tag, const double* __restrict__ Winv /* [G][128][128] inverted diagonal blocks */) {
+                       unsigned tag, const double* __restrict__ Winv /* [G][128][128] inverted diagonal blocks */,
+                       unsigned long long* __restrict__ dbg /* optional [chains * G][8] phase timestamps (ns) of the last step */) {
   using Cfg = SweepCfg<NXC>;
   constexpr int PHC = Cfg::PHC, PARTS = Cfg::PARTS, NT = Cfg::NT, XLD = Cfg::XLD, BUFS = Cfg::BUFS, WPT = Cfg::WPT;
   extern __shared__ __align__(16) unsigned char sweep_smem[];
@@ -436,6 +437,13 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
     }
   };
 
+  auto stamp = [&](int slot) {
+    if (dbg && t == 0) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+      dbg[(size_t)blockIdx.x * 8 + slot] = ns;
+    }
+  };
   issue_part(0);
   issue_part(1);
   issue_part(2);
@@ -471,7 +479,9 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
           const int idx = t + SWEEP_THREADS * u;
           Xs[(size_t)(idx / NXC) * XLD + (idx % NXC)] = -v[u];
         }
+        if (s == nsteps - 1) stamp(0);  // the last awaited block has arrived
       } else {
+        stamp(1);  // updates done
         // ---- X_g = W_g * (right-hand sides of this block): the same MMA loop on the inverted diagonal block ----
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
@@ -485,6 +495,7 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
     }
     cp_async_wait<BUFS - 1>();  // groups are committed in order: all but the two youngest have landed -> part i is in
     __syncthreads();            // buffer i % 3 (and, for hh == 0, Xs) is ready
+    if (own && hh == 0) stamp(2);  // inverted block and right-hand sides in place
     if (own) mma_part(i % BUFS, hh, res);
     else mma_part(i % BUFS, hh, acc);
     __syncthreads();            // everyone is done with buffer i % 3 (and, after the last part, with Xs)
@@ -504,6 +515,8 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
         if (has_readers) LL<double>::store(dst + rr * NXC + cl, (rr < nr && col < nx) ? v : 0.0, tag);
         if (rr < nr && col < nx) X[(size_t)(r0 + rr) * nx + col] = v;
       }
+  stamp(3);  // block product done, solution published
+  stamp(4);
 }
 
 template <typename T>
@@ -563,13 +576,13 @@ int tri_sweeps_dev(const double* Lmat, const double* Umat, size_t n, const uint6
   unsigned long long* d1 = nullptr;
   if (trace) {
     void* dp = nullptr;
-    LA_TRY(scratch_get(ctx->device, 14, 2 * sizeof(unsigned long long) * 8 * G, &dp));
-    LA_CUDA_TRY(cudaMemsetAsync(dp, 0, 2 * sizeof(unsigned long long) * 8 * G, st));
+    LA_TRY(scratch_get(ctx->device, 14, 4 * sizeof(unsigned long long) * 8 * G, &dp));  // [sweep][chain <= 2][G][8]
+    LA_CUDA_TRY(cudaMemsetAsync(dp, 0, 4 * sizeof(unsigned long long) * 8 * G, st));
     d0 = (unsigned long long*)dp;
-    d1 = d0 + 8 * G;
+    d1 = d0 + 16 * G;
   }
   static const int old_sweep = getenv("LA_SOLVE_OLD_SWEEP") ? atoi(getenv("LA_SOLVE_OLD_SWEEP")) : 0;  // A/B knob
-  if (!old_sweep && !trace) {
+  if (!old_sweep) {
     // flagged-word exchange buffers of the two sweeps; tags are unique per launch pair of this host thread (never 0)
     void* xb = nullptr;
     const int max_g = ctx->sm_count;  // cooperative grid: one block row per SM
@@ -599,13 +612,29 @@ int tri_sweeps_dev(const double* Lmat, const double* Umat, size_t n, const uint6
       unsigned tg = call_tag;
       XWord* xw = fwd ? xb0 : xb1;
       int gp = (int)((rows + PB - 1) / PB);
-      void* args[] = {&M, &ldm, &rows, &pv, &rhs, &out, &nxi, &gp, &xw, &tg, &winv};
+      unsigned long long* dg = trace ? (fwd ? d0 : d1) : nullptr;
+      void* args[] = {&M, &ldm, &rows, &pv, &rhs, &out, &nxi, &gp, &xw, &tg, &winv, &dg};
       LA_CUDA_TRY(cudaLaunchCooperativeKernel(fwd ? kf : kb, dim3(gp * chains), dim3(SWEEP_THREADS), args, smem_bytes, st));
       return LA_OK;
     };
     if (G <= max_g) {
       LA_TRY(sweep(true, Lmat, n, piv_dev, B, X, wl));
       LA_TRY(sweep(false, Umat, n, piv_dev, B, X, wu));
+      if (trace) {  // chain 0 only: phase timestamps of every CTA's last step
+        std::vector<unsigned long long> hbuf(32 * (size_t)G);
+        LA_CUDA_TRY(cudaStreamSynchronize(st));
+        LA_CUDA_TRY(cudaMemcpy(hbuf.data(), d0, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (int ph = 0; ph < 2; ++ph) {
+          const unsigned long long* hb = hbuf.data() + (size_t)ph * 16 * G;
+          const unsigned long long t0 = ph == 0 ? hb[3] : hb[(size_t)(G - 1) * 8 + 3];
+          for (int g = 0; g < G; g += (G > 32 ? G / 32 : 1)) {
+            const unsigned long long* e = hb + (size_t)g * 8;
+            fprintf(stderr, "sweep2 %s cta %3d: arrived %8.2f us | +updates %6.2f | +own ready %5.2f | +product/publish %6.2f\n",
+                    ph == 0 ? "fwd" : "bwd", g, e[0] ? (double)(e[0] - t0) * 1e-3 : 0.0,
+                    e[0] ? (double)(e[1] - e[0]) * 1e-3 : 0.0, (double)(e[2] - e[1]) * 1e-3, (double)(e[3] - e[2]) * 1e-3);
+          }
+        }
+      }
       return LA_OK;
     }
     // More block rows than SMs: leading parts of sm_count block rows each; between the parts the solved rows update the
@@ -640,11 +669,11 @@ int tri_sweeps_dev(const double* Lmat, const double* Umat, size_t n, const uint6
   LA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)solve_sweep_kernel<false>, dim3(G), dim3(SWEEP_THREADS), a1,
                                           SWEEP_SMEM, st));
   if (trace) {
-    std::vector<unsigned long long> hbuf(16 * (size_t)G);
+    std::vector<unsigned long long> hbuf(32 * (size_t)G);
     LA_CUDA_TRY(cudaStreamSynchronize(st));
     LA_CUDA_TRY(cudaMemcpy(hbuf.data(), d0, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     for (int ph = 0; ph < 2; ++ph) {
-      const unsigned long long* hb = hbuf.data() + (size_t)ph * 8 * G;
+      const unsigned long long* hb = hbuf.data() + (size_t)ph * 16 * G;
       const unsigned long long t0 = ph == 0 ? hb[3] : hb[(size_t)(G - 1) * 8 + 3];
       for (int g = 0; g < G; g += (G > 16 ? G / 16 : 1)) {
         const unsigned long long* e = hb + (size_t)g * 8;

@@ -514,6 +514,25 @@ int mg_connect(la_mg* c, const void* handles) {
     c->peer_base[q] = p;
     c->peer_flags[q] = reinterpret_cast<MgFlags*>(p + c->replica_bytes);
   }
+  // Load every kernel a product launches, and run the copy paths once, while no rank can be waiting on this one
+  // (lazy kernel loading and the driver's staging of 2-D copies may wait for the device; a peer's pull kernel that spins
+  // on OUR publish would make that wait circular when ranks share a device).
+  {
+    cudaFuncAttributes fa;
+    LA_CUDA_TRY(cudaFuncGetAttributes(&fa, mg_publish_kernel));
+    LA_CUDA_TRY(cudaFuncGetAttributes(&fa, mg_wait_acks_kernel));
+    LA_CUDA_TRY(cudaFuncGetAttributes(&fa, mg_ack_kernel));
+    LA_CUDA_TRY(cudaFuncGetAttributes(&fa, mg_pull_kernel));
+    LA_TRY(gemm_f64_preload());
+    LA_TRY(gemm_f32_preload());
+    LA_TRY(gemm_simt_preload());
+    unsigned char warm[64] = {0};
+    char* pad = reinterpret_cast<char*>(c->flags) + 16;  // inside MgFlags::pad: never read by the protocol
+    LA_CUDA_TRY(cudaMemcpy2DAsync(pad, 32, warm, 16, 16, 2, cudaMemcpyHostToDevice, c->s_h2d));
+    LA_CUDA_TRY(cudaMemcpy2DAsync(warm + 32, 16, pad, 32, 16, 2, cudaMemcpyDeviceToHost, c->s_d2h));
+    LA_CUDA_TRY(cudaStreamSynchronize(c->s_h2d));
+    LA_CUDA_TRY(cudaStreamSynchronize(c->s_d2h));
+  }
   c->connected = true;
   return LA_OK;
 }

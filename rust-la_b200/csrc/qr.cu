@@ -499,7 +499,9 @@ int qr_factor_dev(T* QR, size_t m, size_t n, T* rdiag, T* tmat, cudaStream_t st)
   };
   static const int lookahead = getenv("LA_QR_LOOKAHEAD") ? atoi(getenv("LA_QR_LOOKAHEAD")) : 1;
   const int nblk = (dc + nb - 1) / nb;
-  if (!lookahead || nblk < 3) {
+  // fp32 block reflectors run on the tcgen05 product, whose operand scratch is per host thread, not per stream: the two
+  // streams of the look-ahead would share it -- fp32 stays on the single-stream schedule
+  if (!lookahead || nblk < 3 || !std::is_same<T, double>::value) {
     for (int blk = 0; blk < nblk; ++blk) {
       const int j0 = blk * nb, jb = dc - j0 < nb ? dc - j0 : nb, c1 = j0 + jb;
       LA_TRY(run_panel(j0, jb, blk, false, st));

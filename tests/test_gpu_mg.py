@@ -28,9 +28,9 @@ def _ran_in_child(request):
     a hang fails this test only."""
     if os.environ.get("LA_MG_CHILD") == "1":
         return False
-    env = dict(os.environ, LA_MG_CHILD="1")
+    env = dict(os.environ, LA_MG_CHILD="1", CUDA_MODULE_LOADING="EAGER")
     out = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider", request.node.nodeid], cwd=ROOT,
-                         env=env, capture_output=True, text=True, timeout=150)
+                         env=env, capture_output=True, text=True, timeout=90)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
     return True
 
