@@ -346,6 +346,9 @@ struct SweepCfg {
   static constexpr int WPT = WORDS / SWEEP_THREADS;    // ... per thread
   static constexpr int SMEM = (BUFS * PB * PHC + PB * XLD) * (int)sizeof(double);
   static constexpr int CTAS_PER_SM = NXC == 16 ? 1 : 2;
+  // independent accumulator sets per output tile (k-steps are dealt round robin): a DMMA result takes ~100+ cycles to come
+  // back, and one set per tile made every block product a chain of 32 dependent MMAs -- latency, not the FP64 pipe, set its time
+  static constexpr int KSPLIT = NXC == 16 ? 2 : 4;
 };
 typedef LL<double>::word XWord;
 
@@ -358,6 +361,7 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
                        unsigned long long* __restrict__ dbg /* optional [chains * G][8] phase timestamps (ns) of the last step */) {
   using Cfg = SweepCfg<NXC>;
   constexpr int PHC = Cfg::PHC, PARTS = Cfg::PARTS, NT = Cfg::NT, XLD = Cfg::XLD, BUFS = Cfg::BUFS, WPT = Cfg::WPT;
+  constexpr int KS = Cfg::KSPLIT;
   extern __shared__ __align__(16) unsigned char sweep_smem[];
   double* Lbuf = reinterpret_cast<double*>(sweep_smem);  // [BUFS][PB][PHC]
   double* Xs = Lbuf + BUFS * PB * PHC;                   // [PB][XLD]: MINUS block k of the solution / this block's rhs
@@ -378,6 +382,9 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
   // already (almost) in place when the last update finishes -- its load is off the dependent chain.
   const int nparts = PARTS * (nsteps + 1);
   constexpr int CHUNKS = PHC / 2;  // 16-byte chunks per buffer row
+  // Every warp streams ITS OWN 16 rows of each part into a private slice of the buffer (rows 16 warp .. 16 warp + 15) and
+  // is the only reader of that slice: completion is a per-thread cp.async wait plus __syncwarp, no block-wide barrier per
+  // part (eight warps rendezvousing sixteen times per step was most of a step's time).
   auto issue_part = [&](int i) {
     if (i < nparts) {
       const int s = i / PARTS, hh = i - s * PARTS;
@@ -386,9 +393,9 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
       const int cbase = kb * PB + hh * PHC;
       const double* wsrc = Winv + (size_t)g * PB * PB + hh * PHC;
 #pragma unroll 4
-      for (int q = 0; q < (PB * CHUNKS) / SWEEP_THREADS; ++q) {
-        const int id = t + SWEEP_THREADS * q;
-        const int rr = id / CHUNKS, cc = id % CHUNKS;
+      for (int q = 0; q < (16 * CHUNKS) / 32; ++q) {
+        const int id = lane + 32 * q;
+        const int rr = 16 * warp + id / CHUNKS, cc = id % CHUNKS;
         const uint32_t dst = lbuf_s + (uint32_t)(((buf * PB + rr) * PHC + ((cc ^ (rr & 7)) << 1)) * sizeof(double));
         if (kb < 0) {
           cp_async16(dst, wsrc + (size_t)rr * PB + 2 * cc, 16);
@@ -403,7 +410,7 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
   };
 
   // acc[mt][nt][0..1] = element (row 16 warp + 8 mt + gid, columns c0 + 8 nt + 2 tig, + 1) of this block's right-hand sides
-  double acc[2][NT][2];
+  double acc[KS][2][NT][2];
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -414,16 +421,18 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
         double v = 0.0;
         if (rr < nr && col < nx)  // X = B(piv,:), lu.rs:246-254
           v = FORWARD ? B[(size_t)(piv ? piv[r0 + rr] : (uint64_t)(r0 + rr)) * nx + col] : X[(size_t)(r0 + rr) * nx + col];
-        acc[mt][nt][e] = v;
+        acc[0][mt][nt][e] = v;
+#pragma unroll
+        for (int q = 1; q < KS; ++q) acc[q][mt][nt][e] = 0.0;
       }
   // d += (rows of buffer buf) * (rows [PHC hh, PHC hh + PHC) of Xs)
-  auto mma_part = [&](int buf, int hh, double (&d)[2][NT][2]) {
+  auto mma_part = [&](int buf, int hh, double (&d)[KS][2][NT][2]) {
     const int row_a0 = 16 * warp + gid;
     const double* La0 = Lbuf + (size_t)(buf * PB + row_a0) * PHC;
     const double* La1 = La0 + 8 * PHC;
     const int sw = row_a0 & 7;  // == (row_a0 + 8) & 7
     const double* Xb = Xs + (size_t)(hh * PHC + tig) * XLD + gid;
-#pragma unroll 8
+#pragma unroll
     for (int ks = 0; ks < PHC / 4; ++ks) {
       const int col = 4 * ks + tig;
       const int off = (((col >> 1) ^ sw) << 1) + (col & 1);
@@ -431,8 +440,8 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const double bv = Xb[(size_t)(4 * ks) * XLD + 8 * nt];
-        dmma884(d[0][nt][0], d[0][nt][1], a0, bv);
-        dmma884(d[1][nt][0], d[1][nt][1], a1, bv);
+        dmma884(d[ks % KS][0][nt][0], d[ks % KS][0][nt][1], a0, bv);
+        dmma884(d[ks % KS][1][nt][0], d[ks % KS][1][nt][1], a1, bv);
       }
     }
   };
@@ -447,11 +456,12 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
   issue_part(0);
   issue_part(1);
   issue_part(2);
-  double res[2][NT][2];
+  double res[KS][2][NT][2];
   for (int i = 0; i < nparts; ++i) {
     const int s = i / PARTS, hh = i - s * PARTS;
     const bool own = s == nsteps;  // the parts of the inverted diagonal block
     if (hh == 0) {
+      __syncthreads();  // every warp has finished reading the previous block from Xs
       if (!own) {
         // ---- block kb of the solution: poll the producer's flagged words (WPT per thread), store MINUS the values ----
         const XWord* src = xbuf + (size_t)step_block(s) * Cfg::WORDS;
@@ -488,17 +498,25 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
             const int rr = 16 * warp + 8 * mt + gid, col = 8 * nt + 2 * tig;
-            *reinterpret_cast<double2*>(&Xs[(size_t)rr * XLD + col]) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
-            res[mt][nt][0] = res[mt][nt][1] = 0.0;
+            double r0v = acc[0][mt][nt][0], r1v = acc[0][mt][nt][1];
+#pragma unroll
+            for (int q = 1; q < KS; ++q) {
+              r0v += acc[q][mt][nt][0];
+              r1v += acc[q][mt][nt][1];
+            }
+            *reinterpret_cast<double2*>(&Xs[(size_t)rr * XLD + col]) = make_double2(r0v, r1v);
+#pragma unroll
+            for (int q = 0; q < KS; ++q) res[q][mt][nt][0] = res[q][mt][nt][1] = 0.0;
           }
       }
+      __syncthreads();  // Xs is complete
+      if (own) stamp(2);
     }
-    cp_async_wait<BUFS - 1>();  // groups are committed in order: all but the two youngest have landed -> part i is in
-    __syncthreads();            // buffer i % 3 (and, for hh == 0, Xs) is ready
-    if (own && hh == 0) stamp(2);  // inverted block and right-hand sides in place
+    cp_async_wait<BUFS - 1>();  // this thread's groups are committed in order: all but the two youngest have landed
+    __syncwarp();               // ... and so have the other lanes' chunks of this warp's slice of part i
     if (own) mma_part(i % BUFS, hh, res);
     else mma_part(i % BUFS, hh, acc);
-    __syncthreads();            // everyone is done with buffer i % 3 (and, after the last part, with Xs)
+    __syncwarp();               // the warp is done with its slice of buffer i % 3
     issue_part(i + BUFS);
   }
   // publish: flagged words for the CTAs that still need this block, plain values into X
@@ -511,7 +529,9 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int rr = 16 * warp + 8 * mt + gid, cl = 8 * nt + 2 * tig + e, col = c0 + cl;
-        const double v = res[mt][nt][e];
+        double v = res[0][mt][nt][e];
+#pragma unroll
+        for (int q = 1; q < KS; ++q) v += res[q][mt][nt][e];
         if (has_readers) LL<double>::store(dst + rr * NXC + cl, (rr < nr && col < nx) ? v : 0.0, tag);
         if (rr < nr && col < nx) X[(size_t)(r0 + rr) * nx + col] = v;
       }
