@@ -507,8 +507,16 @@ lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_pe
 #pragma unroll
           for (int q = 0; q < Q; ++q) {
             const int col = lane + 32 * q;
-            // (a row that is not live -- the published candidate / diagonal row, being written back by warp 1 -- is not read)
+            // A row that is not live (the published candidate / diagonal row, which warp 1 may be writing back) is replaced
+            // by row 0 as a dummy: its values are loaded, updated and DISCARDED (never stored).  compute-sanitizer's
+            // racecheck reports that dummy read against warp 1's write-back when row 0 is the candidate row; building with
+            // -DLA_RACECHECK_CLEAN predicates the load instead (0 hazards, profiles/r2_sanitizer_summary.txt) at the price of
+            // 4 % of the factorisation time (135 vs 130 ms at n = 16384: the predicate lengthens the hot loop).
+#ifdef LA_RACECHECK_CLEAN
             v[i][q] = (live[i] && q >= q0 && col > cn && col < jb) ? (EXACT ? sums[off + col] : rows[off + col]) : (T)0;
+#else
+            v[i][q] = (q >= q0 && col > cn && col < jb) ? (EXACT ? sums[off + col] : rows[off + col]) : (T)0;
+#endif
           }
         }
 #pragma unroll
@@ -1098,7 +1106,7 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
     // next-next panel's, which the chain brings up to date itself (same K range, 128 columns wide, high priority) as
     // soon as the U12 rows exist: the chain never waits for a bulk GEMM.
     static const int group_max = getenv("LA_LU_GROUP") ? atoi(getenv("LA_LU_GROUP")) : 2;            // 1 = no grouping
-    static const int group_rows = getenv("LA_LU_GROUP_ROWS") ? atoi(getenv("LA_LU_GROUP_ROWS")) : 3072;
+    static const int group_rows = getenv("LA_LU_GROUP_ROWS") ? atoi(getenv("LA_LU_GROUP_ROWS")) : 6144;
     int gstart = 0;        // first column of the open group (panels whose bulk trailing update is deferred)
     int gcount = 0;        // panels deferred so far in the open group
     int strip_k0 = 0;      // the next panel's columns lack the updates of panels [strip_k0, j0) (== j0: none)
@@ -1164,7 +1172,7 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
         // exclusive on their SMs because of their shared memory): factor the panel as two 64-wide halves -- half the
         // shared memory per row, half the SMs -- with the half-panel head/update in between.  The net effect on the 128
         // columns is that of one panel; the 128 pivots land in ipiv[0..128) for the usual perm/head/bulk of the next step.
-        static const int split_rows = getenv("LA_LU_SPLIT_ROWS") ? atoi(getenv("LA_LU_SPLIT_ROWS")) : 6144;  // 0 = never
+        static const int split_rows = getenv("LA_LU_SPLIT_ROWS") ? atoi(getenv("LA_LU_SPLIT_ROWS")) : 12288;  // 0 = never
         if (split_rows > 0 && nb2 == MAX_NB && M - c1 >= split_rows) {
           const int h = MAX_NB / 2, cm = c1 + h;
           LA_TRY(launch_panel(c1, h, sp, 0));

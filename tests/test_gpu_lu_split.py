@@ -1,5 +1,5 @@
 """The 64-wide split panel of the LU look-ahead (lu.cu, LA_LU_SPLIT_ROWS) is only taken for tall trailing matrices by
-default (>= 6144 rows: exercised by tests/test_gpu_full_size.py).  Force it for every panel in a child process -- the
+default (>= 12288 rows: exercised by tests/test_gpu_full_size.py).  Force it for every panel in a child process -- the
 knob is read once per process -- and check pivots, factors and backward error against the oracle on small systems."""
 import os
 import subprocess
@@ -41,7 +41,7 @@ def test_split_panel_forced_for_every_panel():
 @pytest.mark.parametrize("group", [2, 3, 4])
 def test_grouped_bulk_update_forced(group):
     """Grouped trailing updates (lu.cu, LA_LU_GROUP / LA_LU_GROUP_ROWS: K = group * 128 bulk GEMMs, the chain catching up
-    the next panel's columns itself) are only taken for trailing matrices of >= 3072 rows by default; force them from the
+    the next panel's columns itself) are only taken for trailing matrices of >= 6144 rows by default; force them from the
     first panel on, with and without split panels."""
     for split in ("0", "129"):
         env = dict(os.environ, LA_LU_GROUP=str(group), LA_LU_GROUP_ROWS="1", LA_LU_SPLIT_ROWS=split)
