@@ -385,24 +385,45 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
   // Every warp streams ITS OWN 16 rows of each part into a private slice of the buffer (rows 16 warp .. 16 warp + 15) and
   // is the only reader of that slice: completion is a per-thread cp.async wait plus __syncwarp, no block-wide barrier per
   // part (eight warps rendezvousing sixteen times per step was most of a step's time).
+  // The 16-byte chunks a thread copies keep their place from part to part (same rows of the warp's slice, same chunk
+  // column): shared-memory offsets, row validity and the row-to-row pointer strides are computed once; per part only the
+  // base pointers change (the address arithmetic of 8..16 cp.async per thread and part was as many issue slots as the MMAs).
+  constexpr int NQ = (16 * CHUNKS) / 32;       // chunks per thread and part
+  constexpr int ROWSTEP = 32 / CHUNKS;         // rows between a thread's consecutive chunks (CHUNKS = 16 or 32)
+  const int cc = lane % CHUNKS;
+  const int rr0 = 16 * warp + lane / CHUNKS;   // first row of this thread
+  uint32_t dst_off[NQ];
+  unsigned row_ok = 0;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int rr = rr0 + q * ROWSTEP;
+    dst_off[q] = (uint32_t)((rr * PHC + ((cc ^ (rr & 7)) << 1)) * sizeof(double));
+    if (r0 + rr < N) row_ok |= 1u << q;
+  }
+  const char* lu_row0 = reinterpret_cast<const char*>(LU + (size_t)(r0 + rr0) * ld + 2 * cc);
+  const size_t lu_stride = (size_t)ROWSTEP * ld * sizeof(double);
+  const char* w_row0 = reinterpret_cast<const char*>(Winv + (size_t)g * PB * PB + (size_t)rr0 * PB + 2 * cc);
+  constexpr size_t W_STRIDE = (size_t)ROWSTEP * PB * sizeof(double);
   auto issue_part = [&](int i) {
     if (i < nparts) {
       const int s = i / PARTS, hh = i - s * PARTS;
-      const int kb = s < nsteps ? step_block(s) : -1;
-      const int buf = i % BUFS;
-      const int cbase = kb * PB + hh * PHC;
-      const double* wsrc = Winv + (size_t)g * PB * PB + hh * PHC;
-#pragma unroll 4
-      for (int q = 0; q < (16 * CHUNKS) / 32; ++q) {
-        const int id = lane + 32 * q;
-        const int rr = 16 * warp + id / CHUNKS, cc = id % CHUNKS;
-        const uint32_t dst = lbuf_s + (uint32_t)(((buf * PB + rr) * PHC + ((cc ^ (rr & 7)) << 1)) * sizeof(double));
-        if (kb < 0) {
-          cp_async16(dst, wsrc + (size_t)rr * PB + 2 * cc, 16);
-        } else {
-          const int col = cbase + 2 * cc;
-          const bool ok = r0 + rr < N && col < N;  // n is even: a pair of columns is inside or outside as a whole
-          cp_async16(dst, ok ? LU + (size_t)(r0 + rr) * ld + col : LU, ok ? 16 : 0);
+      const uint32_t dbase = lbuf_s + (uint32_t)((i % BUFS) * PB * PHC * sizeof(double));
+      if (s < nsteps) {
+        const int cbase = step_block(s) * PB + hh * PHC;
+        const bool col_ok = cbase + 2 * cc < N;  // n is even: a pair of columns is inside or outside as a whole
+        const char* src = lu_row0 + (size_t)cbase * sizeof(double);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const bool ok = col_ok && ((row_ok >> q) & 1u);
+          cp_async16(dbase + dst_off[q], ok ? (const void*)src : (const void*)LU, ok ? 16 : 0);
+          src += lu_stride;
+        }
+      } else {
+        const char* src = w_row0 + (size_t)hh * PHC * sizeof(double);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          cp_async16(dbase + dst_off[q], src, 16);
+          src += W_STRIDE;
         }
       }
     }

@@ -117,6 +117,52 @@ mg_pull_kernel(const char* __restrict__ src, char* __restrict__ dst, size_t pitc
   }
 }
 
+// One launch pulls the column blocks of SEVERAL owners (a whole pass: everything right of our block, or everything left
+// of it): the grid is divided evenly over the owners, every CTA waits for its owner's ready flag and streams that block.
+// Small blocks (the f32 config: 8 MiB each) are latency-bound -- seven back-to-back (pull, ack) launch pairs cost more than
+// the multiply they feed; large ones lose nothing.
+struct MgPullList {
+  int count;
+  const char* src[MG_MAX_RANKS];
+  const MgFlags* ready[MG_MAX_RANKS];   // the owner's flag block (its `ready` word is polled)
+  unsigned* ack[MG_MAX_RANKS];          // where our ack for that owner goes (its flag block, our slot)
+  size_t col_off[MG_MAX_RANKS];
+  size_t width_bytes[MG_MAX_RANKS];
+};
+__global__ void __launch_bounds__(PULL_THREADS)
+mg_pull_multi_kernel(const __grid_constant__ MgPullList L, char* __restrict__ dst, size_t pitch, size_t rows, int ctas_per_owner,
+                     unsigned e) {
+  const int o = blockIdx.x / ctas_per_owner, b = blockIdx.x - o * ctas_per_owner;
+  if (threadIdx.x == 0) {
+    while ((int)(ld_acquire_sys(&L.ready[o]->ready) - e) < 0) __nanosleep(100);
+  }
+  __syncthreads();
+  const char* __restrict__ src = L.src[o];
+  const size_t col_off = L.col_off[o];
+  const size_t chunks_per_row = L.width_bytes[o] / 16;
+  const size_t total = rows * chunks_per_row;
+  const size_t stride = (size_t)ctas_per_owner * PULL_THREADS;
+  for (size_t base = (size_t)b * PULL_THREADS + threadIdx.x; base < total; base += stride * PULL_UNROLL) {
+    uint4 v[PULL_UNROLL];
+    size_t off[PULL_UNROLL];
+#pragma unroll
+    for (int u = 0; u < PULL_UNROLL; ++u) {
+      const size_t c = base + (size_t)u * stride;
+      const size_t r = c / chunks_per_row;
+      off[u] = r * pitch + col_off + (c - r * chunks_per_row) * 16;
+      if (c < total) v[u] = ld_relaxed_sys_v4(src + off[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < PULL_UNROLL; ++u)
+      if (base + (size_t)u * stride < total) *reinterpret_cast<uint4*>(dst + off[u]) = v[u];
+  }
+}
+// acks of a whole pass: thread o tells owner o that its block of epoch e has been pulled (runs after the pull kernel)
+__global__ void mg_ack_multi_kernel(const __grid_constant__ MgPullList L, unsigned e) {
+  __threadfence_system();
+  if ((int)threadIdx.x < L.count) st_release_sys(L.ack[threadIdx.x], e);
+}
+
 }  // namespace
 }  // namespace la
 
@@ -207,20 +253,38 @@ int mg_queue_pulls(la_mg* c, unsigned e) {
   const size_t pitch = c->n * c->elem;
   for (int pass = 0; pass < 2; ++pass) {
     const int q0 = pass == 0 ? c->rank + 1 : 0, q1 = pass == 0 ? c->nranks : c->rank;
-    for (int q = q0; q < q1; ++q) {
-      const size_t off = c->col0[q] * c->elem, wb = (c->col1[q] - c->col0[q]) * c->elem;
-      if (wb == 0) continue;
-      if (mg_pull_with_ce()) {
+    if (mg_pull_with_ce()) {
+      for (int q = q0; q < q1; ++q) {
+        const size_t off = c->col0[q] * c->elem, wb = (c->col1[q] - c->col0[q]) * c->elem;
+        if (wb == 0) continue;
         // the flag wait still happens on the device: a one-CTA pull of zero rows
         mg_pull_kernel<<<1, PULL_THREADS, 0, c->s_pull>>>(c->peer_base[q], c->base, pitch, off, wb, 0, c->peer_flags[q], e);
         LA_CUDA_TRY(cudaMemcpy2DAsync(c->base + off, pitch, c->peer_base[q] + off, pitch, wb, c->k, cudaMemcpyDeviceToDevice,
                                       c->s_pull));
-      } else {
-        mg_pull_kernel<<<mg_pull_ctas(), PULL_THREADS, 0, c->s_pull>>>(c->peer_base[q], c->base, pitch, off, wb, c->k,
-                                                                      c->peer_flags[q], e);
+        mg_ack_kernel<<<1, 1, 0, c->s_pull>>>(c->peer_flags[q], c->rank, e);
+        LA_CUDA_TRY(cudaGetLastError());
       }
-      mg_ack_kernel<<<1, 1, 0, c->s_pull>>>(c->peer_flags[q], c->rank, e);
-      LA_CUDA_TRY(cudaGetLastError());
+    } else {
+      MgPullList L;
+      L.count = 0;
+      for (int q = q0; q < q1; ++q) {
+        const size_t wb = (c->col1[q] - c->col0[q]) * c->elem;
+        if (wb == 0) continue;
+        const int o = L.count++;
+        L.src[o] = c->peer_base[q];
+        L.ready[o] = c->peer_flags[q];
+        L.ack[o] = &c->peer_flags[q]->ack[c->rank * MG_ACK_STRIDE];
+        L.col_off[o] = c->col0[q] * c->elem;
+        L.width_bytes[o] = wb;
+      }
+      if (L.count > 0) {
+        // mg_pull_ctas() CTAs per owner, at most twice that in total (pull CTAs take SMs from the GEMM that runs beside them)
+        int per = mg_pull_ctas();
+        if (per * L.count > 2 * mg_pull_ctas()) per = (2 * mg_pull_ctas() + L.count - 1) / L.count;
+        mg_pull_multi_kernel<<<per * L.count, PULL_THREADS, 0, c->s_pull>>>(L, c->base, pitch, c->k, per, e);
+        mg_ack_multi_kernel<<<1, MG_MAX_RANKS, 0, c->s_pull>>>(L, e);
+        LA_CUDA_TRY(cudaGetLastError());
+      }
     }
     LA_CUDA_TRY(cudaEventRecord(c->ev_pull[pass], c->s_pull));
   }
@@ -523,6 +587,8 @@ int mg_connect(la_mg* c, const void* handles) {
     LA_CUDA_TRY(cudaFuncGetAttributes(&fa, mg_wait_acks_kernel));
     LA_CUDA_TRY(cudaFuncGetAttributes(&fa, mg_ack_kernel));
     LA_CUDA_TRY(cudaFuncGetAttributes(&fa, mg_pull_kernel));
+    LA_CUDA_TRY(cudaFuncGetAttributes(&fa, mg_pull_multi_kernel));
+    LA_CUDA_TRY(cudaFuncGetAttributes(&fa, mg_ack_multi_kernel));
     LA_TRY(gemm_f64_preload());
     LA_TRY(gemm_f32_preload());
     LA_TRY(gemm_simt_preload());
