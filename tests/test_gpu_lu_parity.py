@@ -257,3 +257,32 @@ def test_small_gemm_is_bit_exact(oracle, shape):
         suf = "f64" if dt == np.float64 else "f32"
         check(getattr(lib(), f"la_gemm_{suf}_host")(a.ctypes.data, b.ctypes.data, c.ctypes.data, m, k, n))
         assert np.array_equal(c.view(np.uint8), oracle.gemm(a, b, form="canon").view(np.uint8))
+
+
+@pytest.mark.parametrize("cond", [1e4, 1e8, 1e12])
+def test_solve_residual_on_ill_conditioned_systems(oracle, cond):
+    """The fast solves multiply by explicitly inverted 128 x 128 diagonal blocks instead of substituting (lu_solve.cu).
+    On ill-conditioned systems (prescribed singular values 1 .. 1/cond, and a row-graded matrix) the scaled residual must
+    stay within 10x of the reference's substitution (lu.rs:255-275) for both the sweep kernels (nx <= 16) and the GEMM sweeps
+    (nx > 16); the solutions themselves may differ by cond * eps."""
+    rng = np.random.default_rng(7)
+    n = 1024
+    q1, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    q2, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    mats = [np.ascontiguousarray(q1 @ np.diag(np.logspace(0, -np.log10(cond), n)) @ q2)]
+    if cond == 1e8:
+        mats.append(np.ascontiguousarray(rng.standard_normal((n, n)) * np.logspace(0, -8, n)[:, None]))
+
+    def res(a, x, b):
+        return np.linalg.norm(a @ x - b) / (np.linalg.norm(a) * np.linalg.norm(x))
+
+    for a in mats:
+        lu, piv, _ = oracle.lu(a)
+        dec = LUDecomposition.new(Matrix.from_numpy(a))
+        for nx in (3, 40):
+            b = np.ascontiguousarray(rng.standard_normal((n, nx)))
+            xr = oracle.lu_solve(lu, piv, b)
+            xg = dec.solve(Matrix.from_numpy(b)).to_numpy()
+            assert np.all(np.isfinite(xg))
+            assert res(a, xg, b) <= 10 * max(res(a, xr, b), 1e-16)
+            assert np.linalg.norm(xg - xr) <= 1e3 * cond * np.finfo(np.float64).eps * np.linalg.norm(xr)
