@@ -335,16 +335,21 @@ solve_sweep_kernel(const double* __restrict__ LU, size_t n, const uint64_t* __re
 // <= 8; 32-column quarters, three 32 KB buffers, two CTAs per SM).  Two chains halve the block products on the dependent
 // path (each CTA multiplies 128 x 128 x 8), the critical CTAs of the two chains sit on different SMs, and the second reader
 // of every LU block hits L2.
-template <int NXC>
+// BULK (experiment, off by default -- slower, see tri_sweeps_dev): every row segment of a part arrives by ONE cp.async.bulk
+// (TMA engine, 256 / 512 contiguous bytes, completion on a per-warp mbarrier) instead of 16 / 32 sixteen-byte cp.async.
+// Rows are padded by two doubles instead of swizzled (a bulk copy is contiguous); needs n a multiple of 128.
+template <int NXC, bool BULK = false>
 struct SweepCfg {
   static constexpr int PHC = NXC == 16 ? 64 : 32;      // LU columns per shared-memory buffer
+  static constexpr int RS = BULK ? PHC + 2 : PHC;      // row stride of a buffer (doubles)
+  static constexpr int BAR_BYTES = BULK ? 256 : 0;     // 8 warps x 3 buffers mbarriers
   static constexpr int PARTS = PB / PHC;               // buffers per 128-column block
   static constexpr int NT = NXC / 8;                   // 8-column MMA tiles
   static constexpr int XLD = NXC == 16 ? 24 : 8;       // row stride of the X block: a fragment load covers all banks twice
   static constexpr int BUFS = 3;
   static constexpr int WORDS = PB * NXC;               // flagged words per solved block
   static constexpr int WPT = WORDS / SWEEP_THREADS;    // ... per thread
-  static constexpr int SMEM = (BUFS * PB * PHC + PB * XLD) * (int)sizeof(double);
+  static constexpr int SMEM = (BUFS * PB * RS + PB * XLD) * (int)sizeof(double) + BAR_BYTES;
   static constexpr int CTAS_PER_SM = NXC == 16 ? 1 : 2;
   // independent accumulator sets per output tile (k-steps are dealt round robin): a DMMA result takes ~100+ cycles to come
   // back, and one set per tile made every block product a chain of 32 dependent MMAs -- latency, not the FP64 pipe, set its time
@@ -352,19 +357,26 @@ struct SweepCfg {
 };
 typedef LL<double>::word XWord;
 
-template <bool FORWARD, int NXC>
-__global__ void __launch_bounds__(SWEEP_THREADS, SweepCfg<NXC>::CTAS_PER_SM)
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(mbar)
+               : "memory");
+}
+
+template <bool FORWARD, int NXC, bool BULK>
+__global__ void __launch_bounds__(SWEEP_THREADS, SweepCfg<NXC, BULK>::CTAS_PER_SM)
 solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const uint64_t* __restrict__ piv,
                        const double* __restrict__ B, double* __restrict__ X, int nx, int G,
                        XWord* __restrict__ xbuf /* [chains][G][PB * NXC] flagged words */,
                        unsigned tag, const double* __restrict__ Winv /* [G][128][128] inverted diagonal blocks */,
                        unsigned long long* __restrict__ dbg /* optional [chains * G][8] phase timestamps (ns) of the last step */) {
-  using Cfg = SweepCfg<NXC>;
+  using Cfg = SweepCfg<NXC, BULK>;
   constexpr int PHC = Cfg::PHC, PARTS = Cfg::PARTS, NT = Cfg::NT, XLD = Cfg::XLD, BUFS = Cfg::BUFS, WPT = Cfg::WPT;
-  constexpr int KS = Cfg::KSPLIT;
+  constexpr int KS = Cfg::KSPLIT, RS = Cfg::RS;
   extern __shared__ __align__(16) unsigned char sweep_smem[];
-  double* Lbuf = reinterpret_cast<double*>(sweep_smem);  // [BUFS][PB][PHC]
-  double* Xs = Lbuf + BUFS * PB * PHC;                   // [PB][XLD]: MINUS block k of the solution / this block's rhs
+  double* Lbuf = reinterpret_cast<double*>(sweep_smem);  // [BUFS][PB][RS]
+  double* Xs = Lbuf + BUFS * PB * RS;                    // [PB][XLD]: MINUS block k of the solution / this block's rhs
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Xs + PB * XLD);  // BULK: [8 warps][BUFS] "part has landed"
   const int chain = blockIdx.x / G, g = blockIdx.x - chain * G;
   const int c0 = chain * NXC;                            // first right-hand side of this chain
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -404,7 +416,29 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
   const size_t lu_stride = (size_t)ROWSTEP * ld * sizeof(double);
   const char* w_row0 = reinterpret_cast<const char*>(Winv + (size_t)g * PB * PB + (size_t)rr0 * PB + 2 * cc);
   constexpr size_t W_STRIDE = (size_t)ROWSTEP * PB * sizeof(double);
+  // BULK: lane q < 16 copies row 16 warp + q of the part (PHC * 8 contiguous bytes); the warp's mbarrier of that buffer
+  // counts the bytes.  Every row and column is inside the matrix (n is a multiple of 128 on this path).
+  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(bars + warp * BUFS);
+  const char* lu_brow = reinterpret_cast<const char*>(LU + (size_t)(r0 + 16 * warp + (lane & 15)) * ld);
+  const char* w_brow = reinterpret_cast<const char*>(Winv + (size_t)g * PB * PB + (size_t)(16 * warp + (lane & 15)) * PB);
+  const uint32_t brow_dst = (uint32_t)((16 * warp + (lane & 15)) * RS * sizeof(double));
   auto issue_part = [&](int i) {
+    if constexpr (BULK) {
+      if (i < nparts) {
+        const int s = i / PARTS, hh = i - s * PARTS;
+        const int buf = i % BUFS;
+        const uint32_t bar = bar_s + (uint32_t)(buf * sizeof(uint64_t));
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(16u * PHC * 8u) : "memory");
+        __syncwarp();
+        if (lane < 16) {
+          const char* src = s < nsteps ? lu_brow + ((size_t)step_block(s) * PB + (size_t)hh * PHC) * sizeof(double)
+                                       : w_brow + (size_t)hh * PHC * sizeof(double);
+          bulk_copy_g2s(lbuf_s + (uint32_t)(buf * PB * RS * sizeof(double)) + brow_dst, src, PHC * 8u, bar);
+        }
+      }
+      return;
+    }
     if (i < nparts) {
       const int s = i / PARTS, hh = i - s * PARTS;
       const uint32_t dbase = lbuf_s + (uint32_t)((i % BUFS) * PB * PHC * sizeof(double));
@@ -449,14 +483,14 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
   // d += (rows of buffer buf) * (rows [PHC hh, PHC hh + PHC) of Xs)
   auto mma_part = [&](int buf, int hh, double (&d)[KS][2][NT][2]) {
     const int row_a0 = 16 * warp + gid;
-    const double* La0 = Lbuf + (size_t)(buf * PB + row_a0) * PHC;
-    const double* La1 = La0 + 8 * PHC;
+    const double* La0 = Lbuf + (size_t)(buf * PB + row_a0) * RS;
+    const double* La1 = La0 + 8 * RS;
     const int sw = row_a0 & 7;  // == (row_a0 + 8) & 7
     const double* Xb = Xs + (size_t)(hh * PHC + tig) * XLD + gid;
 #pragma unroll
     for (int ks = 0; ks < PHC / 4; ++ks) {
       const int col = 4 * ks + tig;
-      const int off = (((col >> 1) ^ sw) << 1) + (col & 1);
+      const int off = BULK ? col : (((col >> 1) ^ sw) << 1) + (col & 1);  // padded rows (BULK) or swizzled chunks
       const double a0 = La0[off], a1 = La1[off];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
@@ -474,6 +508,12 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
       dbg[(size_t)blockIdx.x * 8 + slot] = ns;
     }
   };
+  if constexpr (BULK) {
+    if (lane == 0)
+      for (int b = 0; b < BUFS; ++b) mbar_init(bars + warp * BUFS + b, 1);
+    mbar_fence_init();
+    __syncwarp();
+  }
   issue_part(0);
   issue_part(1);
   issue_part(2);
@@ -533,8 +573,12 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
       __syncthreads();  // Xs is complete
       if (own) stamp(2);
     }
-    cp_async_wait<BUFS - 1>();  // this thread's groups are committed in order: all but the two youngest have landed
-    __syncwarp();               // ... and so have the other lanes' chunks of this warp's slice of part i
+    if constexpr (BULK) {
+      mbar_wait(bars + warp * BUFS + i % BUFS, (uint32_t)((i / BUFS) & 1));  // the warp's slice of part i has landed
+    } else {
+      cp_async_wait<BUFS - 1>();  // this thread's groups are committed in order: all but the two youngest have landed
+      __syncwarp();               // ... and so have the other lanes' chunks of this warp's slice of part i
+    }
     if (own) mma_part(i % BUFS, hh, res);
     else mma_part(i % BUFS, hh, acc);
     __syncwarp();               // the warp is done with its slice of buffer i % 3
@@ -638,9 +682,17 @@ int tri_sweeps_dev(const double* Lmat, const double* Umat, size_t n, const uint6
     static thread_local unsigned call_tag = 0;
     XWord* xb0 = (XWord*)xb;
     XWord* xb1 = xb0 + words;
-    const int smem_bytes = narrow ? SweepCfg<8>::SMEM : SweepCfg<16>::SMEM;
-    const void* kf = narrow ? (const void*)solve_sweep_mma_kernel<true, 8> : (const void*)solve_sweep_mma_kernel<true, 16>;
-    const void* kb = narrow ? (const void*)solve_sweep_mma_kernel<false, 8> : (const void*)solve_sweep_mma_kernel<false, 16>;
+    // bulk (TMA engine) copies, one 256 / 512-byte row segment per instruction: OFF by default -- measured 2.45 ms against
+    // 1.92 ms for the 16-byte cp.async form at n = 16384 (128 small bulk requests per part and CTA cost more than the issue
+    // slots they save); LA_SOLVE_BULK=1 keeps the experiment reproducible (needs n a multiple of 128)
+    static const int bulk_knob = getenv("LA_SOLVE_BULK") ? atoi(getenv("LA_SOLVE_BULK")) : 0;
+    const bool bulk = bulk_knob && n % PB == 0 && ((uintptr_t)wl % 16 == 0) && ((uintptr_t)wu % 16 == 0);
+    const int smem_bytes = narrow ? (bulk ? SweepCfg<8, true>::SMEM : SweepCfg<8>::SMEM)
+                                  : (bulk ? SweepCfg<16, true>::SMEM : SweepCfg<16>::SMEM);
+    const void* kf = narrow ? (bulk ? (const void*)solve_sweep_mma_kernel<true, 8, true> : (const void*)solve_sweep_mma_kernel<true, 8, false>)
+                            : (bulk ? (const void*)solve_sweep_mma_kernel<true, 16, true> : (const void*)solve_sweep_mma_kernel<true, 16, false>);
+    const void* kb = narrow ? (bulk ? (const void*)solve_sweep_mma_kernel<false, 8, true> : (const void*)solve_sweep_mma_kernel<false, 8, false>)
+                            : (bulk ? (const void*)solve_sweep_mma_kernel<false, 16, true> : (const void*)solve_sweep_mma_kernel<false, 16, false>);
     LA_CUDA_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     LA_CUDA_TRY(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     LA_CUDA_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
