@@ -477,8 +477,9 @@ int qr_factor_dev(T* QR, size_t m, size_t n, T* rdiag, T* tmat, cudaStream_t st)
     const int R = M - j0;
     int rpc = (R + sms - 1) / sms;
     if (beside_bulk) {  // a panel CTA owns its SM (shared memory): fewer, fuller CTAs leave the rest to the DMMA GEMMs
+      static const int rpc_div = getenv("LA_QR_RPC_DIV") ? atoi(getenv("LA_QR_RPC_DIV")) : 48;  // tuning knob
       const int fit = (int)(QR_SMEM_BUDGET / ((size_t)(jb | 1) * sizeof(T)));
-      int want = R / 48;
+      int want = R / rpc_div;
       if (want > fit) want = fit;
       if (rpc < want) rpc = want;
     }
