@@ -345,10 +345,7 @@ struct SweepCfg {
   static constexpr int BAR_BYTES = BULK ? 256 : 0;     // 8 warps x 3 buffers mbarriers
   static constexpr int PARTS = PB / PHC;               // buffers per 128-column block
   static constexpr int NT = NXC / 8;                   // 8-column MMA tiles
-  // the X block is stored as k-PAIRS, Xs[k >> 1][n][k & 1]: one 16-byte load feeds the B fragments of an even-k and an odd-k
-  // MMA (an MMA's four k's need not be adjacent), as one 16-byte load of LU feeds both A fragments; XPS = pair-row stride
-  static constexpr int XPS = NXC == 16 ? 36 : 16;
-  static constexpr int XLD = XPS / 2;                  // doubles per k (only the total size uses it)
+  static constexpr int XLD = NXC == 16 ? 24 : 8;       // row stride of the X block: a fragment load covers all banks twice
   static constexpr int BUFS = 3;
   static constexpr int WORDS = PB * NXC;               // flagged words per solved block
   static constexpr int WPT = WORDS / SWEEP_THREADS;    // ... per thread
@@ -356,7 +353,7 @@ struct SweepCfg {
   static constexpr int CTAS_PER_SM = NXC == 16 ? 1 : 2;
   // independent accumulator sets per output tile (k-steps are dealt round robin): a DMMA result takes ~100+ cycles to come
   // back, and one set per tile made every block product a chain of 32 dependent MMAs -- latency, not the FP64 pipe, set its time
-  static constexpr int KSPLIT = 2;  // even-k and odd-k MMAs accumulate separately
+  static constexpr int KSPLIT = NXC == 16 ? 2 : 4;
 };
 typedef LL<double>::word XWord;
 
@@ -375,7 +372,7 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
                        unsigned long long* __restrict__ dbg /* optional [chains * G][8] phase timestamps (ns) of the last step */) {
   using Cfg = SweepCfg<NXC, BULK>;
   constexpr int PHC = Cfg::PHC, PARTS = Cfg::PARTS, NT = Cfg::NT, XLD = Cfg::XLD, BUFS = Cfg::BUFS, WPT = Cfg::WPT;
-  constexpr int KS = Cfg::KSPLIT, RS = Cfg::RS, XPS = Cfg::XPS;
+  constexpr int KS = Cfg::KSPLIT, RS = Cfg::RS;
   extern __shared__ __align__(16) unsigned char sweep_smem[];
   double* Lbuf = reinterpret_cast<double*>(sweep_smem);  // [BUFS][PB][RS]
   double* Xs = Lbuf + BUFS * PB * RS;                    // [PB][XLD]: MINUS block k of the solution / this block's rhs
@@ -489,21 +486,17 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
     const double* La0 = Lbuf + (size_t)(buf * PB + row_a0) * RS;
     const double* La1 = La0 + 8 * RS;
     const int sw = row_a0 & 7;  // == (row_a0 + 8) & 7
-    const double* Xb = Xs + (size_t)((hh * PHC) / 2 + tig) * XPS + 2 * gid;
-    // 8 k's per trip: lane tig supplies k = 8 c + 2 tig (even MMA) and 8 c + 2 tig + 1 (odd MMA) from ONE 16-byte load each
+    const double* Xb = Xs + (size_t)(hh * PHC + tig) * XLD + gid;
 #pragma unroll
-    for (int c = 0; c < PHC / 8; ++c) {
-      const int chunk = 4 * c + tig;                                        // 16-byte chunk (pair of columns) of the row
-      const int off = BULK ? 2 * chunk : ((chunk ^ sw) << 1);               // padded rows (BULK) or swizzled chunks
-      const double2 a0 = *reinterpret_cast<const double2*>(La0 + off);
-      const double2 a1 = *reinterpret_cast<const double2*>(La1 + off);
+    for (int ks = 0; ks < PHC / 4; ++ks) {
+      const int col = 4 * ks + tig;
+      const int off = BULK ? col : (((col >> 1) ^ sw) << 1) + (col & 1);  // padded rows (BULK) or swizzled chunks
+      const double a0 = La0[off], a1 = La1[off];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        const double2 bv = *reinterpret_cast<const double2*>(Xb + (size_t)(4 * c) * XPS + 16 * nt);
-        dmma884(d[(2 * c) % KS][0][nt][0], d[(2 * c) % KS][0][nt][1], a0.x, bv.x);
-        dmma884(d[(2 * c) % KS][1][nt][0], d[(2 * c) % KS][1][nt][1], a1.x, bv.x);
-        dmma884(d[(2 * c + 1) % KS][0][nt][0], d[(2 * c + 1) % KS][0][nt][1], a0.y, bv.y);
-        dmma884(d[(2 * c + 1) % KS][1][nt][0], d[(2 * c + 1) % KS][1][nt][1], a1.y, bv.y);
+        const double bv = Xb[(size_t)(4 * ks) * XLD + 8 * nt];
+        dmma884(d[ks % KS][0][nt][0], d[ks % KS][0][nt][1], a0, bv);
+        dmma884(d[ks % KS][1][nt][0], d[ks % KS][1][nt][1], a1, bv);
       }
     }
   };
@@ -555,8 +548,7 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
 #pragma unroll
         for (int u = 0; u < WPT; ++u) {
           const int idx = t + SWEEP_THREADS * u;
-          const int kk = idx / NXC, nn = idx % NXC;
-          Xs[(size_t)(kk >> 1) * XPS + 2 * nn + (kk & 1)] = -v[u];
+          Xs[(size_t)(idx / NXC) * XLD + (idx % NXC)] = -v[u];
         }
         if (s == nsteps - 1) stamp(0);  // the last awaited block has arrived
       } else {
@@ -573,8 +565,7 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
               r0v += acc[q][mt][nt][0];
               r1v += acc[q][mt][nt][1];
             }
-            Xs[(size_t)(rr >> 1) * XPS + 2 * col + (rr & 1)] = r0v;
-            Xs[(size_t)(rr >> 1) * XPS + 2 * (col + 1) + (rr & 1)] = r1v;
+            *reinterpret_cast<double2*>(&Xs[(size_t)rr * XLD + col]) = make_double2(r0v, r1v);
 #pragma unroll
             for (int q = 0; q < KS; ++q) res[q][mt][nt][0] = res[q][mt][nt][1] = 0.0;
           }
