@@ -32,7 +32,7 @@ template <typename T>
 int tri_block_inverses(const T* M, size_t n, int mode, int first_block, int nblocks, T* W, int trans_out,
                        cudaStream_t st);  // lu.cu
 int tri_sweeps_dev(const double* Lmat, const double* Umat, size_t n, const uint64_t* piv_dev, const double* B, size_t nx,
-                   double* X, const double* wl, const double* wu, cudaStream_t st);  // lu_solve.cu
+                   double* X, const double* wl, const double* wu, cudaStream_t st, int wu_mode);  // lu_solve.cu
 
 namespace {
 constexpr int CB = 128;  // block size
@@ -325,9 +325,9 @@ int chol_solve_dev(const T* L, size_t n, const T* B, size_t nx, T* X, cudaStream
       double* WU = WL + (size_t)G * CB * CB;
       LA_TRY(transpose_dev<double>(L, LT, n, n, st));
       LA_TRY(tri_block_inverses<double>(L, n, 2, 0, G, WL, 0, st));
+      if (nx <= 16 && ctx->coop)  // few right-hand sides: the LU solve's persistent sweep kernels (they invert the blocks
+        return tri_sweeps_dev(L, LT, n, nullptr, B, nx, X, WL, WU, st, 1);  // of L' beside the forward sweep)
       LA_TRY(tri_block_inverses<double>(LT, n, 1, 0, G, WU, 0, st));
-      if (nx <= 16 && ctx->coop)  // few right-hand sides: the LU solve's persistent sweep kernels
-        return tri_sweeps_dev(L, LT, n, nullptr, B, nx, X, WL, WU, st);
       for (int b = 0; b < G; ++b) {  // L Y = B
         const size_t r0 = (size_t)b * CB, nr = (n - r0 < (size_t)CB) ? (n - r0) : (size_t)CB;
         double* Xb = X + r0 * nx;

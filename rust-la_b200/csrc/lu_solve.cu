@@ -25,6 +25,8 @@ namespace la {
 int gemm_f64_tensor(const double* A, size_t lda, const double* B, size_t ldb, double* C, size_t ldc, size_t m, size_t k,
                     size_t n, int mode, cudaStream_t st);  // gemm_f64.cu: TMA/DMMA kernel regardless of size
 int lu_diag_block_inverses(const double* LU, size_t n, double* WL, double* WU, cudaStream_t st);  // lu.cu
+template <typename T>
+int tri_block_inverses(const T* M, size_t n, int mode, int first_block, int nblocks, T* W, int trans_out, cudaStream_t st);  // lu.cu
 namespace {
 
 constexpr int SB = 64;        // diagonal block
@@ -357,6 +359,59 @@ struct SweepCfg {
 };
 typedef LL<double>::word XWord;
 
+// M_g = W_g * T[g][g -+ 1] (FORWARD: the block left of the diagonal block; backward: the block right of it), zero where
+// the triangle has no such block.  With it the solved block of the neighbour enters a CTA's result by ONE product,
+// x_g = W_g (b_g - sum_{others} ...) - M_g x_neighbour: the own-block product W_g (...) no longer waits for the neighbour.
+template <bool FORWARD>
+__global__ void __launch_bounds__(256) sweep_combine_kernel(const double* __restrict__ T, size_t ld, int n,
+                                                             const double* __restrict__ Winv, double* __restrict__ Mout) {
+  __shared__ double Ws[PB][17];   // W_g[:, k0 .. k0+16)
+  __shared__ double Ts[16][PB + 1];  // T block rows k0 .. k0+16
+  const int g = blockIdx.x, G = gridDim.x;
+  const int nb = FORWARD ? g - 1 : g + 1;
+  double* M = Mout + (size_t)g * PB * PB;
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  if (nb < 0 || nb >= G) {
+    for (int i = t; i < PB * PB; i += 256) M[i] = 0.0;
+    return;
+  }
+  const double* W = Winv + (size_t)g * PB * PB;
+  double acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+  for (int k0 = 0; k0 < PB; k0 += 16) {
+    for (int i = t; i < PB * 16; i += 256) {
+      const int r = i >> 4, k = i & 15;
+      Ws[r][k] = W[(size_t)r * PB + k0 + k];
+    }
+    for (int i = t; i < 16 * PB; i += 256) {
+      const int k = i / PB, c = i - k * PB;
+      const int row = g * PB + k0 + k, col = nb * PB + c;
+      Ts[k][c] = (row < n && col < n) ? T[(size_t)row * ld + col] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      double a[8], b[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = Ws[ty * 8 + i][k];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = Ts[k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) M[(size_t)(ty * 8 + i) * PB + tx + 16 * j] = acc[i][j];
+}
+
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                "r"(bytes), "r"(mbar)
@@ -369,6 +424,7 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
                        const double* __restrict__ B, double* __restrict__ X, int nx, int G,
                        XWord* __restrict__ xbuf /* [chains][G][PB * NXC] flagged words */,
                        unsigned tag, const double* __restrict__ Winv /* [G][128][128] inverted diagonal blocks */,
+                       const double* __restrict__ Mcomb /* [G][128][128] W_g * neighbour block, or null: plain last update */,
                        unsigned long long* __restrict__ dbg /* optional [chains * G][8] phase timestamps (ns) of the last step */) {
   using Cfg = SweepCfg<NXC, BULK>;
   constexpr int PHC = Cfg::PHC, PARTS = Cfg::PARTS, NT = Cfg::NT, XLD = Cfg::XLD, BUFS = Cfg::BUFS, WPT = Cfg::WPT;
@@ -392,7 +448,12 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
   // The CTA consumes a sequence of PHC-column parts: PARTS per block of LU (steps 0 .. nsteps-1), then the parts of its own
   // inverted diagonal block.  Part i lives in buffer i % 3 and is requested three parts ahead, so the inverted block is
   // already (almost) in place when the last update finishes -- its load is off the dependent chain.
-  const int nparts = PARTS * (nsteps + 1);
+  // With the precombined neighbour blocks (Mcomb) the sequence is: plain updates for steps 0 .. nsteps-2, the own inverted
+  // block (its product starts as soon as the second-to-last solved block has been applied), then M_g against the LAST
+  // awaited block -- one product between that block's arrival and the publication of this CTA's block.
+  const bool comb = Mcomb != nullptr && nsteps > 0;
+  const int ublocks = comb ? nsteps - 1 : nsteps;       // blocks applied by plain updates
+  const int nparts = PARTS * (ublocks + 1 + (comb ? 1 : 0));
   constexpr int CHUNKS = PHC / 2;  // 16-byte chunks per buffer row
   // Every warp streams ITS OWN 16 rows of each part into a private slice of the buffer (rows 16 warp .. 16 warp + 15) and
   // is the only reader of that slice: completion is a per-thread cp.async wait plus __syncwarp, no block-wide barrier per
@@ -415,12 +476,15 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
   const char* lu_row0 = reinterpret_cast<const char*>(LU + (size_t)(r0 + rr0) * ld + 2 * cc);
   const size_t lu_stride = (size_t)ROWSTEP * ld * sizeof(double);
   const char* w_row0 = reinterpret_cast<const char*>(Winv + (size_t)g * PB * PB + (size_t)rr0 * PB + 2 * cc);
+  const char* m_row0 = reinterpret_cast<const char*>((comb ? Mcomb : Winv) + (size_t)g * PB * PB + (size_t)rr0 * PB + 2 * cc);
   constexpr size_t W_STRIDE = (size_t)ROWSTEP * PB * sizeof(double);
   // BULK: lane q < 16 copies row 16 warp + q of the part (PHC * 8 contiguous bytes); the warp's mbarrier of that buffer
   // counts the bytes.  Every row and column is inside the matrix (n is a multiple of 128 on this path).
   const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(bars + warp * BUFS);
   const char* lu_brow = reinterpret_cast<const char*>(LU + (size_t)(r0 + 16 * warp + (lane & 15)) * ld);
   const char* w_brow = reinterpret_cast<const char*>(Winv + (size_t)g * PB * PB + (size_t)(16 * warp + (lane & 15)) * PB);
+  const char* m_brow = reinterpret_cast<const char*>((comb ? Mcomb : Winv) + (size_t)g * PB * PB +
+                                                     (size_t)(16 * warp + (lane & 15)) * PB);
   const uint32_t brow_dst = (uint32_t)((16 * warp + (lane & 15)) * RS * sizeof(double));
   auto issue_part = [&](int i) {
     if constexpr (BULK) {
@@ -432,8 +496,8 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(16u * PHC * 8u) : "memory");
         __syncwarp();
         if (lane < 16) {
-          const char* src = s < nsteps ? lu_brow + ((size_t)step_block(s) * PB + (size_t)hh * PHC) * sizeof(double)
-                                       : w_brow + (size_t)hh * PHC * sizeof(double);
+          const char* src = s < ublocks ? lu_brow + ((size_t)step_block(s) * PB + (size_t)hh * PHC) * sizeof(double)
+                            : (s == ublocks ? w_brow : m_brow) + (size_t)hh * PHC * sizeof(double);
           bulk_copy_g2s(lbuf_s + (uint32_t)(buf * PB * RS * sizeof(double)) + brow_dst, src, PHC * 8u, bar);
         }
       }
@@ -442,7 +506,7 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
     if (i < nparts) {
       const int s = i / PARTS, hh = i - s * PARTS;
       const uint32_t dbase = lbuf_s + (uint32_t)((i % BUFS) * PB * PHC * sizeof(double));
-      if (s < nsteps) {
+      if (s < ublocks) {
         const int cbase = step_block(s) * PB + hh * PHC;
         const bool col_ok = cbase + 2 * cc < N;  // n is even: a pair of columns is inside or outside as a whole
         const char* src = lu_row0 + (size_t)cbase * sizeof(double);
@@ -453,7 +517,7 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
           src += lu_stride;
         }
       } else {
-        const char* src = w_row0 + (size_t)hh * PHC * sizeof(double);
+        const char* src = (s == ublocks ? w_row0 : m_row0) + (size_t)hh * PHC * sizeof(double);
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
           cp_async16(dbase + dst_off[q], src, 16);
@@ -520,12 +584,13 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
   double res[KS][2][NT][2];
   for (int i = 0; i < nparts; ++i) {
     const int s = i / PARTS, hh = i - s * PARTS;
-    const bool own = s == nsteps;  // the parts of the inverted diagonal block
+    const bool own = s == ublocks;   // the parts of the inverted diagonal block
+    const bool last = s > ublocks;   // (comb) the parts of M_g against the last awaited block
     if (hh == 0) {
       __syncthreads();  // every warp has finished reading the previous block from Xs
       if (!own) {
         // ---- block kb of the solution: poll the producer's flagged words (WPT per thread), store MINUS the values ----
-        const XWord* src = xbuf + (size_t)step_block(s) * Cfg::WORDS;
+        const XWord* src = xbuf + (size_t)step_block(last ? nsteps - 1 : s) * Cfg::WORDS;
         double v[WPT];
         bool ok[WPT];
         {
@@ -550,7 +615,7 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
           const int idx = t + SWEEP_THREADS * u;
           Xs[(size_t)(idx / NXC) * XLD + (idx % NXC)] = -v[u];
         }
-        if (s == nsteps - 1) stamp(0);  // the last awaited block has arrived
+        if (last || (!comb && s == nsteps - 1)) stamp(0);  // the last awaited block has arrived
       } else {
         stamp(1);  // updates done
         // ---- X_g = W_g * (right-hand sides of this block): the same MMA loop on the inverted diagonal block ----
@@ -579,7 +644,7 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
       cp_async_wait<BUFS - 1>();  // this thread's groups are committed in order: all but the two youngest have landed
       __syncwarp();               // ... and so have the other lanes' chunks of this warp's slice of part i
     }
-    if (own) mma_part(i % BUFS, hh, res);
+    if (own || last) mma_part(i % BUFS, hh, res);  // (comb) res = W_g R - M_g x_last: Xs holds MINUS x_last
     else mma_part(i % BUFS, hh, acc);
     __syncwarp();               // the warp is done with its slice of buffer i % 3
     issue_part(i + BUFS);
@@ -636,8 +701,29 @@ __global__ void det_kernel(const T* __restrict__ diag, size_t n, int pospivsign,
 // below and of Umat strictly above the block diagonal are read, the diagonal blocks arriving inverted in WL / WU
 // ([G][128][128]).  Lmat == Umat == packed LU for the LU solve; L and L' for Cholesky.  piv_dev may be null (identity).
 // Caller guarantees: nx <= 16, n even, 16-byte aligned matrices, ceil(n / 128) <= SM count, cooperative launch support.
+namespace {
+struct SweepSide {
+  cudaStream_t s = nullptr;
+  cudaEvent_t e_in = nullptr, e_out = nullptr;
+};
+int sweep_side(int device, SweepSide** out) {
+  static thread_local SweepSide side[64];
+  LA_REQUIRE(device >= 0 && device < 64, "device ordinal out of range");
+  SweepSide& s = side[device];
+  if (!s.s) {
+    LA_CUDA_TRY(cudaStreamCreateWithFlags(&s.s, cudaStreamNonBlocking));
+    LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e_in, cudaEventDisableTiming));
+    LA_CUDA_TRY(cudaEventCreateWithFlags(&s.e_out, cudaEventDisableTiming));
+  }
+  *out = &s;
+  return LA_OK;
+}
+}  // namespace
+
+// wu_mode >= 0: the inverted diagonal blocks of Umat are NOT in wu yet -- they are computed here (tri_block_inverses mode
+// wu_mode) on a side stream together with the U-side neighbour products, under the forward sweep.
 int tri_sweeps_dev(const double* Lmat, const double* Umat, size_t n, const uint64_t* piv_dev, const double* B, size_t nx,
-                   double* X, const double* wl, const double* wu, cudaStream_t st) {
+                   double* X, const double* wl, const double* wu, cudaStream_t st, int wu_mode) {
   const DeviceCtx* ctx;
   LA_TRY(current_device_ctx(&ctx));
   const int G = (int)((n + PB - 1) / PB);
@@ -698,21 +784,63 @@ int tri_sweeps_dev(const double* Lmat, const double* Umat, size_t n, const uint6
     LA_CUDA_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     LA_CUDA_TRY(cudaFuncSetAttribute(kb, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     size_t ldm = n;
+    // precombined neighbour blocks M_g = W_g * T[g][g -+ 1] for both triangles (one launch each; LA_SOLVE_COMBINE=0: off)
+    static const int combine_knob = getenv("LA_SOLVE_COMBINE") ? atoi(getenv("LA_SOLVE_COMBINE")) : 1;
+    const double* mcl = nullptr;
+    const double* mcu = nullptr;
+    SweepSide* side = nullptr;
+    LA_TRY(sweep_side(ctx->device, &side));
+    const bool combine = combine_knob && G > 1;
+    const bool use_side = combine || wu_mode >= 0;
+    double* m1 = nullptr;
+    if (combine) {
+      void* mp = nullptr;
+      LA_TRY(scratch_get(ctx->device, 44, sizeof(double) * 2 * (size_t)G * PB * PB, &mp));
+      double* m0 = (double*)mp;
+      m1 = m0 + (size_t)G * PB * PB;
+      sweep_combine_kernel<true><<<G, 256, 0, st>>>(Lmat, n, (int)n, wl, m0);
+      LA_CUDA_TRY(cudaGetLastError());
+      mcl = m0;
+      mcu = m1;
+    }
+    if (use_side) LA_CUDA_TRY(cudaEventRecord(side->e_in, st));  // everything the U side reads is ready here
+    // U-side preparation: queued AFTER the first forward sweep has been launched, so that it fills the SMs that sweep
+    // leaves free instead of delaying it; needed by the first backward sweep
+    bool side_queued = false;
+    auto queue_side = [&]() -> int {
+      if (!use_side || side_queued) return LA_OK;
+      side_queued = true;
+      LA_CUDA_TRY(cudaStreamWaitEvent(side->s, side->e_in, 0));
+      if (wu_mode >= 0) LA_TRY(tri_block_inverses<double>(Umat, n, wu_mode, 0, G, const_cast<double*>(wu), 0, side->s));
+      if (combine) {
+        sweep_combine_kernel<false><<<G, 256, 0, side->s>>>(Umat, n, (int)n, wu, m1);
+        LA_CUDA_TRY(cudaGetLastError());
+      }
+      LA_CUDA_TRY(cudaEventRecord(side->e_out, side->s));
+      return LA_OK;
+    };
+    auto join_side = [&]() -> int {  // before the first backward sweep
+      LA_TRY(queue_side());
+      if (use_side) LA_CUDA_TRY(cudaStreamWaitEvent(st, side->e_out, 0));
+      return LA_OK;
+    };
     auto sweep = [&](bool fwd, const double* M, size_t rows, const uint64_t* pv, const double* rhs, double* out,
-                     const double* winv) -> int {
+                     const double* winv, const double* mcomb) -> int {
       call_tag += 1;
       if (call_tag == 0) call_tag = 1;
       unsigned tg = call_tag;
       XWord* xw = fwd ? xb0 : xb1;
       int gp = (int)((rows + PB - 1) / PB);
       unsigned long long* dg = trace ? (fwd ? d0 : d1) : nullptr;
-      void* args[] = {&M, &ldm, &rows, &pv, &rhs, &out, &nxi, &gp, &xw, &tg, &winv, &dg};
+      void* args[] = {&M, &ldm, &rows, &pv, &rhs, &out, &nxi, &gp, &xw, &tg, &winv, &mcomb, &dg};
       LA_CUDA_TRY(cudaLaunchCooperativeKernel(fwd ? kf : kb, dim3(gp * chains), dim3(SWEEP_THREADS), args, smem_bytes, st));
       return LA_OK;
     };
     if (G <= max_g) {
-      LA_TRY(sweep(true, Lmat, n, piv_dev, B, X, wl));
-      LA_TRY(sweep(false, Umat, n, piv_dev, B, X, wu));
+      LA_TRY(sweep(true, Lmat, n, piv_dev, B, X, wl, mcl));
+      LA_TRY(queue_side());
+      LA_TRY(join_side());
+      LA_TRY(sweep(false, Umat, n, piv_dev, B, X, wu, mcu));
       if (trace) {  // chain 0 only: phase timestamps of every CTA's last step
         std::vector<unsigned long long> hbuf(32 * (size_t)G);
         LA_CUDA_TRY(cudaStreamSynchronize(st));
@@ -722,9 +850,10 @@ int tri_sweeps_dev(const double* Lmat, const double* Umat, size_t n, const uint6
           const unsigned long long t0 = ph == 0 ? hb[3] : hb[(size_t)(G - 1) * 8 + 3];
           for (int g = 0; g < G; g += (G > 32 ? G / 32 : 1)) {
             const unsigned long long* e = hb + (size_t)g * 8;
-            fprintf(stderr, "sweep2 %s cta %3d: arrived %8.2f us | +updates %6.2f | +own ready %5.2f | +product/publish %6.2f\n",
-                    ph == 0 ? "fwd" : "bwd", g, e[0] ? (double)(e[0] - t0) * 1e-3 : 0.0,
-                    e[0] ? (double)(e[1] - e[0]) * 1e-3 : 0.0, (double)(e[2] - e[1]) * 1e-3, (double)(e[3] - e[2]) * 1e-3);
+            auto us = [&](int k) { return e[k] ? ((double)e[k] - (double)t0) * 1e-3 : 0.0; };
+            fprintf(stderr, "sweep2 %s cta %3d: last block arrived %8.2f us | own product started %8.2f | published %8.2f "
+                            "(arrival -> publication %5.2f us)\n",
+                    ph == 0 ? "fwd" : "bwd", g, us(0), us(2), us(3), e[0] ? us(3) - us(0) : 0.0);
           }
         }
       }
@@ -742,19 +871,24 @@ int tri_sweeps_dev(const double* Lmat, const double* Umat, size_t n, const uint6
     const size_t part = (size_t)max_g * PB;
     for (size_t p0 = 0; p0 < n; p0 += part) {  // forward
       const size_t rows = n - p0 < part ? n - p0 : part, p1 = p0 + rows;
-      LA_TRY(sweep(true, Lmat + p0 * n + p0, rows, nullptr, X + p0 * nx, X + p0 * nx, wl + (p0 / PB) * PB * PB));
+      LA_TRY(sweep(true, Lmat + p0 * n + p0, rows, nullptr, X + p0 * nx, X + p0 * nx, wl + (p0 / PB) * PB * PB,
+                   mcl ? mcl + (p0 / PB) * PB * PB : nullptr));
+      LA_TRY(queue_side());
       if (p1 < n)
         LA_TRY(gemm_dev<double>(Lmat + p1 * n + p0, n, X + p0 * nx, nx, X + p1 * nx, nx, n - p1, rows, nx, LA_GEMM_SUB, st));
     }
     const size_t nparts = (n + part - 1) / part;
+    LA_TRY(join_side());
     for (size_t ip = nparts; ip-- > 0;) {  // backward
       const size_t p0 = ip * part, rows = n - p0 < part ? n - p0 : part;
-      LA_TRY(sweep(false, Umat + p0 * n + p0, rows, nullptr, X + p0 * nx, X + p0 * nx, wu + (p0 / PB) * PB * PB));
+      LA_TRY(sweep(false, Umat + p0 * n + p0, rows, nullptr, X + p0 * nx, X + p0 * nx, wu + (p0 / PB) * PB * PB,
+                   mcu ? mcu + (p0 / PB) * PB * PB : nullptr));
       if (p0 > 0) LA_TRY(gemm_dev<double>(Umat + p0, n, X + p0 * nx, nx, X, nx, p0, rows, nx, LA_GEMM_SUB, st));
     }
     return LA_OK;
   }
   LA_REQUIRE(G <= ctx->sm_count, "la_lu_solve: the first-generation sweep kernel needs ceil(n / 128) <= SM count");
+  if (wu_mode >= 0) LA_TRY(tri_block_inverses<double>(Umat, n, wu_mode, 0, G, const_cast<double*>(wu), 0, st));
   void* a0[] = {&lu_p, &nn, &piv_dev, &b_p, &x_p, &nxi, &f0, &wl, &d0};
   void* a1[] = {&uu_p, &nn, &piv_dev, &b_p, &x_p, &nxi, &f1, &wu, &d1};
   LA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)solve_sweep_kernel<true>, dim3(G), dim3(SWEEP_THREADS), a0,
@@ -798,8 +932,8 @@ int lu_solve_dev(const T* LU, size_t n, const uint64_t* piv_dev, const T* B, siz
       LA_TRY(scratch_get(ctx->device, 15, sizeof(double) * 2 * (size_t)G * PB * PB, &wbuf));
       double* wl = (double*)wbuf;
       double* wu = wl + (size_t)G * PB * PB;
-      LA_TRY(lu_diag_block_inverses(LU, n, wl, wu, st));
-      LA_TRY(tri_sweeps_dev(LU, LU, n, piv_dev, B, nx, X, wl, wu, st));
+      LA_TRY(tri_block_inverses<double>(LU, n, 0, 0, G, wl, 0, st));  // inv(L_bb); inv(U_bb) is made under the forward sweep
+      LA_TRY(tri_sweeps_dev(LU, LU, n, piv_dev, B, nx, X, wl, wu, st, 1));
       return LA_OK;
     }
   }
