@@ -347,7 +347,8 @@ struct SweepCfg {
   static constexpr int BAR_BYTES = BULK ? 256 : 0;     // 8 warps x 3 buffers mbarriers
   static constexpr int PARTS = PB / PHC;               // buffers per 128-column block
   static constexpr int NT = NXC / 8;                   // 8-column MMA tiles
-  static constexpr int XLD = NXC == 16 ? 24 : 8;       // row stride of the X block: a fragment load covers all banks twice
+  // row stride of the X block: the four k-rows x 32 bytes a half warp reads must tile a 128-byte bank period (96 / 160 bytes)
+  static constexpr int XLD = NXC == 16 ? 20 : 12;
   static constexpr int BUFS = 3;
   static constexpr int WORDS = PB * NXC;               // flagged words per solved block
   static constexpr int WPT = WORDS / SWEEP_THREADS;    // ... per thread
@@ -470,7 +471,7 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     const int rr = rr0 + q * ROWSTEP;
-    dst_off[q] = (uint32_t)((rr * PHC + ((cc ^ (rr & 7)) << 1)) * sizeof(double));
+    dst_off[q] = (uint32_t)((rr * PHC + ((cc ^ ((rr & 3) << 1)) << 1)) * sizeof(double));
     if (r0 + rr < N) row_ok |= 1u << q;
   }
   const char* lu_row0 = reinterpret_cast<const char*>(LU + (size_t)(r0 + rr0) * ld + 2 * cc);
@@ -549,7 +550,10 @@ solve_sweep_mma_kernel(const double* __restrict__ LU, size_t ld, size_t n, const
     const int row_a0 = 16 * warp + gid;
     const double* La0 = Lbuf + (size_t)(buf * PB + row_a0) * RS;
     const double* La1 = La0 + 8 * RS;
-    const int sw = row_a0 & 7;  // == (row_a0 + 8) & 7
+    // 64-bit shared loads are served per HALF warp (gid 0..3 / 4..7, all tig): its four rows x two 16-byte chunks must land
+    // in eight different chunk positions of a 128-byte bank period -> chunk index XOR 2 * (row & 3) (XOR with row & 7 made
+    // rows r and r ^ 1 collide: ncu counted 4 wavefronts per fragment load instead of 2)
+    const int sw = (row_a0 & 3) << 1;  // == ((row_a0 + 8) & 3) << 1
     const double* Xb = Xs + (size_t)(hh * PHC + tig) * XLD + gid;
 #pragma unroll
     for (int ks = 0; ks < PHC / 4; ++ks) {
