@@ -162,6 +162,28 @@ LA_API int la_lu_factor_f32_host(const float* A, float* LU_out, size_t m, size_t
 LA_API int la_lu_factor_f64_dev(double* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, void* cuda_stream);
 LA_API int la_lu_factor_f32_dev(float* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, void* cuda_stream);
 
+/* ---- LU of one n x n fp64 matrix across several GPUs of one node, driven by one host thread (SURVEY.md 8(f) rank 4;
+ * same result contract as la_lu_factor_f64: `LUDecomposition::new`, src/decomp/lu.rs:104-168).  128-column blocks are dealt
+ * round-robin to the devices; the panel owner's factored block column travels to every device by peer copy; streams,
+ * events and copies only -- no collective library, no host round trip.  A device may be listed more than once (its
+ * entries then share it: the 1-GPU test configuration).  Contexts are not thread-safe; one factorisation at a time.
+ *   create -> upload (or fill_hash: element (i, j) = hash(seed, i * n + j), the bench / test generator) -> factor (queues
+ *   the work and returns) -> download (waits; any output may be NULL) -> ... -> destroy.
+ * la_lu_mg_last_ms: device time of the last factorisation (events on the first device, which waits for all others). */
+typedef struct la_lu_mg la_lu_mg;
+LA_API int la_lu_mg_create(int ngpus, const int* devices, size_t n, la_lu_mg** out);
+LA_API int la_lu_mg_destroy(la_lu_mg* ctx);
+LA_API int la_lu_mg_devices(const la_lu_mg* ctx, int* ndev_out); /* devices in use: min(ngpus, number of block columns) */
+LA_API int la_lu_mg_upload_f64(la_lu_mg* ctx, const double* A /* host, row-major n x n */);
+LA_API int la_lu_mg_fill_hash_f64(la_lu_mg* ctx, uint64_t seed);
+LA_API int la_lu_mg_factor_f64(la_lu_mg* ctx);
+LA_API int la_lu_mg_sync(la_lu_mg* ctx);
+LA_API int la_lu_mg_download_f64(la_lu_mg* ctx, double* LU_out, uint64_t* piv_out, int* pospivsign_out);
+LA_API int la_lu_mg_last_ms(la_lu_mg* ctx, float* ms_out);
+/* one call from host memory (create + upload + factor + download + destroy) */
+LA_API int la_lu_factor_f64_mg(int ngpus, const int* devices, const double* A, double* LU_out, size_t n, uint64_t* piv_out,
+                               int* pospivsign_out);
+
 /* `is_non_singular` (src/decomp/lu.rs:174-182): *out = 0 iff some LU[j*n+j] == 0 exactly, j < n. */
 LA_API int la_lu_is_nonsingular_f64(const la_buf* LU, size_t n, int* out);
 LA_API int la_lu_is_nonsingular_f32(const la_buf* LU, size_t n, int* out);

@@ -25,6 +25,7 @@
 #include <limits.h>
 #include <stdlib.h>
 
+#include <string>
 #include <type_traits>
 #include <vector>
 #include <stdio.h>
@@ -555,7 +556,7 @@ lu_panel_kernel(T* __restrict__ A, size_t ld, int m, int j0, int jb, int rows_pe
 template <typename T>
 __global__ void __launch_bounds__(2 * MAX_NB)
 lu_perm_kernel(void* ws_base, int G, int parity, int j0, int jb, uint64_t* __restrict__ piv, int* __restrict__ sign,
-               int ipiv_off, int update_piv) {
+               int ipiv_off, int update_piv, const int* __restrict__ ipiv_src /* null: the workspace header's */) {
   // One thread per position that can change: the jb top rows and the (distinct) pivot rows below them.  The content
   // that ends up at position q is the original row reached by tracing q BACKWARDS through the jb transpositions.
   __shared__ int ipiv_s[MAX_NB];
@@ -564,7 +565,7 @@ lu_perm_kernel(void* ws_base, int G, int parity, int j0, int jb, uint64_t* __res
   const WsView<T> ws = ws_view<T>(ws_base, G);
   MoveList* ml = &ws.hdr->moves[parity];
   const int tid = threadIdx.x;
-  if (tid < jb) ipiv_s[tid] = ws.hdr->ipiv[ipiv_off + tid];
+  if (tid < jb) ipiv_s[tid] = ipiv_src ? ipiv_src[tid] : ws.hdr->ipiv[ipiv_off + tid];
   if (tid == 0) {
     nm = 0;
     flips = 0;
@@ -814,7 +815,8 @@ constexpr int HEAD_COLS = 16;  // columns per CTA (8 warps x 2)
 constexpr int HEAD_LD = MAX_NB + 1;
 template <typename T>
 __global__ void __launch_bounds__(256)
-lu_head_kernel(T* __restrict__ A, size_t ld, int j0, int jb, int col0, int col1, const void* ws_base, int G, int parity) {
+lu_head_kernel(T* __restrict__ A, size_t ld, int j0, int jb, int col0, int col1, const void* ws_base, int G, int parity,
+               const T* __restrict__ L11 /* the panel's diagonal block (the multi-device driver keeps a copy) */, size_t ldl) {
   extern __shared__ __align__(16) unsigned char head_smem[];
   T(*LT)[HEAD_LD] = reinterpret_cast<T(*)[HEAD_LD]>(head_smem);                  // [MAX_NB]: LT[k][i] = L11[i][k]
   T(*X)[HEAD_COLS + 1] = reinterpret_cast<T(*)[HEAD_COLS + 1]>(LT + MAX_NB);     // [MAX_NB]: top jb rows of the strip
@@ -852,7 +854,7 @@ lu_head_kernel(T* __restrict__ A, size_t ld, int j0, int jb, int col0, int col1,
   // L11 (strictly lower part), transposed so that step k reads one contiguous shared-memory row
   for (int idx = tid; idx < MAX_NB * MAX_NB; idx += 256) {
     const int i = idx / MAX_NB, k = idx - i * MAX_NB;
-    LT[k][i] = (i < jb && k < i) ? __ldcg(&A[(size_t)(j0 + i) * ld + j0 + k]) : (T)0;
+    LT[k][i] = (i < jb && k < i) ? __ldcg(&L11[(size_t)i * ldl + k]) : (T)0;
   }
   __syncthreads();
   for (int i = ty; i < no; i += 256 / HEAD_COLS)
@@ -913,6 +915,39 @@ struct LuSide {
   cudaStream_t sp = nullptr, sw = nullptr;
   cudaEvent_t e_in = nullptr, e_head = nullptr, e_bulk = nullptr, e_panel = nullptr, e_w = nullptr, e_u12 = nullptr;
 };
+// Rows per panel CTA.  Fewer, fuller CTAs leave more SMs wholly to the bulk GEMMs (a panel CTA takes half the register
+// file, so a GEMM runs at half occupancy next to it) and the in-panel look-ahead hides their longer update; near the end
+// the bulk is negligible and many small CTAs give the shortest column time.
+struct PanelShape {
+  int rpc, G;
+  size_t smem;
+};
+template <typename T>
+PanelShape panel_shape(int R, int jb, int sms, bool exact) {
+  static const int rpc_min = getenv("LA_LU_RPC_MIN") ? atoi(getenv("LA_LU_RPC_MIN")) : 200;  // tuning knobs
+  static const int rpc_div = getenv("LA_LU_RPC_DIV") ? atoi(getenv("LA_LU_RPC_DIV")) : 64;
+  int rpc = (R + sms - 1) / sms;
+  int want = R / rpc_div;
+  int rpc_cap = rpc_min;
+  if (jb <= MAX_NB / 2 && !exact) {  // a 64-wide half panel holds twice the rows in the same shared memory
+    const int fit = (int)(PANEL_SMEM_BUDGET / ((size_t)(jb | 1) * sizeof(T))) / 8 * 8;
+    rpc_cap = 2 * rpc_min < fit ? 2 * rpc_min : fit;
+    want = 2 * want;
+  }
+  if (want > rpc_cap) want = rpc_cap;
+  // never more rows than the shared-memory budget holds (the bit-exact panel keeps a second array of deferred sums:
+  // a tall single-panel matrix such as 8000 x 128 would otherwise ask for 125 rows x 129 x 16 B = 258 KB)
+  const int fit_rows = (int)(PANEL_SMEM_BUDGET / ((size_t)(jb | 1) * sizeof(T) * (exact ? 2 : 1)));
+  if (want > fit_rows) want = fit_rows;
+  if (want < 8) want = 8;  // at least one row per warp
+  if (rpc < want) rpc = want;
+  PanelShape ps;
+  ps.rpc = rpc;
+  ps.G = (R + rpc - 1) / rpc;
+  ps.smem = (size_t)rpc * (jb | 1) * sizeof(T) * (exact ? 2 : 1);
+  return ps;
+}
+
 int lu_side(int device, LuSide** out) {
   static thread_local LuSide side[64];
   LA_REQUIRE(device >= 0 && device < 64, "device ordinal out of range");
@@ -995,29 +1030,9 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
   int G_cur = 1;
   // panel factorisation of columns [j0, j0+jb) on stream s (ipiv lands in the workspace header)
   auto launch_panel = [&](int j0, int jb, cudaStream_t s, int ipiv_off = 0) -> int {
-    const int R = M - j0;
-    // Rows per CTA.  Fewer, fuller CTAs leave more SMs wholly to the bulk GEMMs (a panel CTA takes half the register
-    // file, so a GEMM runs at half occupancy next to it) and the in-panel look-ahead hides their longer update; near
-    // the end the bulk is negligible and many small CTAs give the shortest column time.
-    static const int rpc_min = getenv("LA_LU_RPC_MIN") ? atoi(getenv("LA_LU_RPC_MIN")) : 200;  // tuning knobs
-    static const int rpc_div = getenv("LA_LU_RPC_DIV") ? atoi(getenv("LA_LU_RPC_DIV")) : 64;
-    int rpc = (R + sms - 1) / sms;
-    int want = R / rpc_div;
-    int rpc_cap = rpc_min;
-    if (jb <= MAX_NB / 2 && !exact) {  // a 64-wide half panel holds twice the rows in the same shared memory
-      const int fit = (int)(PANEL_SMEM_BUDGET / ((size_t)(jb | 1) * sizeof(T))) / 8 * 8;
-      rpc_cap = 2 * rpc_min < fit ? 2 * rpc_min : fit;
-      want = 2 * want;
-    }
-    if (want > rpc_cap) want = rpc_cap;
-    // never more rows than the shared-memory budget holds (the bit-exact panel keeps a second array of deferred sums:
-    // a tall single-panel matrix such as 8000 x 128 would otherwise ask for 125 rows x 129 x 16 B = 258 KB)
-    const int fit_rows = (int)(PANEL_SMEM_BUDGET / ((size_t)(jb | 1) * sizeof(T) * (exact ? 2 : 1)));
-    if (want > fit_rows) want = fit_rows;
-    if (want < 8) want = 8;  // at least one row per warp
-    if (rpc < want) rpc = want;
-    const int G = (R + rpc - 1) / rpc;
-    const size_t smem = (size_t)rpc * (jb | 1) * sizeof(T) * (exact ? 2 : 1);
+    const PanelShape ps = panel_shape<T>(M - j0, jb, sms, exact);
+    const int rpc = ps.rpc, G = ps.G;
+    const size_t smem = ps.smem;
     T* a = LU;
     size_t ld = n;
     int mm = M, jj0 = j0, jjb = jb, rr = rpc;
@@ -1032,7 +1047,8 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
   };
   // net permutation + piv / sign bookkeeping of the panel just factored
   auto launch_perm = [&](int j0, int jb, int parity, cudaStream_t s, int ipiv_off = 0, int update_piv = 1) -> int {
-    lu_perm_kernel<T><<<1, 2 * MAX_NB, 0, s>>>(ws_base, G_cur, parity, j0, jb, piv_dev, sign_dev, ipiv_off, update_piv);
+    lu_perm_kernel<T><<<1, 2 * MAX_NB, 0, s>>>(ws_base, G_cur, parity, j0, jb, piv_dev, sign_dev, ipiv_off, update_piv,
+                                               nullptr);
     LA_CUDA_TRY(cudaGetLastError());
     return LA_OK;
   };
@@ -1163,7 +1179,7 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
       mark(sp);  // [1] perm done and bulk(i-1) done
       if (has_next) {
         lu_head_kernel<T><<<(nb2 + HEAD_COLS - 1) / HEAD_COLS, 256, HEAD_SMEM, sp>>>(LU, n, j0, jb, c1, c2, ws_base, G_cur,
-                                                                                    parity);
+                                                                                    parity, LU + (size_t)j0 * n + j0, n);
         LA_CUDA_TRY(cudaGetLastError());
         mark(sp);  // [2] next panel's columns interchanged, U12 solved
         LA_TRY(trailing(c1, c2, sp));
@@ -1177,7 +1193,8 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
           const int h = MAX_NB / 2, cm = c1 + h;
           LA_TRY(launch_panel(c1, h, sp, 0));
           LA_TRY(launch_perm(c1, h, 2, sp, 0, 0));
-          lu_head_kernel<T><<<(h + HEAD_COLS - 1) / HEAD_COLS, 256, HEAD_SMEM, sp>>>(LU, n, c1, h, cm, c2, ws_base, G_cur, 2);
+          lu_head_kernel<T><<<(h + HEAD_COLS - 1) / HEAD_COLS, 256, HEAD_SMEM, sp>>>(LU, n, c1, h, cm, c2, ws_base, G_cur, 2,
+                                                                                   LU + (size_t)c1 * n + c1, n);
           LA_CUDA_TRY(cudaGetLastError());
           if (cm < M)
             LA_TRY(gemm_f64_tensor(A + (size_t)cm * ld + c1, ld, A + (size_t)c1 * ld + cm, ld, A + (size_t)cm * ld + cm, ld,
@@ -1276,7 +1293,7 @@ int lu_factor_dev(T* LU, size_t m, size_t n, uint64_t* piv_dev, int* sign_dev, c
       auto head_and_update = [&](int cb, int ce, cudaStream_t s) -> int {  // columns [cb, ce)
         if (ce <= cb) return LA_OK;
         lu_head_kernel<T><<<(ce - cb + HEAD_COLS - 1) / HEAD_COLS, 256, HEAD_SMEM, s>>>(LU, n, j0, jb, cb, ce, ws_base, G_cur,
-                                                                                    parity);
+                                                                                    parity, LU + (size_t)j0 * n + j0, n);
         LA_CUDA_TRY(cudaGetLastError());
         if (c1 < M)
           LA_TRY(gemm_dev<T>(LU + (size_t)c1 * ld + j0, ld, LU + (size_t)j0 * ld + cb, ld, LU + (size_t)c1 * ld + cb, ld,
@@ -1334,4 +1351,470 @@ int lu_diag_block_inverses(const double* LU, size_t n, double* WL, double* WU, c
 template int lu_factor_dev<double>(double*, size_t, size_t, uint64_t*, int*, cudaStream_t);
 template int lu_factor_dev<float>(float*, size_t, size_t, uint64_t*, int*, cudaStream_t);
 
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-device LU: LUDecomposition::new (lu.rs:104-168) of one n x n fp64 matrix across several
+// GPUs driven by one host thread.
+//
+// Layout: 128-column blocks dealt round-robin (block b lives on device b mod G, all n rows of it), so every device keeps
+// a share of the trailing matrix until the end.  Panel k is factored by its owner with the single-device panel kernel;
+// the factored block column (L11 over L21), and its 128 pivot rows, are copied into a ring slot on every device (peer
+// copies queued on the owner's chain stream, the next owner first), after which each device is on its own: it folds the
+// pivots into its own copy of `piv`, interchanges the rows of its columns, inverts L11 on a side stream, forms its U12
+// rows (W * A12, DMMA GEMM) and updates its part of the trailing matrix (DMMA GEMM, L21 from the ring slot).  No
+// collective and no host round trip: streams, events and peer copies only.
+// Look-ahead as on one device: the owner of panel k+1 brings that panel's columns up to date first (substitution head +
+// a 128-column GEMM on its high-priority chain stream) and factors it while every device's bulk update of step k runs.
+// The chain (panel -> copy -> head -> update -> panel) hops from device to device and bounds the factorisation from
+// below at ~0.6 ms per panel; the bulk work is what the devices share.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int MGLU_RING = 4;  // panels in flight: ring slots of L / W / pivots, move lists (PanelWs::moves has four)
+constexpr int MGLU_MAX_DEV = 16;
+
+struct LuMgDev {
+  int device = -1, sms = 0;
+  int ncols = 0;   // local columns
+  size_t ld = 0;   // local leading dimension (even: TMA rows are 16-byte aligned)
+  double* A = nullptr;
+  double* Lring = nullptr;  // [RING][n][128]
+  double* Wring = nullptr;  // [RING][128][128]
+  int* ipiv_ring = nullptr; // [RING][128]
+  void* ws = nullptr;       // panel workspace (exchange area + move lists)
+  uint64_t* piv = nullptr;  // every device keeps the whole permutation
+  int* sign = nullptr;
+  cudaStream_t sp = nullptr, sw = nullptr, st = nullptr;  // chain (high priority), side, bulk
+  cudaEvent_t e_arr[MGLU_MAX_DEV][MGLU_RING] = {};  // as owner: slot s has landed on device q
+  cudaEvent_t e_sent[MGLU_RING] = {};               // as owner: every copy of slot s is done
+  cudaEvent_t e_perm[MGLU_RING] = {}, e_w[MGLU_RING] = {}, e_bulk[MGLU_RING] = {};
+  cudaEvent_t e_in = nullptr, e_tail = nullptr;
+  unsigned epoch = 0;
+};
+
+struct DevSwitch {  // restores the caller's current device
+  int prev = -1;
+  DevSwitch() { cudaGetDevice(&prev); }
+  ~DevSwitch() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+__global__ void lu_mg_fill_kernel(double* __restrict__ A, size_t ld, int n, int ncols, int d, int G, uint64_t seed) {
+  const size_t total = (size_t)n * ncols;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = e / ncols;
+    const int lc = (int)(e - r * ncols);
+    const size_t gc = ((size_t)(lc / MAX_NB) * G + d) * MAX_NB + lc % MAX_NB;
+    A[r * ld + lc] = (double)(hash64(seed, r * (size_t)n + gc) >> 11) * 0x1.0p-53;
+  }
+}
+}  // namespace
 }  // namespace la
+
+struct la_lu_mg {
+  int ndev = 0;
+  size_t n = 0;
+  int nblk = 0;
+  la::LuMgDev dev[la::MGLU_MAX_DEV];
+  cudaEvent_t t0 = nullptr, t1 = nullptr;  // on dev[0]: the factorisation as the devices saw it
+  float last_ms = -1.f;
+};
+
+namespace la {
+namespace {
+
+inline int mglu_width(const la_lu_mg* c, int b) {
+  const size_t left = c->n - (size_t)b * MAX_NB;
+  return left < (size_t)MAX_NB ? (int)left : MAX_NB;
+}
+// first local column (on device q of G) that lies right of block k
+inline int mglu_cols_through(const la_lu_mg* c, int k, int q) {
+  const int blocks = k >= q ? (k - q) / c->ndev + 1 : 0;
+  const int cols = blocks * MAX_NB;
+  return cols < c->dev[q].ncols ? cols : c->dev[q].ncols;
+}
+
+int lu_mg_destroy(la_lu_mg* c) {
+  if (!c) return LA_OK;
+  DevSwitch keep;
+  for (int q = 0; q < c->ndev; ++q) {
+    LuMgDev& D = c->dev[q];
+    if (D.device < 0 || cudaSetDevice(D.device) != cudaSuccess) continue;
+    if (D.st) cudaStreamSynchronize(D.st);
+    if (D.sp) cudaStreamSynchronize(D.sp);
+    if (D.sw) cudaStreamSynchronize(D.sw);
+    for (int s = 0; s < MGLU_RING; ++s) {
+      for (int r = 0; r < MGLU_MAX_DEV; ++r)
+        if (D.e_arr[r][s]) cudaEventDestroy(D.e_arr[r][s]);
+      if (D.e_sent[s]) cudaEventDestroy(D.e_sent[s]);
+      if (D.e_perm[s]) cudaEventDestroy(D.e_perm[s]);
+      if (D.e_w[s]) cudaEventDestroy(D.e_w[s]);
+      if (D.e_bulk[s]) cudaEventDestroy(D.e_bulk[s]);
+    }
+    if (D.e_in) cudaEventDestroy(D.e_in);
+    if (D.e_tail) cudaEventDestroy(D.e_tail);
+    if (q == 0) {
+      if (c->t0) cudaEventDestroy(c->t0);
+      if (c->t1) cudaEventDestroy(c->t1);
+    }
+    if (D.sp) cudaStreamDestroy(D.sp);
+    if (D.sw) cudaStreamDestroy(D.sw);
+    if (D.st) cudaStreamDestroy(D.st);
+    cudaFree(D.A);
+    cudaFree(D.Lring);
+    cudaFree(D.Wring);
+    cudaFree(D.ipiv_ring);
+    cudaFree(D.ws);
+    cudaFree(D.piv);
+    cudaFree(D.sign);
+  }
+  cudaGetLastError();
+  delete c;
+  return LA_OK;
+}
+
+int lu_mg_create_impl(la_lu_mg* c, int ngpus, const int* devices, size_t n) {
+  c->n = n;
+  c->nblk = (int)((n + MAX_NB - 1) / MAX_NB);
+  c->ndev = ngpus < c->nblk ? ngpus : c->nblk;  // a device without a block column has nothing to do
+  const int G = c->ndev;
+  for (int q = 0; q < G; ++q) {
+    LuMgDev& D = c->dev[q];
+    const DeviceCtx* ctx;
+    LA_TRY(device_ctx(devices[q], &ctx));
+    if (!ctx->coop) return fail(LA_ERR_UNSUPPORTED, "la_lu_mg: device %d lacks cooperative launch", devices[q]);
+    D.device = devices[q];
+    D.sms = ctx->sm_count;
+    const int rpc = (int)((n + D.sms - 1) / D.sms);
+    if ((size_t)rpc * (MAX_NB | 1) * sizeof(double) > PANEL_SMEM_BUDGET)
+      return fail(LA_ERR_UNSUPPORTED, "la_lu_mg: %zu rows exceed the shared-memory panel capacity of %d SMs", n, D.sms);
+    LA_CUDA_TRY(cudaSetDevice(D.device));
+    for (int r = 0; r < G; ++r) {  // peer copies go straight over NVLink where the devices can reach each other
+      if (devices[r] == D.device) continue;
+      int can = 0;
+      LA_CUDA_TRY(cudaDeviceCanAccessPeer(&can, D.device, devices[r]));
+      if (can) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(devices[r], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          return fail(LA_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", devices[r], cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+    }
+    int nloc = 0;
+    for (int b = q; b < c->nblk; b += G) nloc += mglu_width(c, b);
+    D.ncols = nloc;
+    D.ld = (size_t)((nloc + 1) / 2 * 2);
+    LA_CUDA_TRY(cudaMalloc(&D.A, sizeof(double) * n * D.ld));
+    LA_CUDA_TRY(cudaMalloc(&D.Lring, sizeof(double) * MGLU_RING * n * MAX_NB));
+    LA_CUDA_TRY(cudaMalloc(&D.Wring, sizeof(double) * MGLU_RING * MAX_NB * MAX_NB));
+    LA_CUDA_TRY(cudaMalloc(&D.ipiv_ring, sizeof(int) * MGLU_RING * MAX_NB));
+    LA_CUDA_TRY(cudaMalloc(&D.ws, ws_bytes<double>(D.sms)));
+    LA_CUDA_TRY(cudaMalloc(&D.piv, sizeof(uint64_t) * n));
+    LA_CUDA_TRY(cudaMalloc(&D.sign, sizeof(int)));
+    int lo = 0, hi = 0;
+    LA_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    LA_CUDA_TRY(cudaStreamCreateWithPriority(&D.sp, cudaStreamNonBlocking, hi));
+    LA_CUDA_TRY(cudaStreamCreateWithPriority(&D.sw, cudaStreamNonBlocking, hi));
+    LA_CUDA_TRY(cudaStreamCreateWithPriority(&D.st, cudaStreamNonBlocking, lo));
+    for (int s = 0; s < MGLU_RING; ++s) {
+      for (int r = 0; r < G; ++r) LA_CUDA_TRY(cudaEventCreateWithFlags(&D.e_arr[r][s], cudaEventDisableTiming));
+      LA_CUDA_TRY(cudaEventCreateWithFlags(&D.e_sent[s], cudaEventDisableTiming));
+      LA_CUDA_TRY(cudaEventCreateWithFlags(&D.e_perm[s], cudaEventDisableTiming));
+      LA_CUDA_TRY(cudaEventCreateWithFlags(&D.e_w[s], cudaEventDisableTiming));
+      LA_CUDA_TRY(cudaEventCreateWithFlags(&D.e_bulk[s], cudaEventDisableTiming));
+    }
+    LA_CUDA_TRY(cudaEventCreateWithFlags(&D.e_in, cudaEventDisableTiming));
+    LA_CUDA_TRY(cudaEventCreateWithFlags(&D.e_tail, cudaEventDisableTiming));
+    if (q == 0) {
+      LA_CUDA_TRY(cudaEventCreate(&c->t0));
+      LA_CUDA_TRY(cudaEventCreate(&c->t1));
+    }
+  }
+  return LA_OK;
+}
+
+int lu_mg_create(int ngpus, const int* devices, size_t n, la_lu_mg** out) {
+  LA_REQUIRE(devices && out, "la_lu_mg_create: null pointer");
+  LA_REQUIRE(ngpus >= 1 && ngpus <= MGLU_MAX_DEV, "la_lu_mg_create: bad device count %d", ngpus);
+  LA_REQUIRE(n > 0 && n < (1u << 30), "la_lu_mg_create: bad order %zu", n);
+  *out = nullptr;
+  DevSwitch keep;
+  la_lu_mg* c = new la_lu_mg();
+  const int s = lu_mg_create_impl(c, ngpus, devices, n);
+  if (s != LA_OK) {
+    const std::string why = error_text();
+    lu_mg_destroy(c);
+    set_error("%s", why.c_str());
+    return s;
+  }
+  *out = c;
+  return LA_OK;
+}
+
+// host matrix (row-major n x n) <-> the devices' block columns
+int lu_mg_upload(la_lu_mg* c, const double* A) {
+  LA_REQUIRE(c && A, "la_lu_mg_upload: null pointer");
+  DevSwitch keep;
+  const size_t n = c->n;
+  for (int b = 0; b < c->nblk; ++b) {
+    LuMgDev& D = c->dev[b % c->ndev];
+    LA_CUDA_TRY(cudaSetDevice(D.device));
+    LA_CUDA_TRY(cudaMemcpy2DAsync(D.A + (size_t)(b / c->ndev) * MAX_NB, D.ld * sizeof(double), A + (size_t)b * MAX_NB,
+                                  n * sizeof(double), (size_t)mglu_width(c, b) * sizeof(double), n, cudaMemcpyHostToDevice,
+                                  D.st));
+  }
+  for (int q = 0; q < c->ndev; ++q) {
+    LA_CUDA_TRY(cudaSetDevice(c->dev[q].device));
+    LA_CUDA_TRY(cudaStreamSynchronize(c->dev[q].st));
+  }
+  return LA_OK;
+}
+
+int lu_mg_fill_hash(la_lu_mg* c, uint64_t seed) {
+  LA_REQUIRE(c, "la_lu_mg_fill_hash: null context");
+  DevSwitch keep;
+  for (int q = 0; q < c->ndev; ++q) {
+    LuMgDev& D = c->dev[q];
+    LA_CUDA_TRY(cudaSetDevice(D.device));
+    lu_mg_fill_kernel<<<D.sms * 16, 256, 0, D.st>>>(D.A, D.ld, (int)c->n, D.ncols, q, c->ndev, seed);
+    LA_CUDA_TRY(cudaGetLastError());
+  }
+  return LA_OK;
+}
+
+int lu_mg_sync(la_lu_mg* c) {
+  LA_REQUIRE(c, "la_lu_mg_sync: null context");
+  DevSwitch keep;
+  for (int q = 0; q < c->ndev; ++q) {
+    LA_CUDA_TRY(cudaSetDevice(c->dev[q].device));
+    LA_CUDA_TRY(cudaStreamSynchronize(c->dev[q].st));
+  }
+  if (c->last_ms == -2.f) {  // a factorisation was queued since the last read
+    LA_CUDA_TRY(cudaSetDevice(c->dev[0].device));
+    LA_CUDA_TRY(cudaEventElapsedTime(&c->last_ms, c->t0, c->t1));
+  }
+  return LA_OK;
+}
+
+int lu_mg_download(la_lu_mg* c, double* LU, uint64_t* piv, int* pospivsign) {
+  LA_REQUIRE(c, "la_lu_mg_download: null context");
+  LA_TRY(lu_mg_sync(c));
+  DevSwitch keep;
+  const size_t n = c->n;
+  if (LU) {
+    for (int b = 0; b < c->nblk; ++b) {
+      LuMgDev& D = c->dev[b % c->ndev];
+      LA_CUDA_TRY(cudaSetDevice(D.device));
+      LA_CUDA_TRY(cudaMemcpy2DAsync(LU + (size_t)b * MAX_NB, n * sizeof(double), D.A + (size_t)(b / c->ndev) * MAX_NB,
+                                    D.ld * sizeof(double), (size_t)mglu_width(c, b) * sizeof(double), n,
+                                    cudaMemcpyDeviceToHost, D.st));
+    }
+  }
+  LuMgDev& D0 = c->dev[0];
+  LA_CUDA_TRY(cudaSetDevice(D0.device));
+  if (piv) LA_CUDA_TRY(cudaMemcpyAsync(piv, D0.piv, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, D0.st));
+  if (pospivsign) LA_CUDA_TRY(cudaMemcpyAsync(pospivsign, D0.sign, sizeof(int), cudaMemcpyDeviceToHost, D0.st));
+  return lu_mg_sync(c);
+}
+
+int lu_mg_factor(la_lu_mg* c) {
+  LA_REQUIRE(c, "la_lu_mg_factor: null context");
+  DevSwitch keep;
+  using T = double;
+  const int G = c->ndev, M = (int)c->n, nblk = c->nblk;
+  const int SWAP_SMEM = (int)(sizeof(T) * MAX_MOVES * SWAP_W);
+  const int INVL_SMEM = (int)(sizeof(T) * ((size_t)MAX_NB * INVL_LD + 3 * IB * IB));
+  const int HEAD_SMEM = (int)(sizeof(T) * ((size_t)MAX_NB * HEAD_LD + (size_t)MAX_NB * (HEAD_COLS + 1) +
+                                           (size_t)MAX_NB * HEAD_COLS));
+  auto use = [&](LuMgDev& D) -> int {
+    LA_CUDA_TRY(cudaSetDevice(D.device));
+    return LA_OK;
+  };
+  auto lslot = [&](LuMgDev& D, int slot) { return D.Lring + (size_t)slot * M * MAX_NB; };
+  auto launch_panel = [&](LuMgDev& D, int j0, int jb, int lc) -> int {  // columns [lc, lc + jb) of D hold block column j0
+    const PanelShape ps = panel_shape<T>(M - j0, jb, D.sms, false);
+    // the kernel addresses column j0 + c of a full matrix: shift the base so that this lands on local column lc + c
+    T* a = (T*)((uintptr_t)D.A + ((intptr_t)lc - (intptr_t)j0) * (intptr_t)sizeof(T));
+    size_t ld = D.ld;
+    int mm = M, jj0 = j0, jjb = jb, rr = ps.rpc, ioff = 0;
+    void* wsb = D.ws;
+    unsigned ep = ++D.epoch;
+    void* args[] = {&a, &ld, &mm, &jj0, &jjb, &rr, &wsb, &ep, &ioff};
+    LA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)lu_panel_kernel<T, false>, dim3(ps.G), dim3(PANEL_THREADS), args,
+                                            ps.smem, D.sp));
+    return LA_OK;
+  };
+
+  // ---- per device: kernel attributes, piv = identity, exchange tags invalid; the clock starts on device 0 ----
+  LA_TRY(use(c->dev[0]));
+  LA_CUDA_TRY(cudaEventRecord(c->t0, c->dev[0].st));
+  for (int q = 0; q < G; ++q) {
+    LuMgDev& D = c->dev[q];
+    LA_TRY(use(D));
+    LA_CUDA_TRY(cudaFuncSetAttribute(lu_panel_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)PANEL_SMEM_BUDGET + 2048));
+    LA_CUDA_TRY(cudaFuncSetAttribute(lu_swap_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWAP_SMEM));
+    LA_CUDA_TRY(cudaFuncSetAttribute(lu_invl_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, INVL_SMEM));
+    LA_CUDA_TRY(cudaFuncSetAttribute(lu_head_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM));
+    if (q > 0) LA_CUDA_TRY(cudaStreamWaitEvent(D.st, c->t0, 0));
+    lu_init_piv_kernel<T><<<(M + 255) / 256, 256, 0, D.st>>>(D.piv, M, D.sign);
+    LA_CUDA_TRY(cudaGetLastError());
+    LA_CUDA_TRY(cudaMemsetAsync((char*)D.ws + ws_hdr_bytes<T>(), 0, ws_bytes<T>(D.sms) - ws_hdr_bytes<T>(), D.st));
+    D.epoch = 0;
+    LA_CUDA_TRY(cudaEventRecord(D.e_in, D.st));
+    LA_CUDA_TRY(cudaStreamWaitEvent(D.sp, D.e_in, 0));
+    LA_CUDA_TRY(cudaStreamWaitEvent(D.sw, D.e_in, 0));
+  }
+  LA_TRY(use(c->dev[0]));
+  LA_TRY(launch_panel(c->dev[0], 0, mglu_width(c, 0), 0));
+
+  for (int k = 0; k < nblk; ++k) {
+    const int j0 = k * MAX_NB, jb = mglu_width(c, k), c1 = j0 + jb;
+    const int o = k % G, slot = k % MGLU_RING;
+    const bool has_next = k + 1 < nblk;
+    const int nb2 = has_next ? mglu_width(c, k + 1) : 0;
+    const int o2 = (k + 1) % G;
+    const int lc0 = (k / G) * MAX_NB, lcn = ((k + 1) / G) * MAX_NB;
+    LuMgDev& O = c->dev[o];
+    // ---- owner: the factored block column and its pivots go to every device's ring slot (the next owner first) ----
+    LA_TRY(use(O));
+    for (int i = 0; i < G; ++i) {
+      const int q = (o2 + i) % G;
+      LuMgDev& D = c->dev[q];
+      if (k >= MGLU_RING) LA_CUDA_TRY(cudaStreamWaitEvent(O.sp, D.e_bulk[slot], 0));  // step k - RING has left the slot
+      LA_CUDA_TRY(cudaMemcpy2DAsync(lslot(D, slot), MAX_NB * sizeof(T), O.A + (size_t)j0 * O.ld + lc0, O.ld * sizeof(T),
+                                    (size_t)jb * sizeof(T), (size_t)(M - j0), cudaMemcpyDeviceToDevice, O.sp));
+      LA_CUDA_TRY(cudaMemcpyAsync(D.ipiv_ring + slot * MAX_NB, ((PanelWs<T>*)O.ws)->ipiv, sizeof(int) * MAX_NB,
+                                  cudaMemcpyDeviceToDevice, O.sp));
+      LA_CUDA_TRY(cudaEventRecord(O.e_arr[q][slot], O.sp));
+    }
+    LA_CUDA_TRY(cudaEventRecord(O.e_sent[slot], O.sp));
+    // ---- every device, the next owner first ----
+    for (int i = 0; i < G; ++i) {
+      const int q = (o2 + i) % G;
+      LuMgDev& D = c->dev[q];
+      LA_TRY(use(D));
+      T* Ls = lslot(D, slot);
+      T* W = D.Wring + (size_t)slot * MAX_NB * MAX_NB;
+      const bool next_owner = has_next && q == o2;
+      const int lr = mglu_cols_through(c, k, q);       // local columns right of the panel start here
+      const int cb = lr + (next_owner ? nb2 : 0);      // ... and the bulk's share of them here
+      const int wcols = D.ncols - cb;
+      // chain stream: pivots -> net permutation, this device's piv / sign
+      LA_CUDA_TRY(cudaStreamWaitEvent(D.sp, O.e_arr[q][slot], 0));
+      lu_perm_kernel<T><<<1, 2 * MAX_NB, 0, D.sp>>>(D.ws, 1, slot, j0, jb, D.piv, D.sign, 0, 1, D.ipiv_ring + slot * MAX_NB);
+      LA_CUDA_TRY(cudaGetLastError());
+      LA_CUDA_TRY(cudaEventRecord(D.e_perm[slot], D.sp));
+      // side stream: W = inv(L11) from the ring slot (only the bulk needs it)
+      if (wcols > 0) {
+        LA_CUDA_TRY(cudaStreamWaitEvent(D.sw, O.e_arr[q][slot], 0));
+        const T* Lshift = (const T*)((uintptr_t)Ls - ((size_t)j0 * MAX_NB + j0) * sizeof(T));  // (j0 + i, j0 + k) -> Ls[i][k]
+        lu_invl_kernel<T, 0><<<1, INVL_THREADS, INVL_SMEM, D.sw>>>(Lshift, MAX_NB, j0, jb, c1, W, 0);
+        LA_CUDA_TRY(cudaGetLastError());
+        LA_CUDA_TRY(cudaEventRecord(D.e_w[slot], D.sw));
+      }
+      // chain stream of the next owner: its panel's columns first, then the panel
+      if (next_owner) {
+        if (k > 0) LA_CUDA_TRY(cudaStreamWaitEvent(D.sp, D.e_bulk[(k - 1) % MGLU_RING], 0));  // bulk(k-1) updated them
+        lu_head_kernel<T><<<(nb2 + HEAD_COLS - 1) / HEAD_COLS, 256, HEAD_SMEM, D.sp>>>(D.A, D.ld, j0, jb, lcn, lcn + nb2,
+                                                                                     D.ws, 1, slot, Ls, MAX_NB);
+        LA_CUDA_TRY(cudaGetLastError());
+        if (c1 < M)
+          LA_TRY(gemm_f64_tensor(Ls + (size_t)(c1 - j0) * MAX_NB, MAX_NB, D.A + (size_t)j0 * D.ld + lcn, D.ld,
+                                 D.A + (size_t)c1 * D.ld + lcn, D.ld, (size_t)(M - c1), (size_t)jb, (size_t)nb2, LA_GEMM_SUB,
+                                 D.sp));
+        LA_TRY(launch_panel(D, c1, nb2, lcn));
+      }
+      // bulk stream: interchanges of every other local column, U12 = W * A12, A22 -= L21 * U12
+      LA_CUDA_TRY(cudaStreamWaitEvent(D.st, D.e_perm[slot], 0));
+      if (q == o) LA_CUDA_TRY(cudaStreamWaitEvent(D.st, O.e_sent[slot], 0));  // later interchanges touch the panel's columns
+      int s0 = 0, s1 = 0;  // columns interchanged elsewhere: the panel's own (inside the panel kernel), the next panel's (head)
+      if (q == o) {
+        s0 = lc0;
+        s1 = lc0 + jb;
+      }
+      if (next_owner) {
+        if (q == o) {
+          s1 += nb2;  // one device: the two ranges are adjacent
+        } else {
+          s0 = lcn;
+          s1 = lcn + nb2;
+        }
+      }
+      const int nswap = D.ncols - (s1 - s0);
+      if (nswap > 0) {
+        lu_swap_kernel<T><<<(nswap + SWAP_W - 1) / SWAP_W, 256, SWAP_SMEM, D.st>>>(D.A, D.ld, 0, D.ncols, s0, s1, D.ws, 1, slot);
+        LA_CUDA_TRY(cudaGetLastError());
+      }
+      if (wcols > 0) {
+        LA_CUDA_TRY(cudaStreamWaitEvent(D.st, D.e_w[slot], 0));
+        T* U12 = D.A + (size_t)j0 * D.ld + cb;
+        LA_TRY(gemm_f64_tensor(W, MAX_NB, U12, D.ld, U12, D.ld, (size_t)jb, (size_t)jb, (size_t)wcols, LA_GEMM_ASSIGN, D.st));
+        if (c1 < M)
+          LA_TRY(gemm_f64_tensor(Ls + (size_t)(c1 - j0) * MAX_NB, MAX_NB, U12, D.ld, D.A + (size_t)c1 * D.ld + cb, D.ld,
+                                 (size_t)(M - c1), (size_t)jb, (size_t)wcols, LA_GEMM_SUB, D.st));
+      }
+      LA_CUDA_TRY(cudaEventRecord(D.e_bulk[slot], D.st));
+    }
+  }
+  // ---- every bulk stream covers its device's chain and side streams; device 0's covers every device; clock stops ----
+  for (int q = 0; q < G; ++q) {
+    LuMgDev& D = c->dev[q];
+    LA_TRY(use(D));
+    LA_CUDA_TRY(cudaEventRecord(D.e_tail, D.sp));
+    LA_CUDA_TRY(cudaStreamWaitEvent(D.st, D.e_tail, 0));
+    LA_CUDA_TRY(cudaEventRecord(D.e_in, D.sw));
+    LA_CUDA_TRY(cudaStreamWaitEvent(D.st, D.e_in, 0));
+    LA_CUDA_TRY(cudaEventRecord(D.e_tail, D.st));
+  }
+  LuMgDev& D0 = c->dev[0];
+  LA_TRY(use(D0));
+  for (int q = 1; q < G; ++q) LA_CUDA_TRY(cudaStreamWaitEvent(D0.st, c->dev[q].e_tail, 0));
+  LA_CUDA_TRY(cudaEventRecord(c->t1, D0.st));
+  c->last_ms = -2.f;
+  return LA_OK;
+}
+
+}  // namespace
+}  // namespace la
+
+extern "C" {
+int la_lu_mg_create(int ngpus, const int* devices, size_t n, la_lu_mg** out) { return la::lu_mg_create(ngpus, devices, n, out); }
+int la_lu_mg_destroy(la_lu_mg* ctx) { return la::lu_mg_destroy(ctx); }
+int la_lu_mg_upload_f64(la_lu_mg* ctx, const double* A) { return la::lu_mg_upload(ctx, A); }
+int la_lu_mg_fill_hash_f64(la_lu_mg* ctx, uint64_t seed) { return la::lu_mg_fill_hash(ctx, seed); }
+int la_lu_mg_factor_f64(la_lu_mg* ctx) { return la::lu_mg_factor(ctx); }
+int la_lu_mg_sync(la_lu_mg* ctx) { return la::lu_mg_sync(ctx); }
+int la_lu_mg_download_f64(la_lu_mg* ctx, double* LU_out, uint64_t* piv_out, int* pospivsign_out) {
+  return la::lu_mg_download(ctx, LU_out, piv_out, pospivsign_out);
+}
+int la_lu_mg_last_ms(la_lu_mg* ctx, float* ms_out) {
+  if (!ctx || !ms_out) return la::fail(LA_ERR_INVALID, "la_lu_mg_last_ms: null pointer");
+  int s = la::lu_mg_sync(ctx);
+  if (s != LA_OK) return s;
+  if (ctx->last_ms < 0.f) return la::fail(LA_ERR_INVALID, "la_lu_mg_last_ms: no factorisation has run in this context");
+  *ms_out = ctx->last_ms;
+  return LA_OK;
+}
+int la_lu_mg_devices(const la_lu_mg* ctx, int* ndev_out) {
+  if (!ctx || !ndev_out) return la::fail(LA_ERR_INVALID, "la_lu_mg_devices: null pointer");
+  *ndev_out = ctx->ndev;
+  return LA_OK;
+}
+// One call from host memory: A (row-major n x n) -> packed LU, piv, pospivsign, across the listed devices.
+int la_lu_factor_f64_mg(int ngpus, const int* devices, const double* A, double* LU_out, size_t n, uint64_t* piv_out,
+                        int* pospivsign_out) {
+  if (!A || !LU_out || !piv_out || !pospivsign_out) return la::fail(LA_ERR_INVALID, "la_lu_factor_f64_mg: null pointer");
+  la_lu_mg* c = nullptr;
+  int s = la::lu_mg_create(ngpus, devices, n, &c);
+  if (s == LA_OK) s = la::lu_mg_upload(c, A);
+  if (s == LA_OK) s = la::lu_mg_factor(c);
+  if (s == LA_OK) s = la::lu_mg_download(c, LU_out, piv_out, pospivsign_out);
+  if (s != LA_OK) {
+    const std::string why = la::error_text();
+    la::lu_mg_destroy(c);
+    la::set_error("%s", why.c_str());
+    return s;
+  }
+  return la::lu_mg_destroy(c);
+}
+}  // extern "C"

@@ -72,6 +72,16 @@ SIGNATURES = {
     "la_lu_factor_f32_host": ([_p, _p, _sz, _sz, _p, _pi], _i),
     "la_lu_factor_f64_dev": ([_p, _sz, _sz, _p, _p, _p], _i),
     "la_lu_factor_f32_dev": ([_p, _sz, _sz, _p, _p, _p], _i),
+    "la_lu_mg_create": ([_i, _p, _sz, _p], _i),
+    "la_lu_mg_destroy": ([_p], _i),
+    "la_lu_mg_devices": ([_p, _pi], _i),
+    "la_lu_mg_upload_f64": ([_p, _p], _i),
+    "la_lu_mg_fill_hash_f64": ([_p, ctypes.c_uint64], _i),
+    "la_lu_mg_factor_f64": ([_p], _i),
+    "la_lu_mg_sync": ([_p], _i),
+    "la_lu_mg_download_f64": ([_p, _p, _p, _pi], _i),
+    "la_lu_mg_last_ms": ([_p, _p], _i),
+    "la_lu_factor_f64_mg": ([_i, _p, _p, _p, _sz, _p, _pi], _i),
     "la_lu_is_nonsingular_f64": ([_p, _sz, _pi], _i),
     "la_lu_is_nonsingular_f32": ([_p, _sz, _pi], _i),
     "la_lu_det_f64": ([_p, _sz, _i, ctypes.POINTER(ctypes.c_double)], _i),

@@ -122,3 +122,69 @@ def gemm_mg(a, b, devices):
     check(getattr(lib(), f"la_gemm_{suf}_mg")(len(devices), devs, a.ctypes.data, b.ctypes.data, c.ctypes.data, a.shape[0],
                                               a.shape[1], b.shape[1]))
     return c
+
+
+class LuMgContext:
+    """LU of one n x n fp64 matrix across several devices driven by this thread (la_lu_mg_*, include/la_cabi.h): 128-column
+    blocks dealt round-robin, the owner's factored block column copied to every device, no collective."""
+
+    def __init__(self, devices, n):
+        self.n = int(n)
+        self.h = ctypes.c_void_p()
+        devs = (ctypes.c_int * len(devices))(*devices)
+        check(lib().la_lu_mg_create(len(devices), devs, self.n, ctypes.byref(self.h)))
+
+    def devices_in_use(self):
+        out = ctypes.c_int()
+        check(lib().la_lu_mg_devices(self.h, ctypes.byref(out)))
+        return out.value
+
+    def upload(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        assert a.shape == (self.n, self.n)
+        check(lib().la_lu_mg_upload_f64(self.h, a.ctypes.data))
+
+    def fill_hash(self, seed):
+        check(lib().la_lu_mg_fill_hash_f64(self.h, seed))
+
+    def factor(self):
+        check(lib().la_lu_mg_factor_f64(self.h))
+
+    def sync(self):
+        check(lib().la_lu_mg_sync(self.h))
+
+    def last_ms(self):
+        out = ctypes.c_float()
+        check(lib().la_lu_mg_last_ms(self.h, ctypes.byref(out)))
+        return out.value
+
+    def download(self, want_lu=True):
+        lu = np.empty((self.n, self.n), dtype=np.float64) if want_lu else None
+        piv = np.empty(self.n, dtype=np.uint64)
+        sign = ctypes.c_int(-7)
+        check(lib().la_lu_mg_download_f64(self.h, lu.ctypes.data if want_lu else None, piv.ctypes.data, ctypes.byref(sign)))
+        return lu, piv, bool(sign.value)
+
+    def destroy(self):
+        if self.h:
+            lib().la_lu_mg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def lu_factor_mg(a, devices):
+    """(packed LU, piv, pospivsign) of a host matrix across `devices` (la_lu_factor_f64_mg)."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    n = a.shape[0]
+    assert a.shape == (n, n)
+    lu = np.empty_like(a)
+    piv = np.empty(n, dtype=np.uint64)
+    sign = ctypes.c_int(-7)
+    devs = (ctypes.c_int * len(devices))(*devices)
+    check(lib().la_lu_factor_f64_mg(len(devices), devs, a.ctypes.data, lu.ctypes.data, n, piv.ctypes.data, ctypes.byref(sign)))
+    return lu, piv, bool(sign.value)

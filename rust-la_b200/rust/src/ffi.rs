@@ -10,6 +10,10 @@ pub struct la_buf {
 pub struct la_mg {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct la_lu_mg {
+    _private: [u8; 0],
+}
 pub const LA_MG_HANDLE_BYTES: usize = 256;
 pub const LA_EW_ADD: c_int = 0;
 pub const LA_EW_SUB: c_int = 1;
@@ -121,6 +125,16 @@ extern "C" {
     pub fn la_gemm_f64_mg_rank(ctx: *mut la_mg, a_shard: *const f64, lda: usize, c_shard: *mut f64, ldc: usize, m_local: usize, cuda_stream: *mut c_void) -> c_int;
     pub fn la_gemm_f64_mg_rank_host(ctx: *mut la_mg, a_shard: *const f64, b_block: *const f64, ldb: usize, c_shard: *mut f64, m_local: usize) -> c_int;
     pub fn la_get_gemm_f32_mode(out: *mut c_int) -> c_int;
+    pub fn la_lu_factor_f64_mg(ngpus: c_int, devices: *const c_int, a: *const f64, lu_out: *mut f64, n: usize, piv_out: *mut u64, pospivsign_out: *mut c_int) -> c_int;
+    pub fn la_lu_mg_create(ngpus: c_int, devices: *const c_int, n: usize, out: *mut *mut la_lu_mg) -> c_int;
+    pub fn la_lu_mg_destroy(ctx: *mut la_lu_mg) -> c_int;
+    pub fn la_lu_mg_devices(ctx: *const la_lu_mg, ndev_out: *mut c_int) -> c_int;
+    pub fn la_lu_mg_download_f64(ctx: *mut la_lu_mg, lu_out: *mut f64, piv_out: *mut u64, pospivsign_out: *mut c_int) -> c_int;
+    pub fn la_lu_mg_factor_f64(ctx: *mut la_lu_mg) -> c_int;
+    pub fn la_lu_mg_fill_hash_f64(ctx: *mut la_lu_mg, seed: u64) -> c_int;
+    pub fn la_lu_mg_last_ms(ctx: *mut la_lu_mg, ms_out: *mut f32) -> c_int;
+    pub fn la_lu_mg_sync(ctx: *mut la_lu_mg) -> c_int;
+    pub fn la_lu_mg_upload_f64(ctx: *mut la_lu_mg, a: *const f64) -> c_int;
     pub fn la_mg_b_block(ctx: *const la_mg, block_dev: *mut *mut c_void, ldb: *mut usize, col0: *mut usize, col1: *mut usize) -> c_int;
     pub fn la_mg_connect(ctx: *mut la_mg, handles: *const c_void) -> c_int;
     pub fn la_mg_create(rank: c_int, nranks: c_int, device: c_int, elem_bytes: usize, k: usize, n: usize, out: *mut *mut la_mg) -> c_int;

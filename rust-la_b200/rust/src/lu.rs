@@ -63,6 +63,32 @@ pub struct LUDecomposition<T> {
     _marker: ::std::marker::PhantomData<T>,
 }
 
+impl LUDecomposition<f64> {
+    /// The same factorisation spread over several GPUs of the node (`la_lu_factor_f64_mg`: 128-column blocks dealt
+    /// round-robin, the panel owner's block column copied to every device).  The packed factors come back to device 0,
+    /// so `solve`, `det`, `get_l` ... work as after `new`.
+    pub fn new_on_devices(a: &Matrix<f64>, devices: &[c_int]) -> LUDecomposition<f64> {
+        let (m, n) = (a.rows(), a.cols());
+        assert!(m == n);
+        assert!(!devices.is_empty());
+        let mut lu = vec![0f64; n * n];
+        let mut piv64 = vec![0u64; n];
+        let mut sign: c_int = 1;
+        ffi::check(unsafe {
+            ffi::la_lu_factor_f64_mg(devices.len() as c_int, devices.as_ptr(), a.get_data().as_ptr(), lu.as_mut_ptr(), n,
+                                     piv64.as_mut_ptr(), &mut sign)
+        });
+        let bytes = n * n * ::std::mem::size_of::<f64>();
+        let buf = DevBuf::new(bytes);
+        ffi::check(unsafe { ffi::la_buf_upload(buf.0, 0, lu.as_ptr() as *const _, bytes) });
+        LUDecomposition {
+            m: n, n: n, lu_dev: buf, pospivsign: sign != 0,
+            piv: piv64.into_iter().map(|p| p as usize).collect(),
+            _marker: ::std::marker::PhantomData,
+        }
+    }
+}
+
 impl<T: LuScalar> LUDecomposition<T> {
     /// src/decomp/lu.rs:104-168.  Factorises a copy of `a` (:105) on the device.
     pub fn new(a: &Matrix<T>) -> LUDecomposition<T> {

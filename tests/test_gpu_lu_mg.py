@@ -1,0 +1,125 @@
+"""LU across several devices behind the C ABI (la_lu_mg_*, la_lu_factor_f64_mg) against the oracle.
+
+The driver is one host thread with streams, events and peer copies, so a device may be listed more than once: [0, 0] and
+[0, 0, 0] run the whole protocol (block-cyclic columns, ring slots, the chain hopping between owners, per-device pivot
+bookkeeping) on a 1-GPU box.  The tests with distinct devices are skipped below 2 GPUs.  Bars as for the single-device LU:
+identical pivot permutation, element error <= 1e-12 * n, backward error within 10x of the reference's."""
+import os
+
+import numpy as np
+import pytest
+
+from la import _cabi, sharding
+
+pytestmark = pytest.mark.gpu
+FIX = os.path.join(os.path.dirname(__file__), "golden", "lu16384_f64.npz")
+
+
+def _check(oracle, a, lu, piv, sign):
+    n = a.shape[0]
+    ref_lu, ref_piv, ref_sign = oracle.lu(a)
+    assert np.array_equal(piv, ref_piv), f"pivot mismatch at {np.nonzero(piv != ref_piv)[0][:5]}"
+    assert sign == ref_sign
+    den = np.maximum(np.abs(ref_lu), float(np.max(np.abs(a))))
+    err = float(np.max(np.abs(lu - ref_lu) / den))
+    assert err <= 1e-12 * n, f"element error {err}"
+    be_ref = oracle.lu_backward_error(a, ref_lu, ref_piv)
+    be = oracle.lu_backward_error(a, lu, piv)
+    assert be <= 10 * max(be_ref, np.finfo(np.float64).eps), f"backward error {be} vs reference {be_ref}"
+
+
+@pytest.mark.parametrize("n", [129, 256, 300, 515, 1000, 1024, 1411, 2048])
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_lu_mg_ranks_on_one_device(oracle, n, world):
+    a = oracle.fill((n, n), 1)
+    lu, piv, sign = sharding.lu_factor_mg(a, [0] * world)
+    _check(oracle, a, lu, piv, sign)
+
+
+def test_lu_mg_more_devices_than_block_columns(oracle):
+    """n = 200 has two block columns: five listed devices collapse to two; n = 100 to one."""
+    for n, expect in ((200, 2), (100, 1)):
+        ctx = sharding.LuMgContext([0] * 5, n)
+        try:
+            assert ctx.devices_in_use() == expect
+            a = oracle.fill((n, n), 3) - 0.5
+            ctx.upload(a)
+            ctx.factor()
+            lu, piv, sign = ctx.download()
+            _check(oracle, a, lu, piv, sign)
+        finally:
+            ctx.destroy()
+
+
+def test_lu_mg_context_reuse_and_generated_input(oracle):
+    """One context, several factorisations (ring slots, events and epochs are reused), the second on the device-side
+    generator the bench uses: element (i, j) = hash(seed, i * n + j), the oracle's fill."""
+    n = 1536
+    ctx = sharding.LuMgContext([0, 0], n)
+    try:
+        a = oracle.fill((n, n), 5)
+        for _ in range(2):
+            ctx.upload(a)
+            ctx.factor()
+            lu, piv, sign = ctx.download()
+            _check(oracle, a, lu, piv, sign)
+        ctx.fill_hash(1)
+        ctx.factor()
+        lu, piv, sign = ctx.download()
+        _check(oracle, oracle.fill((n, n), 1), lu, piv, sign)
+        assert ctx.last_ms() > 0
+    finally:
+        ctx.destroy()
+
+
+def test_lu_mg_singular_and_zero_pivot(oracle):
+    """Exact singularity is not an error (lu.rs:156-160): a zero column deep in the matrix leaves a zero pivot, the
+    factorisation continues and matches the reference's."""
+    n = 640
+    a = oracle.fill((n, n), 7)
+    a[:, 300] = 0.0
+    lu, piv, sign = sharding.lu_factor_mg(a, [0, 0])
+    _check(oracle, a, lu, piv, sign)
+    assert lu[300, 300] == 0.0
+
+
+def _full_size(devices):
+    fx = np.load(FIX)
+    n = int(fx["n"])
+    ctx = sharding.LuMgContext(devices, n)
+    try:
+        ctx.fill_hash(int(fx["seed"]))
+        ctx.factor()
+        lu, piv, sign = ctx.download()
+        ms = ctx.last_ms()
+    finally:
+        ctx.destroy()
+    mism = np.nonzero(piv.astype(np.int64) != fx["piv"].astype(np.int64))[0]
+    assert mism.size == 0, f"pivot permutation differs from the reference's at {mism[:5]} ({mism.size} rows)"
+    assert sign == bool(fx["pospivsign"])
+    ref_diag = fx["diag_every8"]
+    assert np.max(np.abs(np.diagonal(lu)[::8] - ref_diag) / np.maximum(np.abs(ref_diag), 1.0)) <= 1e-12 * n
+    ref = fx["row_samples_every16"]
+    assert np.max(np.abs(lu[fx["rows"]][:, ::16] - ref) / np.maximum(np.abs(ref), 1.0)) <= 1e-12 * n
+    return ms
+
+
+def test_lu_mg_16384_two_ranks_on_one_device_matches_fixture():
+    """BASELINE config 2's matrix through the multi-device driver: pivots identical to the committed oracle fixture."""
+    _full_size([0, 0])
+
+
+@pytest.mark.parametrize("ndev", [2, 4, 8])
+def test_lu_mg_16384_distinct_devices_matches_fixture(ndev):
+    if _cabi.device_count() < ndev:
+        pytest.skip(f"needs {ndev} GPUs")
+    _full_size(list(range(ndev)))
+
+
+def test_lu_mg_distinct_devices_small(oracle):
+    if _cabi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    for n in (300, 1411, 2048):
+        a = oracle.fill((n, n), 1)
+        lu, piv, sign = sharding.lu_factor_mg(a, [0, 1])
+        _check(oracle, a, lu, piv, sign)
