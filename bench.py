@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--skip-lu", action="store_true", help="N=1 only: do not time the LU n=16384 / Cholesky legs")
     ap.add_argument("--skip-f32", action="store_true", help="do not time the f32 65536x1024x16384 leg")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--skip-lu-mg", action="store_true", help="N>1 only: do not time the LU n=16384 across the N GPUs")
     ap.add_argument("--skip-check", action="store_true", help="skip the in-bench oracle checks (debug)")
     ap.add_argument("--n", type=int, default=0, help="override the GEMM size (debug)")
     args = ap.parse_args()
@@ -695,6 +696,10 @@ def main():
         if lu:
             cpu["lu"] = cpu_lu_baseline(threads)
 
+    lu_mg = None
+    if n_gpus > 1 and not args.skip_lu_mg:
+        lu_mg = lu_mg_leg(n_gpus)
+
     line = {
         "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -713,6 +718,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "lu": lu,
+        "lu_mg": lu_mg,
         "cholesky": chol,
         "qr": qr_leg,
         "streaming": stream_leg,
@@ -722,6 +728,32 @@ def main():
     if n_gpus > 1:
         dist.destroy_process_group()
     return 0
+
+
+def lu_mg_leg(n_gpus):
+    """LU n = 16384 across the N GPUs (la_lu_mg_*: one host thread drives all devices, so it runs once, from rank 0, after the
+    other ranks have finished -- in a child process with a hard timeout so that nothing here can cost the GEMM line)."""
+    devs = ",".join(str(i) for i in range(n_gpus))
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "lu_mg_profile.py"), "16384", "4", "0", devs, "--check"]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"}
+    res = {}
+    for ln in out.stdout.splitlines():
+        if not ln.startswith("lu_mg "):
+            continue
+        key = "one_device" if "devices=[0]:" in ln else "all_devices"
+        best = float(ln.split("best ")[1].split(" ms")[0])
+        res[key] = {"ms": best, "tflops": 2.0 / 3.0 * 16384 ** 3 / (best * 1e-3) / 1e12,
+                    "piv_identical_to_oracle_fixture": "piv_identical_to_oracle_fixture=True" in ln}
+    if "all_devices" not in res:
+        return {"error": (out.stdout + out.stderr)[-400:]}
+    return {"workload": f"f64 LU n=16384 over {n_gpus} GPUs: 128-column blocks dealt round-robin, the panel owner's block "
+                        f"column copied to every device (la_lu_mg_factor_f64), best of 4, device-timed on the first device "
+                        f"which waits for all others", "n_gpus": n_gpus, **res,
+            "speedup_vs_one_device_same_driver": res.get("one_device", {}).get("ms", 0.0) / res["all_devices"]["ms"],
+            "bound": "the panel chain (panel -> peer copy -> head -> update -> panel), which hops from device to device"}
 
 
 def cpu_lu_baseline(threads):

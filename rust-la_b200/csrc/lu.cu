@@ -24,6 +24,7 @@
 #include <float.h>
 #include <limits.h>
 #include <stdlib.h>
+#include <time.h>
 
 #include <string>
 #include <type_traits>
@@ -1666,6 +1667,9 @@ int lu_mg_factor(la_lu_mg* c) {
   }
   LA_TRY(use(c->dev[0]));
   LA_TRY(launch_panel(c->dev[0], 0, mglu_width(c, 0), 0));
+  static const bool trace = getenv("LA_LU_MG_TRACE") && atoi(getenv("LA_LU_MG_TRACE")) != 0;  // host issue time on stderr
+  timespec ts0;
+  clock_gettime(CLOCK_MONOTONIC, &ts0);
 
   for (int k = 0; k < nblk; ++k) {
     const int j0 = k * MAX_NB, jb = mglu_width(c, k), c1 = j0 + jb;
@@ -1771,6 +1775,12 @@ int lu_mg_factor(la_lu_mg* c) {
   for (int q = 1; q < G; ++q) LA_CUDA_TRY(cudaStreamWaitEvent(D0.st, c->dev[q].e_tail, 0));
   LA_CUDA_TRY(cudaEventRecord(c->t1, D0.st));
   c->last_ms = -2.f;
+  if (trace) {
+    timespec ts1;
+    clock_gettime(CLOCK_MONOTONIC, &ts1);
+    fprintf(stderr, "[lu_mg] n=%d devices=%d: all work queued after %.2f ms of host time\n", M, G,
+            (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6);
+  }
   return LA_OK;
 }
 
