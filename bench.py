@@ -638,7 +638,7 @@ def main():
                            ("" if n_gpus == 1 else f", rows sharded over {n_gpus} GPUs through la_gemm_f32_mg_rank (column blocks "
                                                    f"of B pulled over NVLink every step)"),
                "ms": tf_ms, "tflops": f_tf, "mode": "LA_F32_TF32 (opt-in; the mode BASELINE's config names)",
-               "kernel": "gemm_f32_tf32_kernel (tcgen05.mma kind::tf32, TMEM accumulators, TMA in/out) + B transpose",
+               "kernel": "gemm_f32_tf32_pair_kernel (tcgen05.mma cta_group::2 kind::tf32 on CTA pairs, TMEM accumulators, TMA in/out) + B transpose",
                "max_rel_err_vs_fp32_oracle_on_64_rows_per_shard": tf_err, "tolerance": 1e-4 * fk,
                "default_mode_3xtf32": {"ms": x3_ms, "tflops": fl32 / (x3_ms * 1e-3) / 1e12,
                                        "max_rel_err_vs_fp32_oracle_on_64_rows_per_shard": x3_err,

@@ -267,6 +267,219 @@ gemm_f32_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-PAIR kernel (`tcgen05.mma.cta_group::2`): two CTAs of one cluster (the two SMs of a TPC) work on one 256 x 256 tile.
+// Each CTA stages ITS 128 rows of A and ITS 128 of the tile's 256 B^T rows (32 KiB per stage instead of 48, six stages),
+// the leader's elected thread issues M256 N256 K8 instructions that read A from both CTAs' shared memory and each half
+// of B from its CTA, and every CTA ends up with its 128 x 256 block of the accumulator in its own TMEM.  The single-CTA
+// kernel above is bound by the shared-memory pipe (TMA fills + operand reads: 73 % busy at 69 % tensor activity,
+// profiles/r1_gemm_f32_tf32_persistent_ncu_summary.txt); the pair halves the B operand traffic per SM.
+// Barriers: `full[s]` lives in the LEADER (both CTAs' TMA loads complete their bytes on it: `.cta_group::2` loads with the
+// leader's barrier address), `empty[s]` and `acc_full[b]` exist in both CTAs and are signalled by one multicast
+// `tcgen05.commit`, `acc_empty[b]` lives in the leader and counts the eight epilogue warps of both CTAs.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PSTAGES = 6;
+constexpr int PBN_HALF = TBN / 2;                  // B^T rows staged per CTA
+constexpr int PB_BYTES = TBK * PBN_HALF * 4;       // 16 KiB
+constexpr int PSTAGE_BYTES = TA_BYTES + PB_BYTES;  // 32 KiB
+constexpr int PAIR_SMEM = PSTAGES * PSTAGE_BYTES + TOUT_BYTES + 256 + 1024;
+constexpr int PTM = 2 * TBM;                       // tile rows of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same variable in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr,
+                                                 int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster_addr), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on `bar` (same offset) in BOTH CTAs of the pair once all prior MMAs of this thread have finished
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF32_THREADS, 1)
+gemm_f32_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                          const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                          const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int tiles_m, int tiles_n, int group_m,
+                          int kpasses) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* out_stage = smem + PSTAGES * PSTAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(out_stage + TOUT_BYTES);
+  uint64_t* empty = full + PSTAGES;
+  uint64_t* acc_full = empty + PSTAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int ktiles1 = (K + TBK - 1) / TBK;
+  const int ktiles = ktiles1 * kpasses;
+  const int ntiles = tiles_m * tiles_n;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PSTAGES; ++s) {
+      mbar_init(&full[s], 1);   // the leader producer's arrive.expect_tx; bytes from both CTAs' loads
+      mbar_init(&empty[s], 1);  // one multicast commit per use
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 8);  // four epilogue warps in each CTA (only the leader's copy is used)
+    }
+    mbar_fence_init();
+  }
+  cluster_sync_all();  // barriers of both CTAs exist before anybody signals across
+  if (warp == 1) {     // the same warp of both CTAs: a pair-wide TMEM allocation
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own 128 rows of A, own 128 rows of B^T; bytes land on the leader's barrier =====
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      if (kpasses > 1) {
+        tma_prefetch_desc(&tmA1);
+        tma_prefetch_desc(&tmB1);
+      }
+      uint32_t g = 0;
+      for (int t = pair; t < ntiles; t += npairs) {
+        int tile_m, tile_n;
+        tile_coords(t, tiles_m, tiles_n, group_m, tile_m, tile_n);
+        for (int kt = 0; kt < ktiles; ++kt, ++g) {
+          const int s = g % PSTAGES;
+          mbar_wait(&empty[s], ((g / PSTAGES) & 1) ^ 1);
+          uint8_t* sA = smem + s * PSTAGE_BYTES;
+          uint8_t* sB = sA + TA_BYTES;
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * PSTAGE_BYTES);
+          const uint32_t bar = mapa_shared(smem_u32(&full[s]), 0);
+          const int pass = (kpasses > 1) ? kt / ktiles1 : 2;
+          const int kc = (kt - (kpasses > 1 ? pass * ktiles1 : 0)) * TBK;
+          tma_load_2d_pair(sA, pass == 0 ? &tmA1 : &tmA, bar, kc, tile_m * PTM + (int)rank * TBM);
+          tma_load_2d_pair(sB, pass == 1 ? &tmB1 : &tmB, bar, kc, tile_n * TBN + (int)rank * PBN_HALF);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the LEADER drives both tensor cores =====
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(PTM, TBN, 0, 0);
+      uint32_t g = 0;
+      int it = 0;
+      for (int t = pair; t < ntiles; t += npairs, ++it) {
+        const int b = it & 1;
+        mbar_wait(&acc_empty[b], ((it >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(b * TBN);
+        for (int kt = 0; kt < ktiles; ++kt, ++g) {
+          const int s = g % PSTAGES;
+          mbar_wait(&full[s], (g / PSTAGES) & 1);
+          tcgen05_fence_after();
+          const uint32_t sA = smem_u32(smem + s * PSTAGE_BYTES);
+          const uint32_t sB = sA + TA_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < TBK / 8; ++kk) {
+            const uint64_t adesc = umma_smem_desc(sA + kk * 32, 16, 1024);
+            const uint64_t bdesc = umma_smem_desc(sB + kk * 32, 16, 1024);
+            umma_tf32_pair(tmem_d, adesc, bdesc, idesc, (kt | kk) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty[s]);
+        }
+        umma_commit_pair(&acc_full[b]);
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): this CTA's 128 rows of the tile, TMEM lane quarter = warp % 4 =====
+    const int quarter = warp & 3;
+    uint8_t* my_stage = out_stage + (warp - 2) * (2 * TOUT_BOX_BYTES);
+    int it = 0;
+    uint32_t nbox = 0;
+    for (int t = pair; t < ntiles; t += npairs, ++it) {
+      int tile_m, tile_n;
+      tile_coords(t, tiles_m, tiles_n, group_m, tile_m, tile_n);
+      const int b = it & 1;
+      const int row0 = tile_m * PTM + (int)rank * TBM + quarter * 32;
+      mbar_wait(&acc_full[b], (it >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < TBN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * TBN + c0), r);
+        const int col0 = tile_n * TBN + c0;
+        if (row0 < M && col0 < N) {  // warp-uniform
+          uint8_t* box = my_stage + (nbox & 1) * TOUT_BOX_BYTES;
+          ++nbox;
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+#pragma unroll
+          for (int v = 0; v < 8; ++v)
+            *reinterpret_cast<uint4*>(box + lane * 128 + ((v ^ (lane & 7)) << 4)) =
+                make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (MODE == LA_GEMM_ADD) tma_reduce_add_2d(&tmC, box, col0, row0);
+            else tma_store_2d(&tmC, box, col0, row0);
+            bulk_commit();
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[b]), 0));
+    }
+    if (lane == 0) bulk_wait_all();
+  }
+  // nobody leaves (or frees TMEM) while the partner may still read its shared memory or signal its barriers
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
 // Split of an fp32 value for the compensated ("3xTF32") product: big = x rounded to TF32 (10 explicit mantissa bits, so
 // the tensor core's own input conversion is the identity on it), small = x - big (exact in fp32; the tensor core keeps
 // its leading 11 bits).  x*y ~= big_x*big_y + big_x*small_y + small_x*big_y with relative error ~2^-21 per product.
@@ -359,6 +572,20 @@ int launch_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   return LA_OK;
 }
 
+template <int MODE>
+int launch_tf32_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA1, const CUtensorMap& tmB1,
+                     const CUtensorMap& tmC, int M, int N, int K, int kpasses, int sms, cudaStream_t st) {
+  LA_CUDA_TRY(cudaFuncSetAttribute(gemm_f32_tf32_pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+  const int tiles_m = (M + PTM - 1) / PTM, tiles_n = (N + TBN - 1) / TBN;
+  const int ntiles = tiles_m * tiles_n;
+  static const int group_m = getenv("LA_TF32_GROUP_M") ? atoi(getenv("LA_TF32_GROUP_M")) : 16;
+  const int pairs = ntiles < sms / 2 ? ntiles : sms / 2;
+  gemm_f32_tf32_pair_kernel<MODE><<<2 * pairs, TF32_THREADS, PAIR_SMEM, st>>>(tmA, tmB, tmA1, tmB1, tmC, M, N, K, tiles_m,
+                                                                             tiles_n, (group_m + 1) / 2, kpasses);
+  LA_CUDA_TRY(cudaGetLastError());
+  return LA_OK;
+}
+
 }  // namespace
 
 void debug_set_gemm_f32_path(int p) { g_f32_path = p; }
@@ -426,18 +653,27 @@ int gemm_f32_dev(const float* A, size_t lda, const float* B, size_t ldb, float* 
     a_small = asml;
     ld_a = ldt;
   }
+  // CTA pairs (cta_group::2, 256 x 256 tiles) when the product has more than one 128-row band
+  static const int pair_knob = getenv("LA_TF32_PAIR") ? atoi(getenv("LA_TF32_PAIR")) : 1;  // 0: single-CTA kernel
+  const bool pair = pair_knob != 0 && m > (size_t)TBM && ctx->sm_count >= 2;
+  const int b_box = pair ? PBN_HALF : TBN;  // B^T rows per TMA box
   CUtensorMap tmA, tmB, tmA1, tmB1;
   LA_TRY(encode_tensor_map_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a_big, k, m, ld_a * 4, TBK, TBM,
                               CU_TENSOR_MAP_SWIZZLE_128B));
-  LA_TRY(encode_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, bt_big, k, n, ldt * 4, TBK, TBN,
+  LA_TRY(encode_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, bt_big, k, n, ldt * 4, TBK, b_box,
                               CU_TENSOR_MAP_SWIZZLE_128B));
   LA_TRY(encode_tensor_map_2d(&tmA1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a_small, k, m, ld_a * 4, TBK, TBM,
                               CU_TENSOR_MAP_SWIZZLE_128B));
-  LA_TRY(encode_tensor_map_2d(&tmB1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, comp ? bt_small : bt_big, k, n, ldt * 4, TBK, TBN,
+  LA_TRY(encode_tensor_map_2d(&tmB1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, comp ? bt_small : bt_big, k, n, ldt * 4, TBK, b_box,
                               CU_TENSOR_MAP_SWIZZLE_128B));
   CUtensorMap tmC;  // store boxes: 32 columns (128 B) x 32 rows, same swizzle as the epilogue's shared-memory layout
   LA_TRY(encode_tensor_map_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, n, m, ldc * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
   const int kpasses = comp ? 3 : 1;
+  if (pair) {
+    if (mode == LA_GEMM_ASSIGN)
+      return launch_tf32_pair<LA_GEMM_ASSIGN>(tmA, tmB, tmA1, tmB1, tmC, (int)m, (int)n, (int)k, kpasses, ctx->sm_count, st);
+    return launch_tf32_pair<LA_GEMM_ADD>(tmA, tmB, tmA1, tmB1, tmC, (int)m, (int)n, (int)k, kpasses, ctx->sm_count, st);
+  }
   if (mode == LA_GEMM_ASSIGN)
     return launch_tf32<LA_GEMM_ASSIGN>(tmA, tmB, tmA1, tmB1, tmC, (int)m, (int)n, (int)k, kpasses, ctx->sm_count, st);
   return launch_tf32<LA_GEMM_ADD>(tmA, tmB, tmA1, tmB1, tmC, (int)m, (int)n, (int)k, kpasses, ctx->sm_count, st);
@@ -447,6 +683,8 @@ int gemm_f32_preload() {
   cudaFuncAttributes fa;
   LA_CUDA_TRY(cudaFuncGetAttributes(&fa, gemm_f32_tf32_kernel<LA_GEMM_ASSIGN>));
   LA_CUDA_TRY(cudaFuncGetAttributes(&fa, gemm_f32_tf32_kernel<LA_GEMM_ADD>));
+  LA_CUDA_TRY(cudaFuncGetAttributes(&fa, gemm_f32_tf32_pair_kernel<LA_GEMM_ASSIGN>));
+  LA_CUDA_TRY(cudaFuncGetAttributes(&fa, gemm_f32_tf32_pair_kernel<LA_GEMM_ADD>));
   LA_CUDA_TRY(cudaFuncGetAttributes(&fa, transpose_f32_kernel<true>));
   LA_CUDA_TRY(cudaFuncGetAttributes(&fa, transpose_f32_kernel<false>));
   LA_CUDA_TRY(cudaFuncGetAttributes(&fa, split_f32_kernel));
