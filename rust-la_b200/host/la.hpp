@@ -322,6 +322,18 @@ class LUDecomposition {
     check(Abi<T>::factor(lu_.h, m_, n_, piv_.data(), &sign));
     pospivsign_ = sign != 0;
   }
+  // The same factorisation spread over several GPUs (la_lu_factor_f64_mg: 128-column blocks dealt round-robin, the panel
+  // owner's block column copied to every device); the packed factors land on device 0, so solve / det / get_l work as usual.
+  LUDecomposition(const Matrix<T>& a, const std::vector<int>& devices)
+      : m_(a.rows()), n_(a.cols()), lu_(a.rows() * a.cols() * sizeof(T)), piv_(a.rows()) {
+    static_assert(sizeof(T) == sizeof(double), "the multi-device factorisation is fp64 only");
+    LA_ASSERT(m_ == n_ && !devices.empty());
+    std::vector<T> packed(m_ * n_);
+    int sign = 1;
+    check(la_lu_factor_f64_mg(int(devices.size()), devices.data(), a.get_data().data(), packed.data(), n_, piv_.data(), &sign));
+    check(la_buf_upload(lu_.h, 0, packed.data(), packed.size() * sizeof(T)));
+    pospivsign_ = sign != 0;
+  }
   bool is_singular() const { return !is_non_singular(); }
   bool is_non_singular() const {  // lu.rs:174-182 (out-of-bounds panic of the reference for m < n kept as a Panic)
     LA_ASSERT(m_ >= n_);

@@ -194,6 +194,19 @@ int main(int argc, char** argv) {
     CHECK(inv.has_value() && inv->on_device() && !spd.host_materialised());
     CHECK((spd * *inv).approx_eq(Md::id(n, n)));
   });
+  run("LUDecomposition over a device list (la_lu_factor_f64_mg): same pivots and solution as one device", [] {
+    const size_t n = 700;
+    std::vector<double> da(n * n), db(n * 3);
+    for (size_t i = 0; i < n * n; ++i) da[i] = double((i * 7919 + 13) % 1009) / 1009.0;
+    for (size_t i = 0; i < n * 3; ++i) db[i] = double((i * 31) % 97) / 97.0;
+    Md a(n, n, da), b(n, 3, db);
+    la::LUDecomposition<double> one(a), many(a, std::vector<int>{0, 0, 0});
+    CHECK(one.get_piv() == many.get_piv());
+    CHECK(one.pospivsign() == many.pospivsign());
+    CHECK(one.get_lu().approx_eq(many.get_lu()));
+    auto x = many.solve(b);
+    CHECK(x.has_value() && (a * *x).approx_eq(b));
+  });
   printf("%d passed, %d skipped, %d failed\n", passed, skipped, failures);
   return failures ? 1 : 0;
 }
