@@ -81,7 +81,7 @@ template <int MODE, int BN>
 __global__ void __launch_bounds__(TileCfg<BN>::THREADS, TileCfg<BN>::CTAS_PER_SM)
 gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     double* __restrict__ C, size_t ldc, int M, int N, int K, int tiles_m, int tiles_n, int stagger_lo,
-                    int stagger_hi, unsigned stagger_ns, int kt_per_slice, size_t c_slab) {
+                    int stagger_hi, unsigned stagger_ns, int kt_per_slice, size_t c_slab, int lower_only) {
   using Cfg = TileCfg<BN>;
   // Shallow-K launches run two CTAs per SM so that one CTA's epilogue (HBM-bound C tile read-modify-write) overlaps the
   // other's main loop -- which only works if the two are out of phase.  CTAs launched together stay in lock step, so
@@ -109,6 +109,8 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int tile_n = (tile % tiles_per_group) / group_rows;
   const int m0 = tile_m * BM;
   const int n0 = tile_n * BN;
+  // symmetric updates (Cholesky's A22 -= L21 L21'): tiles that lie entirely above the diagonal of C are not computed
+  if (lower_only && n0 > m0 + BM - 1) return;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -282,7 +284,7 @@ int g_gemm_path = 0;  // test hook: 0 auto, 1 SIMT, 2 TMA/DMMA (auto tile), 3 TM
 
 template <int MODE, int BN>
 int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, size_t ldc, int M, int N, int K,
-               cudaStream_t st, int slices = 1, size_t c_slab = 0) {
+               cudaStream_t st, int slices = 1, size_t c_slab = 0, int lower_only = 0) {
   using Cfg = TileCfg<BN>;
   static const int extra_smem = getenv("LA_GEMM_EXTRA_SMEM") ? atoi(getenv("LA_GEMM_EXTRA_SMEM")) : 0;  // debug knob
   LA_CUDA_TRY(cudaFuncSetAttribute(gemm_f64_tma_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -303,7 +305,7 @@ int launch_tma(const CUtensorMap& tmA, const CUtensorMap& tmB, double* C, size_t
   const int kt_per_slice = (ktiles + slices - 1) / slices;
   const int nslices = (ktiles + kt_per_slice - 1) / kt_per_slice;  // every slice gets at least one k-tile
   gemm_f64_tma_kernel<MODE, BN><<<dim3(tiles_m * tiles_n, nslices), Cfg::THREADS, Cfg::SMEM_BYTES + extra_smem, st>>>(
-      tmA, tmB, C, ldc, M, N, K, tiles_m, tiles_n, stagger_lo, stagger_hi, stagger_ns, kt_per_slice, c_slab);
+      tmA, tmB, C, ldc, M, N, K, tiles_m, tiles_n, stagger_lo, stagger_hi, stagger_ns, kt_per_slice, c_slab, lower_only);
   LA_CUDA_TRY(cudaGetLastError());
   return LA_OK;
 }
@@ -408,6 +410,23 @@ int gemm_f64_preload() {
   LA_CUDA_TRY(cudaFuncGetAttributes(&fa, gemm_f64_tma_kernel<LA_GEMM_SUB, 128>));
   LA_CUDA_TRY(cudaFuncGetAttributes(&fa, gemm_f64_tma_kernel<LA_GEMM_ADD, 128>));
   return LA_OK;
+}
+
+// C -= A * B restricted to the tiles of C that touch or lie below its diagonal (C square, m == n): the symmetric trailing
+// update of the Cholesky factorisation in ONE launch; whole CTAs above the diagonal exit at once.
+int gemm_f64_sub_lower(const double* A, size_t lda, const double* B, size_t ldb, double* C, size_t ldc, size_t m, size_t k,
+                       cudaStream_t st) {
+  const bool aligned = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0) &&
+                       lda % 2 == 0 && ldb % 2 == 0 && ldc % 2 == 0;
+  if (!aligned || m == 0 || k == 0)
+    return fail(LA_ERR_INVALID, "internal: lower-triangle GEMM requested for operands that are not TMA-addressable");
+  CUtensorMap tmA, tmB;
+  LA_TRY(encode_tensor_map_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, A, k, m, lda * 8, BK, BM,
+                              CU_TENSOR_MAP_SWIZZLE_128B));
+  LA_TRY(encode_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, B, m, k, ldb * 8, 16, BK,
+                              CU_TENSOR_MAP_SWIZZLE_128B));
+  if (k <= SHALLOW_K) return launch_tma<LA_GEMM_SUB, 64>(tmA, tmB, C, ldc, (int)m, (int)m, (int)k, st, 1, 0, 1);
+  return launch_tma<LA_GEMM_SUB, 128>(tmA, tmB, C, ldc, (int)m, (int)m, (int)k, st, 1, 0, 1);
 }
 
 // Tensor kernel regardless of problem size (the LU driver needs its in-place-safe tile structure: with m <= 128 there
