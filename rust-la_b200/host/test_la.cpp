@@ -197,8 +197,13 @@ int main(int argc, char** argv) {
   run("LUDecomposition over a device list (la_lu_factor_f64_mg): same pivots and solution as one device", [] {
     const size_t n = 700;
     std::vector<double> da(n * n), db(n * 3);
-    for (size_t i = 0; i < n * n; ++i) da[i] = double((i * 7919 + 13) % 1009) / 1009.0;
-    for (size_t i = 0; i < n * 3; ++i) db[i] = double((i * 31) % 97) / 97.0;
+    uint64_t state = 88172645463325252ull;  // 64-bit LCG: a well-conditioned random matrix with real interchanges
+    auto next = [&state] {
+      state = state * 6364136223846793005ull + 1442695040888963407ull;
+      return double(state >> 11) * 0x1.0p-53;
+    };
+    for (size_t i = 0; i < n * n; ++i) da[i] = next();
+    for (size_t i = 0; i < n * 3; ++i) db[i] = next();
     Md a(n, n, da), b(n, 3, db);
     la::LUDecomposition<double> one(a), many(a, std::vector<int>{0, 0, 0});
     CHECK(one.get_piv() == many.get_piv());
