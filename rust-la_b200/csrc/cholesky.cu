@@ -167,6 +167,7 @@ __global__ void chol_solve_exact_kernel(const T* __restrict__ L, size_t n, T* __
 }
 
 }  // namespace
+int transpose_lower_f64_dev(const double* src, double* dst, size_t n, cudaStream_t st);  // la_runtime.cu
 int gemm_f64_sub_lower(const double* A, size_t lda, const double* B, size_t ldb, double* C, size_t ldc, size_t m, size_t k,
                        cudaStream_t st);  // gemm_f64.cu
 namespace {
@@ -337,7 +338,8 @@ int chol_solve_dev(const T* L, size_t n, const T* B, size_t nx, T* X, cudaStream
       double* LT = (double*)ltbuf;
       double* WL = (double*)wbuf;
       double* WU = WL + (size_t)G * CB * CB;
-      LA_TRY(transpose_dev<double>(L, LT, n, n, st));
+      // only the upper triangle of L' is ever read (off-diagonal blocks above the diagonal, upper-triangular diagonal blocks)
+      LA_TRY(transpose_lower_f64_dev(L, LT, n, st));
       LA_TRY(tri_block_inverses<double>(L, n, 2, 0, G, WL, 0, st));
       if (nx <= 16 && ctx->coop)  // few right-hand sides: the LU solve's persistent sweep kernels (they invert the blocks
         return tri_sweeps_dev(L, LT, n, nullptr, B, nx, X, WL, WU, st, 1);  // of L' beside the forward sweep)

@@ -248,10 +248,11 @@ template int identity_dev<float>(float*, size_t, cudaStream_t);
 
 // dst[c][r] = src[r][c] through 32 x 33 shared-memory tiles: reads and writes are both full 128/256-byte row segments
 // (`Matrix::t`, src/matrix/mod.rs:653-669, walks the source with stride cols).
-template <typename T>
+template <typename T, bool LOWER = false>
 __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ src, T* __restrict__ dst, size_t rows, size_t cols) {
   __shared__ T tile[32][33];
   const size_t r0 = (size_t)blockIdx.y * 32, c0 = (size_t)blockIdx.x * 32;
+  if (LOWER && c0 > r0 + 31) return;  // only the tiles that touch or lie below the diagonal of the source
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
@@ -272,6 +273,16 @@ int transpose_dev(const T* src, T* dst, size_t rows, size_t cols, cudaStream_t s
   const size_t gx = (cols + 31) / 32, gy = (rows + 31) / 32;
   LA_REQUIRE(gy <= 65535 && gx < (1u << 31), "la_transpose: dimension too large");
   transpose_kernel<T><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, st>>>(src, dst, rows, cols);
+  LA_CUDA_TRY(cudaGetLastError());
+  return LA_OK;
+}
+// The same for a lower-triangular source (a Cholesky factor): only the tiles at or below the diagonal are moved, so the
+// destination's upper triangle (with the diagonal) is the transpose and everything below its diagonal tiles is left untouched.
+int transpose_lower_f64_dev(const double* src, double* dst, size_t n, cudaStream_t st) {
+  LA_REQUIRE(src && dst && n > 0 && src != dst, "transpose_lower: bad arguments");
+  const size_t g = (n + 31) / 32;
+  LA_REQUIRE(g <= 65535, "transpose_lower: dimension too large");
+  transpose_kernel<double, true><<<dim3((unsigned)g, (unsigned)g), 256, 0, st>>>(src, dst, n, n);
   LA_CUDA_TRY(cudaGetLastError());
   return LA_OK;
 }
