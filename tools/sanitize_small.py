@@ -18,7 +18,7 @@ from la._cabi import check, lib  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 from gpu_util import DevBuf, gemm_dev, max_rel_err, sync  # noqa: E402
 
-which = sys.argv[1:] or ["gemm64", "gemm32", "lu", "solve", "chol", "qr"]
+which = sys.argv[1:] or ["gemm64", "gemm32", "lu", "lu_mg", "solve", "chol", "qr"]
 orc.build()
 if "gemm64" in which:  # TMA + DMMA kernel, both tile configurations, ragged edges, all three epilogues
     for path, (m, k, n) in ((3, (256, 528, 320)), (4, (256, 528, 320)), (2, (130, 64, 260))):
@@ -58,6 +58,15 @@ if "lu" in which:  # single exact panel, multi-panel look-ahead pipeline (fp64 a
         tol = (1e-12 if dt == np.float64 else 1e-4) * max(shape)
         assert float(np.max(np.abs(lu - ref_lu) / np.maximum(np.abs(ref_lu), 1.0))) <= tol
     print("lu ok")
+if "lu_mg" in which:  # multi-device driver with ranks sharing device 0: shifted base pointers, ring slots, peer copies
+    from la import sharding
+    for n, world in ((300, 2), (515, 3), (129, 2)):
+        a = orc.fill((n, n), 1)
+        ref_lu, ref_piv, ref_sign = orc.lu(a)
+        lu, piv, sign = sharding.lu_factor_mg(a, [0] * world)
+        assert np.array_equal(piv, ref_piv) and sign == ref_sign
+        assert float(np.max(np.abs(lu - ref_lu) / np.maximum(np.abs(ref_lu), 1.0))) <= 1e-12 * n
+    print("lu_mg ok")
 if "solve" in which:  # reference-order path (n < 512), persistent sweep kernels (nx <= 16), GEMM sweeps (many RHS)
     for n, nx in ((200, 3), (640, 16), (768, 5), (640, 64)):
         a, rhs = orc.fill((n, n), 1), orc.fill((n, nx), 3)
@@ -66,12 +75,16 @@ if "solve" in which:  # reference-order path (n < 512), persistent sweep kernels
         assert np.linalg.norm(a @ x - rhs) / (np.linalg.norm(a) * np.linalg.norm(x)) <= 1e-13
     print("solve ok")
 if "chol" in which:
-    for n in (100, 400):
+    for n in (100, 400, 644):  # 644: several block columns -> the lower-triangle-only trailing GEMM; solve with 4 RHS
         g = orc.fill((n, n), 5)
         spd = orc.gemm(g, np.ascontiguousarray(g.T)) + n * np.eye(n)
         ch = la.CholeskyDecomposition.new(la.Matrix.from_numpy(spd))
         ref_l = orc.chol(spd)
         assert float(np.max(np.abs(ch.get_l().to_numpy() - ref_l)) / np.max(np.abs(ref_l))) <= 1e-12 * n
+        if n > 512:  # triangular transpose + sweep kernels
+            rhs = orc.fill((n, 4), 3)
+            x = ch.solve(la.Matrix.from_numpy(rhs)).to_numpy()
+            assert np.linalg.norm(spd @ x - rhs) / (np.linalg.norm(spd) * np.linalg.norm(x)) <= 1e-13
     print("chol ok")
 if "qr" in which and hasattr(la, "QRDecomposition"):
     for shape in ((200, 120), (400, 400)):
