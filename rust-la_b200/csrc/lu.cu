@@ -1356,7 +1356,7 @@ template int lu_factor_dev<float>(float*, size_t, size_t, uint64_t*, int*, cudaS
 // Multi-device LU: LUDecomposition::new (lu.rs:104-168) of one n x n fp64 matrix across several
 // GPUs driven by one host thread.
 //
-// Layout: 128-column blocks dealt round-robin (block b lives on device b mod G, all n rows of it), so every device keeps
+// Layout: 128-column blocks (narrower when a 128-wide panel of n rows does not fit one GPU's shared memory) dealt round-robin (block b lives on device b mod G, all n rows of it), so every device keeps
 // a share of the trailing matrix until the end.  Panel k is factored by its owner with the single-device panel kernel;
 // the factored block column (L11 over L21), and its 128 pivot rows, are copied into a ring slot on every device (peer
 // copies queued on the owner's chain stream, the next owner first), after which each device is on its own: it folds the
@@ -1399,12 +1399,12 @@ struct DevSwitch {  // restores the caller's current device
   }
 };
 
-__global__ void lu_mg_fill_kernel(double* __restrict__ A, size_t ld, int n, int ncols, int d, int G, uint64_t seed) {
+__global__ void lu_mg_fill_kernel(double* __restrict__ A, size_t ld, int n, int ncols, int d, int G, int nb, uint64_t seed) {
   const size_t total = (size_t)n * ncols;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const size_t r = e / ncols;
     const int lc = (int)(e - r * ncols);
-    const size_t gc = ((size_t)(lc / MAX_NB) * G + d) * MAX_NB + lc % MAX_NB;
+    const size_t gc = ((size_t)(lc / nb) * G + d) * nb + lc % nb;
     A[r * ld + lc] = (double)(hash64(seed, r * (size_t)n + gc) >> 11) * 0x1.0p-53;
   }
 }
@@ -1414,6 +1414,7 @@ __global__ void lu_mg_fill_kernel(double* __restrict__ A, size_t ld, int n, int 
 struct la_lu_mg {
   int ndev = 0;
   size_t n = 0;
+  int nb = 0;    // block-column (= panel) width: 128 unless a 128-wide panel of n rows exceeds one GPU's shared memory
   int nblk = 0;
   la::LuMgDev dev[la::MGLU_MAX_DEV];
   cudaEvent_t t0 = nullptr, t1 = nullptr;  // on dev[0]: the factorisation as the devices saw it
@@ -1424,13 +1425,13 @@ namespace la {
 namespace {
 
 inline int mglu_width(const la_lu_mg* c, int b) {
-  const size_t left = c->n - (size_t)b * MAX_NB;
-  return left < (size_t)MAX_NB ? (int)left : MAX_NB;
+  const size_t left = c->n - (size_t)b * c->nb;
+  return left < (size_t)c->nb ? (int)left : c->nb;
 }
 // first local column (on device q of G) that lies right of block k
 inline int mglu_cols_through(const la_lu_mg* c, int k, int q) {
   const int blocks = k >= q ? (k - q) / c->ndev + 1 : 0;
-  const int cols = blocks * MAX_NB;
+  const int cols = blocks * c->nb;
   return cols < c->dev[q].ncols ? cols : c->dev[q].ncols;
 }
 
@@ -1475,7 +1476,26 @@ int lu_mg_destroy(la_lu_mg* c) {
 
 int lu_mg_create_impl(la_lu_mg* c, int ngpus, const int* devices, size_t n) {
   c->n = n;
-  c->nblk = (int)((n + MAX_NB - 1) / MAX_NB);
+  // panel width: as wide as the shared memory of the smallest device allows for the tallest (first) panel (cf. lu_factor_dev)
+  int min_sms = 1 << 30;
+  for (int q = 0; q < ngpus; ++q) {
+    const DeviceCtx* ctx;
+    LA_TRY(device_ctx(devices[q], &ctx));
+    if (ctx->sm_count < min_sms) min_sms = ctx->sm_count;
+  }
+  int rpc_first = (int)((n + min_sms - 1) / min_sms);
+  if (rpc_first < 8) rpc_first = 8;
+  int nb = (int)(PANEL_SMEM_BUDGET / ((size_t)rpc_first * sizeof(double))) - 1;  // rows are padded to an odd stride
+  nb = nb < 0 ? 0 : nb / 16 * 16;
+  if (nb > MAX_NB) nb = MAX_NB;
+  if (const char* e = getenv("LA_LU_MG_NB")) {  // test hook: narrower block columns on small matrices
+    const int want = atoi(e) / 16 * 16;
+    if (want >= 16 && want < nb) nb = want;
+  }
+  if (nb < 16)
+    return fail(LA_ERR_UNSUPPORTED, "la_lu_mg: %zu rows exceed the shared-memory panel capacity of %d SMs", n, min_sms);
+  c->nb = nb;
+  c->nblk = (int)((n + nb - 1) / nb);
   c->ndev = ngpus < c->nblk ? ngpus : c->nblk;  // a device without a block column has nothing to do
   const int G = c->ndev;
   for (int q = 0; q < G; ++q) {
@@ -1485,9 +1505,6 @@ int lu_mg_create_impl(la_lu_mg* c, int ngpus, const int* devices, size_t n) {
     if (!ctx->coop) return fail(LA_ERR_UNSUPPORTED, "la_lu_mg: device %d lacks cooperative launch", devices[q]);
     D.device = devices[q];
     D.sms = ctx->sm_count;
-    const int rpc = (int)((n + D.sms - 1) / D.sms);
-    if ((size_t)rpc * (MAX_NB | 1) * sizeof(double) > PANEL_SMEM_BUDGET)
-      return fail(LA_ERR_UNSUPPORTED, "la_lu_mg: %zu rows exceed the shared-memory panel capacity of %d SMs", n, D.sms);
     LA_CUDA_TRY(cudaSetDevice(D.device));
     for (int r = 0; r < G; ++r) {  // peer copies go straight over NVLink where the devices can reach each other
       if (devices[r] == D.device) continue;
@@ -1559,7 +1576,7 @@ int lu_mg_upload(la_lu_mg* c, const double* A) {
   for (int b = 0; b < c->nblk; ++b) {
     LuMgDev& D = c->dev[b % c->ndev];
     LA_CUDA_TRY(cudaSetDevice(D.device));
-    LA_CUDA_TRY(cudaMemcpy2DAsync(D.A + (size_t)(b / c->ndev) * MAX_NB, D.ld * sizeof(double), A + (size_t)b * MAX_NB,
+    LA_CUDA_TRY(cudaMemcpy2DAsync(D.A + (size_t)(b / c->ndev) * c->nb, D.ld * sizeof(double), A + (size_t)b * c->nb,
                                   n * sizeof(double), (size_t)mglu_width(c, b) * sizeof(double), n, cudaMemcpyHostToDevice,
                                   D.st));
   }
@@ -1576,7 +1593,7 @@ int lu_mg_fill_hash(la_lu_mg* c, uint64_t seed) {
   for (int q = 0; q < c->ndev; ++q) {
     LuMgDev& D = c->dev[q];
     LA_CUDA_TRY(cudaSetDevice(D.device));
-    lu_mg_fill_kernel<<<D.sms * 16, 256, 0, D.st>>>(D.A, D.ld, (int)c->n, D.ncols, q, c->ndev, seed);
+    lu_mg_fill_kernel<<<D.sms * 16, 256, 0, D.st>>>(D.A, D.ld, (int)c->n, D.ncols, q, c->ndev, c->nb, seed);
     LA_CUDA_TRY(cudaGetLastError());
   }
   return LA_OK;
@@ -1605,7 +1622,7 @@ int lu_mg_download(la_lu_mg* c, double* LU, uint64_t* piv, int* pospivsign) {
     for (int b = 0; b < c->nblk; ++b) {
       LuMgDev& D = c->dev[b % c->ndev];
       LA_CUDA_TRY(cudaSetDevice(D.device));
-      LA_CUDA_TRY(cudaMemcpy2DAsync(LU + (size_t)b * MAX_NB, n * sizeof(double), D.A + (size_t)(b / c->ndev) * MAX_NB,
+      LA_CUDA_TRY(cudaMemcpy2DAsync(LU + (size_t)b * c->nb, n * sizeof(double), D.A + (size_t)(b / c->ndev) * c->nb,
                                     D.ld * sizeof(double), (size_t)mglu_width(c, b) * sizeof(double), n,
                                     cudaMemcpyDeviceToHost, D.st));
     }
@@ -1672,12 +1689,12 @@ int lu_mg_factor(la_lu_mg* c) {
   clock_gettime(CLOCK_MONOTONIC, &ts0);
 
   for (int k = 0; k < nblk; ++k) {
-    const int j0 = k * MAX_NB, jb = mglu_width(c, k), c1 = j0 + jb;
+    const int j0 = k * c->nb, jb = mglu_width(c, k), c1 = j0 + jb;
     const int o = k % G, slot = k % MGLU_RING;
     const bool has_next = k + 1 < nblk;
     const int nb2 = has_next ? mglu_width(c, k + 1) : 0;
     const int o2 = (k + 1) % G;
-    const int lc0 = (k / G) * MAX_NB, lcn = ((k + 1) / G) * MAX_NB;
+    const int lc0 = (k / G) * c->nb, lcn = ((k + 1) / G) * c->nb;
     LuMgDev& O = c->dev[o];
     // ---- owner: the factored block column and its pivots go to every device's ring slot (the next owner first) ----
     LA_TRY(use(O));

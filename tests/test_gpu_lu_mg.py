@@ -123,3 +123,48 @@ def test_lu_mg_distinct_devices_small(oracle):
         a = oracle.fill((n, n), 1)
         lu, piv, sign = sharding.lu_factor_mg(a, [0, 1])
         _check(oracle, a, lu, piv, sign)
+
+
+@pytest.mark.parametrize("nb", [48, 80])
+@pytest.mark.parametrize("n,world", [(300, 2), (515, 3), (1000, 2)])
+def test_lu_mg_narrow_block_columns(oracle, monkeypatch, nb, n, world):
+    """Matrices taller than one GPU's shared-memory panel capacity at 128 columns get narrower block columns; LA_LU_MG_NB
+    forces that layout on small matrices (block offsets, ring slots and ragged last blocks at a width other than 128)."""
+    monkeypatch.setenv("LA_LU_MG_NB", str(nb))
+    a = oracle.fill((n, n), 11) - 0.25
+    lu, piv, sign = sharding.lu_factor_mg(a, [0] * world)
+    _check(oracle, a, lu, piv, sign)
+
+
+def test_lu_mg_32768_rows_exceed_a_128_wide_panel():
+    """n = 32768: a 128-wide panel of all rows does not fit the shared memory of 148 SMs, so the block columns are 112 wide.
+    No oracle result exists at this size; the single-device factorisation (a different schedule: grouped updates, split
+    panels) of the same matrix must give the identical pivot permutation and factors that agree to 1e-12 * n."""
+    torch = pytest.importorskip("torch")
+    import ctypes
+    from la._cabi import check, lib
+    n = 32768
+    ctx = sharding.LuMgContext([0, 0], n)
+    try:
+        ctx.fill_hash(1)
+        ctx.factor()
+        _, piv, sign = ctx.download(want_lu=False)
+        rows = np.unique(np.concatenate([[0, 1, n // 2, n - 1], np.random.default_rng(5).integers(0, n, 28)]))
+        # sampled rows of the packed factors straight from the context: download everything once (8 GiB) is avoided by
+        # factoring the same matrix on one device and comparing there
+        lu_mg, _, _ = ctx.download(want_lu=True)
+    finally:
+        ctx.destroy()
+    dev = torch.device("cuda", 0)
+    sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    A = torch.empty((n, n), dtype=torch.float64, device=dev)
+    check(lib().la_fill_hash_f64_dev(A.data_ptr(), A.numel(), 1, 0, sp))
+    pv = torch.empty((n,), dtype=torch.int64, device=dev)
+    sg = torch.empty((1,), dtype=torch.int32, device=dev)
+    check(lib().la_lu_factor_f64_dev(A.data_ptr(), n, n, pv.data_ptr(), sg.data_ptr(), sp))
+    torch.cuda.synchronize()
+    assert np.array_equal(piv.astype(np.int64), pv.cpu().numpy())
+    assert sign == bool(sg.item())
+    ref = A[torch.as_tensor(rows, device=dev)].cpu().numpy()
+    got = lu_mg[rows]
+    assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)) <= 1e-12 * n
