@@ -83,3 +83,20 @@ def test_product_never_imports_oracle():
                         if re.search(r"\boracle\b", line) and not re.search(r"//|#|\*|\"\"\"", line):
                             bad.append((f, line.strip()))
     assert not bad, bad
+
+
+def test_rust_ffi_declares_the_same_functions_as_the_header():
+    """rust-la_b200/rust/src/ffi.rs is what the crate binds; there is no Rust toolchain here to compile it,
+    so at least its `extern "C"` block must name exactly the functions la_cabi.h declares, with the same argument counts."""
+    ffi = open(os.path.join(ROOT, "rust-la_b200", "rust", "src", "ffi.rs")).read()
+    rust = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (la_\w+)\s*\(([^)]*)\)", ffi)}
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    cdecl = {m.group(1): m.group(2) for m in re.finditer(r"LA_API\s+[\w\s\*]+?\b(la_\w+)\s*\(([^)]*)\)", text)}
+    assert sorted(rust) == sorted(cdecl), sorted(set(rust) ^ set(cdecl))
+
+    def argc(args):
+        args = args.strip()
+        return 0 if args in ("", "void") else args.count(",") + 1
+
+    wrong = [name for name in cdecl if argc(cdecl[name]) != argc(rust[name])]
+    assert not wrong, f"argument count differs between la_cabi.h and ffi.rs: {wrong}"
