@@ -174,6 +174,11 @@ typedef struct la_lu_mg la_lu_mg;
 LA_API int la_lu_mg_create(int ngpus, const int* devices, size_t n, la_lu_mg** out);
 LA_API int la_lu_mg_destroy(la_lu_mg* ctx);
 LA_API int la_lu_mg_devices(const la_lu_mg* ctx, int* ndev_out); /* devices in use: min(ngpus, number of block columns) */
+/* The layout as pure arithmetic (no device needed): block-column width (128, narrower when a panel of n rows would not fit
+ * the shared memory of `sm_count` SMs), number of block columns, devices in use and the local column count of each
+ * (ncols_out[ngpus]).  Block column b lives on device b % ndev at local column (b / ndev) * width. */
+LA_API int la_lu_mg_plan(size_t n, int ngpus, int sm_count, int* block_width_out, int* nblocks_out, int* ndev_out,
+                         size_t* ncols_out);
 LA_API int la_lu_mg_upload_f64(la_lu_mg* ctx, const double* A /* host, row-major n x n */);
 LA_API int la_lu_mg_fill_hash_f64(la_lu_mg* ctx, uint64_t seed);
 LA_API int la_lu_mg_factor_f64(la_lu_mg* ctx);

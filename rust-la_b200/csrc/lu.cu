@@ -1424,6 +1424,21 @@ struct la_lu_mg {
 namespace la {
 namespace {
 
+// Width of a block column (= panel) for n rows on devices with `sms` SMs: 128 unless the tallest panel would not fit the
+// shared memory of one device (cf. lu_factor_dev); < 16 means "does not fit at all".
+int mglu_block_width(size_t n, int sms) {
+  int rpc_first = (int)((n + sms - 1) / sms);
+  if (rpc_first < 8) rpc_first = 8;
+  int nb = (int)(PANEL_SMEM_BUDGET / ((size_t)rpc_first * sizeof(double))) - 1;  // rows are padded to an odd stride
+  nb = nb < 0 ? 0 : nb / 16 * 16;
+  if (nb > MAX_NB) nb = MAX_NB;
+  if (const char* e = getenv("LA_LU_MG_NB")) {  // test hook: narrower block columns on small matrices
+    const int want = atoi(e) / 16 * 16;
+    if (want >= 16 && want < nb) nb = want;
+  }
+  return nb;
+}
+
 inline int mglu_width(const la_lu_mg* c, int b) {
   const size_t left = c->n - (size_t)b * c->nb;
   return left < (size_t)c->nb ? (int)left : c->nb;
@@ -1483,15 +1498,7 @@ int lu_mg_create_impl(la_lu_mg* c, int ngpus, const int* devices, size_t n) {
     LA_TRY(device_ctx(devices[q], &ctx));
     if (ctx->sm_count < min_sms) min_sms = ctx->sm_count;
   }
-  int rpc_first = (int)((n + min_sms - 1) / min_sms);
-  if (rpc_first < 8) rpc_first = 8;
-  int nb = (int)(PANEL_SMEM_BUDGET / ((size_t)rpc_first * sizeof(double))) - 1;  // rows are padded to an odd stride
-  nb = nb < 0 ? 0 : nb / 16 * 16;
-  if (nb > MAX_NB) nb = MAX_NB;
-  if (const char* e = getenv("LA_LU_MG_NB")) {  // test hook: narrower block columns on small matrices
-    const int want = atoi(e) / 16 * 16;
-    if (want >= 16 && want < nb) nb = want;
-  }
+  const int nb = mglu_block_width(n, min_sms);
   if (nb < 16)
     return fail(LA_ERR_UNSUPPORTED, "la_lu_mg: %zu rows exceed the shared-memory panel capacity of %d SMs", n, min_sms);
   c->nb = nb;
@@ -1820,6 +1827,29 @@ int la_lu_mg_last_ms(la_lu_mg* ctx, float* ms_out) {
   if (s != LA_OK) return s;
   if (ctx->last_ms < 0.f) return la::fail(LA_ERR_INVALID, "la_lu_mg_last_ms: no factorisation has run in this context");
   *ms_out = ctx->last_ms;
+  return LA_OK;
+}
+// The layout as pure arithmetic (no device needed): block width, number of block columns, devices in use, and the number
+// of local columns of every device in use (ncols_out[ngpus]; unused entries are 0).  Block b lives on device b % ndev.
+int la_lu_mg_plan(size_t n, int ngpus, int sm_count, int* block_width_out, int* nblocks_out, int* ndev_out,
+                  size_t* ncols_out) {
+  if (!block_width_out || !nblocks_out || !ndev_out || !ncols_out)
+    return la::fail(LA_ERR_INVALID, "la_lu_mg_plan: null output");
+  if (n == 0 || n >= (1u << 30) || ngpus < 1 || ngpus > la::MGLU_MAX_DEV || sm_count < 1)
+    return la::fail(LA_ERR_INVALID, "la_lu_mg_plan: bad arguments (n=%zu ngpus=%d sm_count=%d)", n, ngpus, sm_count);
+  const int nb = la::mglu_block_width(n, sm_count);
+  if (nb < 16)
+    return la::fail(LA_ERR_UNSUPPORTED, "la_lu_mg: %zu rows exceed the shared-memory panel capacity of %d SMs", n, sm_count);
+  const int nblk = (int)((n + nb - 1) / nb);
+  const int ndev = ngpus < nblk ? ngpus : nblk;
+  for (int q = 0; q < ngpus; ++q) ncols_out[q] = 0;
+  for (int b = 0; b < nblk; ++b) {
+    const size_t left = n - (size_t)b * nb;
+    ncols_out[b % ndev] += left < (size_t)nb ? left : (size_t)nb;
+  }
+  *block_width_out = nb;
+  *nblocks_out = nblk;
+  *ndev_out = ndev;
   return LA_OK;
 }
 int la_lu_mg_devices(const la_lu_mg* ctx, int* ndev_out) {

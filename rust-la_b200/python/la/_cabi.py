@@ -75,6 +75,7 @@ SIGNATURES = {
     "la_lu_mg_create": ([_i, _p, _sz, _p], _i),
     "la_lu_mg_destroy": ([_p], _i),
     "la_lu_mg_devices": ([_p, _pi], _i),
+    "la_lu_mg_plan": ([_sz, _i, _i, _pi, _pi, _pi, _psz], _i),
     "la_lu_mg_upload_f64": ([_p, _p], _i),
     "la_lu_mg_fill_hash_f64": ([_p, ctypes.c_uint64], _i),
     "la_lu_mg_factor_f64": ([_p], _i),

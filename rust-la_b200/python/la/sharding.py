@@ -124,6 +124,15 @@ def gemm_mg(a, b, devices):
     return c
 
 
+def lu_mg_plan(n, ngpus, sm_count=148):
+    """(block width, number of block columns, devices in use, [local columns per device]) of the multi-device LU layout
+    (la_lu_mg_plan: pure arithmetic inside the C library, no device needed)."""
+    nb, nblk, ndev = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    ncols = (ctypes.c_size_t * ngpus)()
+    check(lib().la_lu_mg_plan(n, ngpus, sm_count, ctypes.byref(nb), ctypes.byref(nblk), ctypes.byref(ndev), ncols))
+    return nb.value, nblk.value, ndev.value, [int(x) for x in ncols]
+
+
 class LuMgContext:
     """LU of one n x n fp64 matrix across several devices driven by this thread (la_lu_mg_*, include/la_cabi.h): 128-column
     blocks dealt round-robin, the owner's factored block column copied to every device, no collective."""

@@ -133,6 +133,7 @@ extern "C" {
     pub fn la_lu_mg_factor_f64(ctx: *mut la_lu_mg) -> c_int;
     pub fn la_lu_mg_fill_hash_f64(ctx: *mut la_lu_mg, seed: u64) -> c_int;
     pub fn la_lu_mg_last_ms(ctx: *mut la_lu_mg, ms_out: *mut f32) -> c_int;
+    pub fn la_lu_mg_plan(n: usize, ngpus: c_int, sm_count: c_int, block_width_out: *mut c_int, nblocks_out: *mut c_int, ndev_out: *mut c_int, ncols_out: *mut usize) -> c_int;
     pub fn la_lu_mg_sync(ctx: *mut la_lu_mg) -> c_int;
     pub fn la_lu_mg_upload_f64(ctx: *mut la_lu_mg, a: *const f64) -> c_int;
     pub fn la_mg_b_block(ctx: *const la_mg, block_dev: *mut *mut c_void, ldb: *mut usize, col0: *mut usize, col1: *mut usize) -> c_int;
