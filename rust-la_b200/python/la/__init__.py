@@ -213,6 +213,23 @@ class LUDecomposition:
         check(getattr(lib(), f"la_lu_factor_{suf}")(buf.handle, m, n, _ptr(piv), ctypes.byref(sign)))
         return LUDecomposition(m, n, a.data.dtype, buf, piv, sign.value)
 
+    @staticmethod
+    def new_on_devices(a, devices):
+        """The same factorisation spread over several GPUs (la_lu_factor_f64_mg): 128-column blocks dealt
+        round-robin, the panel owner's block column copied to every device.  fp64, square.  The packed factors land on
+        devices[0], so solve / det / get_l work as after `new`."""
+        _assert(a.rows() == a.cols(), "new_on_devices: the matrix must be square")
+        _assert(a.data.dtype == np.float64, "new_on_devices: fp64 only")
+        _assert(len(devices) > 0, "new_on_devices: empty device list")
+        from . import sharding
+        n = a.rows()
+        lu, piv, sign = sharding.lu_factor_mg(a.data.reshape(n, n), list(devices))
+        buf = _DeviceBuf(lu.nbytes, devices[0])
+        buf.upload(lu.reshape(-1))
+        dec = LUDecomposition(n, n, np.float64, buf, piv, sign)
+        dec._lu_host = Matrix(n, lu.reshape(-1))
+        return dec
+
     def get_lu(self):
         if self._lu_host is None:
             h = np.empty(self._m * self._n, dtype=self._dtype)

@@ -168,3 +168,20 @@ def test_lu_mg_32768_rows_exceed_a_128_wide_panel():
     ref = A[torch.as_tensor(rows, device=dev)].cpu().numpy()
     got = lu_mg[rows]
     assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)) <= 1e-12 * n
+
+
+def test_python_mirror_new_on_devices_solves_like_new(oracle):
+    """LUDecomposition.new_on_devices (the mirror of the Rust / C++ constructors over a device list): same pivots as `new`,
+    and solve / det on the returned object work from the factors it placed on devices[0]."""
+    from la import LUDecomposition, Matrix
+    n = 700
+    a = oracle.fill((n, n), 21) - 0.5
+    b = oracle.fill((n, 3), 22)
+    one = LUDecomposition.new(Matrix.from_numpy(a))
+    many = LUDecomposition.new_on_devices(Matrix.from_numpy(a), [0, 0, 0])
+    assert np.array_equal(one.piv, many.piv) and one.pospivsign == many.pospivsign
+    assert np.max(np.abs(one.get_lu().to_numpy() - many.get_lu().to_numpy())) <= 1e-12 * n
+    x = many.solve(Matrix.from_numpy(b)).to_numpy()
+    assert np.linalg.norm(a @ x - b) / (np.linalg.norm(a) * np.linalg.norm(x)) <= 1e-13
+    d1, d2 = one.det(), many.det()
+    assert d1 == d2 or abs(d1 - d2) <= 1e-9 * abs(d1)
