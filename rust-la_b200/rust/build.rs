@@ -8,7 +8,8 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let cuda = env::var("CUDA_HOME").unwrap_or_else(|_| "/usr/local/cuda".to_string());
     let nvcc = format!("{}/bin/nvcc", cuda);
-    let srcs = ["la_runtime", "gemm_f64", "gemm_f32", "gemm_simt", "lu", "lu_solve", "cholesky", "capi"];
+    let srcs = ["la_runtime", "gemm_f64", "gemm_f32", "gemm_simt", "lu", "lu_solve", "cholesky", "qr", "elementwise", "mg",
+                "capi"];
     let mut objs = Vec::new();
     for s in srcs.iter() {
         let src = format!("../csrc/{}.cu", s);
@@ -24,6 +25,7 @@ fn main() {
         objs.push(obj);
     }
     println!("cargo:rerun-if-changed=../csrc/la_common.cuh");
+    println!("cargo:rerun-if-changed=../csrc/ll_exchange.cuh");
     println!("cargo:rerun-if-changed=../../include/la_cabi.h");
     let lib = out.join("libla_b200.a");
     let st = Command::new("ar").arg("crs").arg(&lib).args(&objs).status().expect("ar");
@@ -33,4 +35,5 @@ fn main() {
     println!("cargo:rustc-link-lib=static=la_b200");
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=stdc++");
+    println!("cargo:rustc-link-lib=dylib=pthread");
 }

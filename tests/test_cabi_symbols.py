@@ -100,3 +100,16 @@ def test_rust_ffi_declares_the_same_functions_as_the_header():
 
     wrong = [name for name in cdecl if argc(cdecl[name]) != argc(rust[name])]
     assert not wrong, f"argument count differs between la_cabi.h and ffi.rs: {wrong}"
+
+
+def test_rust_build_script_compiles_the_same_sources_as_the_makefile():
+    """build.rs is what a maintainer's `cargo build` runs; the Makefile is what this repository's tests run.  Both must
+    compile the same translation units, or the crate would link against missing symbols."""
+    mk = open(os.path.join(ROOT, "rust-la_b200", "Makefile")).read()
+    m = re.search(r"^SRCS\s*[:+]?=\s*(.*)$", mk, flags=re.M)
+    assert m, "SRCS line not found in the Makefile"
+    make_srcs = sorted(os.path.splitext(os.path.basename(w))[0] for w in m.group(1).split() if w.endswith(".cu"))
+    rs = open(os.path.join(ROOT, "rust-la_b200", "rust", "build.rs")).read()
+    block = re.search(r"let srcs = \[(.*?)\];", rs, flags=re.S).group(1)
+    rust_srcs = sorted(re.findall(r'"(\w+)"', block))
+    assert rust_srcs == make_srcs, (rust_srcs, make_srcs)
