@@ -18,5 +18,5 @@ mod qr;
 pub use approxeq::ApproxEq;
 pub use cholesky::{CholScalar, CholeskyDecomposition};
 pub use lu::LUDecomposition;
-pub use matrix::{DeviceScalar, Matrix};
+pub use matrix::{devices, set_devices, DeviceScalar, Matrix};
 pub use qr::{QRDecomposition, QrScalar};

@@ -6,8 +6,22 @@
 //! element types the CUDA library has a kernel for.  This NARROWS the bound of `Mul`; there is no CPU loop left.
 use std::ops::Mul;
 use std::os::raw::c_int;
+use std::sync::Mutex;
 
 use crate::ffi;
+
+/// Devices the products are spread over.  Empty or one entry: the single-device entry points.
+static DEVICES: Mutex<Vec<c_int>> = Mutex::new(Vec::new());
+
+/// Configure the device list used by `Mul` / `mmul` (and available to `LUDecomposition::new_on_devices`): with more than
+/// one device the rows of A and C are sharded and the column blocks of B travel over NVLink inside the library
+/// (`la_gemm_f64_mg` / `la_gemm_f32_mg`).
+pub fn set_devices(devices: &[c_int]) {
+    let mut d = DEVICES.lock().unwrap();
+    d.clear();
+    d.extend_from_slice(devices);
+}
+pub fn devices() -> Vec<c_int> { DEVICES.lock().unwrap().clone() }
 
 mod sealed {
     pub trait Sealed {}
@@ -19,15 +33,31 @@ mod sealed {
 /// Element types with a CUDA GEMM kernel behind the C ABI.
 pub trait DeviceScalar: Copy + PartialEq + sealed::Sealed {
     unsafe fn gemm_host(a: *const Self, b: *const Self, c: *mut Self, m: usize, k: usize, n: usize) -> c_int;
+    /// Product over several devices; the default (element types without a multi-device kernel) runs on one.
+    unsafe fn gemm_mg(_devices: &[c_int], a: *const Self, b: *const Self, c: *mut Self, m: usize, k: usize, n: usize)
+                      -> c_int {
+        Self::gemm_host(a, b, c, m, k, n)
+    }
+    /// Dispatch on the configured device list.
+    unsafe fn gemm(a: *const Self, b: *const Self, c: *mut Self, m: usize, k: usize, n: usize) -> c_int {
+        let devs = devices();
+        if devs.len() > 1 { Self::gemm_mg(&devs, a, b, c, m, k, n) } else { Self::gemm_host(a, b, c, m, k, n) }
+    }
 }
 impl DeviceScalar for f64 {
     unsafe fn gemm_host(a: *const f64, b: *const f64, c: *mut f64, m: usize, k: usize, n: usize) -> c_int {
         ffi::la_gemm_f64_host(a, b, c, m, k, n)
     }
+    unsafe fn gemm_mg(devices: &[c_int], a: *const f64, b: *const f64, c: *mut f64, m: usize, k: usize, n: usize) -> c_int {
+        ffi::la_gemm_f64_mg(devices.len() as c_int, devices.as_ptr(), a, b, c, m, k, n)
+    }
 }
 impl DeviceScalar for f32 {
     unsafe fn gemm_host(a: *const f32, b: *const f32, c: *mut f32, m: usize, k: usize, n: usize) -> c_int {
         ffi::la_gemm_f32_host(a, b, c, m, k, n)
+    }
+    unsafe fn gemm_mg(devices: &[c_int], a: *const f32, b: *const f32, c: *mut f32, m: usize, k: usize, n: usize) -> c_int {
+        ffi::la_gemm_f32_mg(devices.len() as c_int, devices.as_ptr(), a, b, c, m, k, n)
     }
 }
 impl DeviceScalar for i64 {
@@ -78,7 +108,7 @@ impl<T: DeviceScalar> Matrix<T> {
         assert!(dst.rows() == self.no_rows);
         assert!(dst.cols() == m.cols());
         ffi::check(unsafe {
-            T::gemm_host(self.data.as_ptr(), m.data.as_ptr(), dst.data.as_mut_ptr(), self.no_rows, self.cols(), m.cols())
+            T::gemm(self.data.as_ptr(), m.data.as_ptr(), dst.data.as_mut_ptr(), self.no_rows, self.cols(), m.cols())
         });
         dst
     }
@@ -92,7 +122,7 @@ impl<'a, 'b, T: DeviceScalar> Mul<&'a Matrix<T>> for &'b Matrix<T> {
         let elems = self.no_rows * m.cols();
         let mut d = Matrix::<T>::dirty_vec(elems);
         ffi::check(unsafe {
-            T::gemm_host(self.data.as_ptr(), m.data.as_ptr(), d.as_mut_ptr(), self.no_rows, self.cols(), m.cols())
+            T::gemm(self.data.as_ptr(), m.data.as_ptr(), d.as_mut_ptr(), self.no_rows, self.cols(), m.cols())
         });
         Matrix { no_rows: self.no_rows, data: d }
     }
