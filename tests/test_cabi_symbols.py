@@ -67,6 +67,14 @@ def test_no_cpu_fallback_without_device():
     import la
     with pytest.raises(la.LaError):
         la.m("1.0, 2.0; 3.0, 4.0") * la.m("1.0, 0.0; 0.0, 1.0")
+    # the multi-device entry points too: no device list can be honoured, and nothing is computed on the host
+    devs = (ctypes.c_int * 2)(0, 1)
+    st = L.la_lu_factor_f64_mg(2, devs, a.ctypes.data, c.ctypes.data, 2, piv.ctypes.data, ctypes.byref(sign))
+    assert st == _cabi.LA_ERR_NO_DEVICE and np.all(c == 0)
+    ctx = ctypes.c_void_p()
+    assert L.la_lu_mg_create(2, devs, 256, ctypes.byref(ctx)) == _cabi.LA_ERR_NO_DEVICE and not ctx.value
+    st = L.la_gemm_f64_mg(2, devs, a.ctypes.data, a.ctypes.data, c.ctypes.data, 2, 2, 2)
+    assert st == _cabi.LA_ERR_NO_DEVICE and np.all(c == 0)
 
 
 def test_product_never_imports_oracle():
