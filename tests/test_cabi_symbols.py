@@ -121,3 +121,26 @@ def test_rust_build_script_compiles_the_same_sources_as_the_makefile():
     block = re.search(r"let srcs = \[(.*?)\];", rs, flags=re.S).group(1)
     rust_srcs = sorted(re.findall(r'"(\w+)"', block))
     assert rust_srcs == make_srcs, (rust_srcs, make_srcs)
+
+
+def test_rust_sources_are_at_least_balanced():
+    """No Rust toolchain exists in the image, so the mirror cannot be compiled here; this catches the cheapest class of slip
+    (unbalanced delimiters after an edit) in rust/src/*.rs and build.rs.  Comments, strings and char literals are skipped."""
+    rust_dir = os.path.join(ROOT, "rust-la_b200", "rust")
+    files = [os.path.join(rust_dir, "build.rs")] + [os.path.join(rust_dir, "src", f)
+                                                     for f in sorted(os.listdir(os.path.join(rust_dir, "src")))]
+    pairs = {")": "(", "]": "[", "}": "{"}
+    for path in files:
+        text = open(path).read()
+        text = re.sub(r"//[^\n]*", "", text)
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        text = re.sub(r'"(?:\\.|[^"\\])*"', '""', text)
+        text = re.sub(r"'(?:\\.|[^'\\])'", "' '", text)
+        stack = []
+        for ch in text:
+            if ch in "([{":
+                stack.append(ch)
+            elif ch in pairs:
+                assert stack and stack[-1] == pairs[ch], f"{path}: unbalanced '{ch}'"
+                stack.pop()
+        assert not stack, f"{path}: unclosed {stack[-3:]}"
